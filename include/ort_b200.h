@@ -1,0 +1,191 @@
+/*
+ * ort_b200.h -- C ABI of libort_b200.so: the B200 (sm_100a) implementation of the data-parallel
+ * hot path of Sagnac/OpticalRayTracing.jl.
+ *
+ * The reference is pure Julia and has NO FFI/plugin interface; its "boundary" is multiple
+ * dispatch on exported generics.  Each entry point below replaces the body of one reference
+ * method and is what a Julia `ccall` shim binds (julia/OpticalRayTracingB200.jl).
+ * All citations are file:line relative to the reference repository root.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, Float64 everywhere (Julia Vector{Float64} memory).
+ *   - Return 0 (ORT_OK) or a negative ORT_E* code; message via ort_last_error().  Nothing
+ *     throws or longjmps across the ABI.  Per-ray geometric failures are DATA: NaN positions
+ *     exactly where the reference yields NaN, plus ORT_FLAG_* bits.
+ *   - Host-pointer entry points are synchronous (outputs valid on return).  *_dev entry points
+ *     take DEVICE pointers and a cudaStream_t (as void*), enqueue only, and never synchronise.
+ *   - The caller owns every array it passes; the library owns the context, its stream, scratch.
+ *   - One ort_ctx per (process, GPU); a context is not re-entrant; distinct contexts are independent.
+ *   - There is no CPU fallback: ort_init fails with ORT_ECUDA when no sm_100 device is usable.
+ */
+#ifndef ORT_B200_H
+#define ORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ORT_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define ORT_OK            0
+#define ORT_EINVAL       (-1)
+#define ORT_ECUDA        (-2)
+#define ORT_ENCCL        (-3)
+#define ORT_EUNSUPPORTED (-4)
+#define ORT_ENOMEM       (-5)
+
+/* limits */
+#define ORT_MAX_ROWS   64   /* prescription rows incl. object space and the appended image plane */
+#define ORT_MAX_FIELDS 32   /* fields per ort_trace3d_grid call */
+#define ORT_MAX_LENS  128   /* rows of a paraxial Lens matrix */
+
+/* per-ray flag bits */
+#define ORT_FLAG_MISS   1u  /* conic discriminant < 0: position NaN from here on (PupilSampling.jl:9, RayTracing.jl:83) */
+#define ORT_FLAG_TIR    2u  /* total internal reflection: 3-D tracer continues UNDEVIATED (PupilSampling.jl:27-30,58); 2-D tracer sets U = NaN (RayTracing.jl:164) */
+#define ORT_FLAG_DOMAIN 4u  /* Julia would have thrown DomainError (sqrt/asin of an out-of-range real) */
+#define ORT_FLAG_CLIP   8u  /* r_stop > a_stop (PupilSampling.jl:131-132) */
+
+/* arithmetic modes */
+#define ORT_ARITH_STRICT 0  /* reference operation order, no FMA, IEEE div/sqrt: bit-identical to the CPU restatement */
+#define ORT_ARITH_FAST   1  /* direction-cosine reformulation with FMA and Newton div/sqrt (<= 1e-12 rel.);
+                               every discrete decision (miss / TIR / stop clip) that falls inside a guard band is
+                               re-traced in strict arithmetic, so mask and flags stay bit-identical */
+
+typedef struct ort_ctx ort_ctx;
+
+/* One field point of a pupil-grid sweep (src/PupilSampling.jl:94-109,124-127). */
+typedef struct ort_field {
+    int32_t mode;     /* 0: System, collimated -- slopes (u, v) below are used as given (u = tan(U), the
+                            caller applies tan once, :97).  1: RayBasis, finite object -- per ray
+                            U = (ybar - y)/z0, V = -x/z0 then u = tan(U), v = tan(V) (:124-127, :38-39) */
+    int32_t reserved;
+    double  u, v;     /* mode 0 */
+    double  ybar, z0; /* mode 1 */
+    double  h_prime;  /* subtracted from the final y (:134) */
+} ort_field;
+
+typedef struct ort_opts {
+    int32_t arith;    /* ORT_ARITH_* */
+    int32_t compact;  /* 0: full-grid arrays (ny*nx per field, y outer / x inner) + mask.
+                         1: ex, ey, r, theta (and wx, wy) are compacted per field in the reference's push!
+                            order (PupilSampling.jl:134-137); field f's segment still starts at f*ny*nx and
+                            holds stats[f].n_kept entries. */
+    double  wg_nu;    /* wavegrad (PupilSampling.jl:165-167): wx = ex*wg_nu/wg_lambda.  Used iff wx/wy given. */
+    double  wg_lambda;
+} ort_opts;
+
+/* Per-field spot statistics over KEPT rays of the traced half pupil (unmirrored); the host applies
+ * the mirror algebra of PupilSampling.jl:139-146,169-173.  Merge-able across GPUs (Chan). */
+typedef struct ort_stats {
+    int64_t n_kept;
+    double  mean_x, mean_y;   /* centroid of (ex, ey) */
+    double  m2_x, m2_y;       /* sum of squared deviations about the centroid */
+    double  r_max;            /* maximum(r) (:142) */
+    int64_t n_miss, n_tir, n_domain, n_clip;   /* rays carrying each flag */
+} ort_stats;
+
+/* Output arrays of a grid sweep; any pointer may be NULL (= not wanted). */
+typedef struct ort_grid_out {
+    double    *ex, *ey;       /* transverse ray errors: xf, yf - h'                       (:134-135) */
+    double    *r, *theta;     /* hypot / atan at the stop surface                         (:131,133,136-137) */
+    double    *wx, *wy;       /* wavegrad of ex, ey                                       (:165-167) */
+    uint8_t   *mask;          /* 1 = kept (always full grid, never compacted)             (:132) */
+    uint8_t   *flags;         /* ORT_FLAG_* (always full grid) */
+    ort_stats *stats;         /* [n_fields] */
+} ort_grid_out;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int         ort_version(void);
+int         ort_init(ort_ctx **out, int device);           /* device = CUDA ordinal (LOCAL_RANK) */
+void        ort_free(ort_ctx *ctx);
+const char *ort_last_error(ort_ctx *ctx);                  /* ctx may be NULL (error of a failed ort_init) */
+int         ort_sync(ort_ctx *ctx);
+int         ort_device_info(ort_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                            char *name, int name_len);
+void       *ort_host_alloc(size_t bytes);                  /* pinned host memory for fast D2H/H2D */
+void        ort_host_free(void *p);
+int64_t     ort_launch_count(ort_ctx *ctx);                /* kernels launched by this context so far */
+
+/* Prescription = the data contract of Layout (src/Types.jl:82-95): rows x [R t n K], row 1 = object
+ * space.  K may be NULL (zeros, Layout{Spherical}).  Aspheric polynomial terms `p` are Julia closures
+ * and cannot cross a C ABI: the shim must reject p != zero.  For full_trace pass the EXTENDED
+ * surfaces (image plane appended, t[end-1] = focus; src/PupilSampling.jl:111-114). */
+int ort_set_layout(ort_ctx *ctx, int rows, const double *R, const double *t, const double *n,
+                   const double *K);
+
+/* ---- 3-D skew real-ray trace over a pupil grid: replaces the hot loop of full_trace,
+ *      src/PupilSampling.jl:115-138 (per-ray body = raytrace(...,Vector{RealRay}) :34-65) plus the
+ *      statistics inputs of :139-146,169-173.  ys[ny] = collect(range(y1,y2,k)), xs[nx] =
+ *      collect(range(0,y_EP,k/2)) (:121-122).  stop = system.stop (1-based), a_stop = |a[stop]|. */
+int ort_trace3d_grid(ort_ctx *ctx, const ort_field *fields, int n_fields,
+                     const double *ys, int ny, const double *xs, int nx,
+                     int stop, double a_stop, const ort_opts *opts, ort_grid_out *out);
+int ort_trace3d_grid_dev(ort_ctx *ctx, const ort_field *fields /* host */, int n_fields,
+                         const double *d_ys, int ny, const double *d_xs, int nx,
+                         int stop, double a_stop, const ort_opts *opts,
+                         const ort_grid_out *d_out /* device pointers inside */, void *stream);
+
+/* ---- 3-D skew trace of N arbitrary rays, all surfaces recorded: replaces
+ *      raytrace(surfaces, y, x, U, V, Vector{RealRay}) src/PupilSampling.jl:34-65 for a batch.
+ *      u0, v0 are SLOPES tan(U), tan(V).  xv, yv: [(rows-1)][N] (ray index fastest);
+ *      kout: [3][N] final direction cosines (k[1], k[2], k[3] of :40); any output may be NULL. */
+int ort_trace3d_rays(ort_ctx *ctx, int64_t N, const double *y0, const double *x0,
+                     const double *u0, const double *v0, int arith,
+                     double *xv, double *yv, double *kout, uint8_t *flags);
+
+/* ---- 2-D meridional real-ray trace of N rays: replaces raytrace(surfaces, y, U, RealRay)
+ *      src/RayTracing.jl:145-173.  aspheric = 1 is the Layout{Aspheric} method (:171-173: K from the
+ *      layout, atan(tilt) branch); 0 the AbstractMatrix method (K = 0, asin(y/R) branch, :162).
+ *      y_out, U_out, ts_out: [rows][N]; any may be NULL. */
+int ort_trace2d_batch(ort_ctx *ctx, int64_t N, const double *y0, const double *U0, int aspheric,
+                      double *y_out, double *U_out, double *ts_out, uint8_t *flags);
+
+/* ---- paraxial y-nu trace of N rays through a k-row Lens [tau phi]: replaces
+ *      raytrace(lens, y, w, a; clip) src/RayTracing.jl:127-143 (+ :55-69).  a may be NULL (no clip).
+ *      y, w: final (y, nu) per ray (NaN if clipped); clip_idx: 1-based row where clipped, 0 if not;
+ *      y_all, w_all: optional full tables [(k+1)][N] (the reference's rt). */
+int ort_paraxial_batch(ort_ctx *ctx, int k, const double *tau, const double *phi, const double *a,
+                       int clip, int arith, int64_t N, const double *y0, const double *w0,
+                       double *y, double *w, int32_t *clip_idx, double *y_all, double *w_all);
+int ort_paraxial_batch_dev(ort_ctx *ctx, int k, const double *tau, const double *phi,
+                           const double *a, int clip, int arith, int64_t N,
+                           const double *d_y0, const double *d_w0, double *d_y, double *d_w,
+                           int32_t *d_clip_idx, double *d_y_all, double *d_w_all, void *stream);
+
+/* ---- transfer-matrix apply to N rays: replaces transfer(M, v, tau, taup) and
+ *      reverse_transfer(M, v, taup, tau), src/TransferMatrix.jl:8-17.  M: 2x2 column-major
+ *      (Julia memory order).  v_in / v_out: 2 x N column-major = interleaved [y nu] pairs. */
+int ort_transfer_batch(ort_ctx *ctx, const double M[4], double tau, double taup, int reverse,
+                       int64_t N, const double *v_in, double *v_out);
+int ort_transfer_batch_dev(ort_ctx *ctx, const double M[4], double tau, double taup, int reverse,
+                           int64_t N, const double *d_v_in, double *d_v_out, void *stream);
+
+/* ---- candidate-batched 3-D trace (BASELINE config 5; a synthetic batch of PupilSampling.jl:34-65,
+ *      115-138 with no reference counterpart): C prescriptions RtnK[C][4][rows], one shared entrance
+ *      grid ys x xs and one collimated field.  out[C][4] = n_kept, mean_x, mean_y, RMS about centroid. */
+int ort_trace3d_candidates(ort_ctx *ctx, int rows, int64_t C, const double *RtnK,
+                           const ort_field *field, const double *ys, int ny, const double *xs,
+                           int nx, int stop, double a_stop, int arith, double *out);
+int ort_trace3d_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK,
+                               const ort_field *field, const double *d_ys, int ny,
+                               const double *d_xs, int nx, int stop, double a_stop, int arith,
+                               double *d_out, void *stream);
+
+/* ---- measurement helper: register-resident DFMA-chain microbenchmark; the FP64 roofline
+ *      denominator (MEASURED_PEAKS.json holds no FP64 figure).  Returns TFLOP/s (2 flop per DFMA). */
+int ort_fp64_peak(ort_ctx *ctx, double *tflops, double *ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORT_B200_H */

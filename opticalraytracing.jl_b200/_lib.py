@@ -1,0 +1,342 @@
+"""ctypes binding of libort_b200.so (include/ort_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no sm_100 GPU is usable, every
+compute entry point raises.  Nothing in this package imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("ORT_B200_LIB", os.path.join(_HERE, "lib", "libort_b200.so"))
+
+ORT_OK, ORT_EINVAL, ORT_ECUDA, ORT_ENCCL, ORT_EUNSUPPORTED, ORT_ENOMEM = 0, -1, -2, -3, -4, -5
+MAX_ROWS, MAX_FIELDS, MAX_LENS = 64, 32, 128
+FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP = 1, 2, 4, 8
+STRICT, FAST = 0, 1
+
+# every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
+    "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_set_layout",
+    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace2d_batch",
+    "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
+    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_fp64_peak",
+]
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+
+class OrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libort_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Field(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("u", C.c_double), ("v", C.c_double),
+                ("ybar", C.c_double), ("z0", C.c_double), ("h_prime", C.c_double)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("arith", C.c_int32), ("compact", C.c_int32), ("wg_nu", C.c_double),
+                ("wg_lambda", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_kept", C.c_int64), ("mean_x", C.c_double), ("mean_y", C.c_double),
+                ("m2_x", C.c_double), ("m2_y", C.c_double), ("r_max", C.c_double),
+                ("n_miss", C.c_int64), ("n_tir", C.c_int64), ("n_domain", C.c_int64),
+                ("n_clip", C.c_int64)]
+
+
+STATS_DTYPE = np.dtype([("n_kept", "<i8"), ("mean_x", "<f8"), ("mean_y", "<f8"), ("m2_x", "<f8"),
+                        ("m2_y", "<f8"), ("r_max", "<f8"), ("n_miss", "<i8"), ("n_tir", "<i8"),
+                        ("n_domain", "<i8"), ("n_clip", "<i8")])
+assert STATS_DTYPE.itemsize == C.sizeof(Stats) == 80
+
+
+class GridOut(C.Structure):
+    _fields_ = [("ex", C.c_void_p), ("ey", C.c_void_p), ("r", C.c_void_p), ("theta", C.c_void_p),
+                ("wx", C.c_void_p), ("wy", C.c_void_p), ("mask", C.c_void_p), ("flags", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load libort_b200.so (no GPU needed to load; compute calls need one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrtError(ORT_ECUDA, f"{LIB_PATH} not found: build it with `python -c 'import "
+                       "__graft_entry__ as g; g.build()'` (make -C opticalraytracing.jl_b200/csrc). "
+                       "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.ort_version.restype = C.c_int
+    L.ort_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.ort_free.argtypes = [C.c_void_p]
+    L.ort_free.restype = None
+    L.ort_last_error.argtypes = [C.c_void_p]
+    L.ort_last_error.restype = C.c_char_p
+    L.ort_sync.argtypes = [C.c_void_p]
+    L.ort_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.ort_host_alloc.argtypes = [C.c_size_t]
+    L.ort_host_alloc.restype = C.c_void_p
+    L.ort_host_free.argtypes = [C.c_void_p]
+    L.ort_host_free.restype = None
+    L.ort_launch_count.argtypes = [C.c_void_p]
+    L.ort_launch_count.restype = C.c_int64
+    L.ort_set_layout.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
+    grid_args = [C.c_void_p, C.POINTER(Field), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                 C.c_int, C.c_double, C.POINTER(Opts), C.POINTER(GridOut)]
+    L.ort_trace3d_grid.argtypes = grid_args
+    L.ort_trace3d_grid_dev.argtypes = grid_args + [C.c_void_p]
+    L.ort_trace3d_rays.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
+    L.ort_trace2d_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
+    L.ort_paraxial_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
+                                     _dp, _dp, _dp, _dp, _i32p, _dp, _dp]
+    L.ort_paraxial_batch_dev.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_transfer_batch.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_int, C.c_int64, _dp, _dp]
+    L.ort_transfer_batch_dev.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_trace3d_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, C.POINTER(Field), _dp,
+                                         C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp]
+    L.ort_trace3d_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.POINTER(Field),
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.ort_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+    _lib = L
+    return L
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (ort_host_alloc).  Keep the object alive while used."""
+
+    def __init__(self, shape, dtype=np.float64):
+        L = load()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = L.ort_host_alloc(max(self.nbytes, 8))
+        if not self.ptr:
+            raise OrtError(ORT_ENOMEM, f"ort_host_alloc({self.nbytes}) failed")
+        buf = (C.c_uint8 * max(self.nbytes, 8)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().ort_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_fields(fields):
+    """fields: iterable of dicts / Field -> (ctypes array, n)"""
+    fl = list(fields)
+    arr = (Field * len(fl))()
+    for i, f in enumerate(fl):
+        if isinstance(f, Field):
+            arr[i] = f
+        else:
+            arr[i] = Field(int(f.get("mode", 0)), 0, float(f.get("u", 0.0)), float(f.get("v", 0.0)),
+                           float(f.get("ybar", 0.0)), float(f.get("z0", 1.0)), float(f.get("h_prime", 0.0)))
+    return arr, len(fl)
+
+
+class Context:
+    """One ort_ctx (one GPU).  Thin, typed wrapper over the C ABI; numpy arrays in and out."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.ort_init(C.byref(h), int(device))
+        if rc != ORT_OK:
+            raise OrtError(rc, self.L.ort_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self.rows = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ort_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != ORT_OK:
+            raise OrtError(rc, self.L.ort_last_error(self.h).decode())
+
+    # ---- context -------------------------------------------------------------------------
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        self._ck(self.L.ort_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), name, 128))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def sync(self):
+        self._ck(self.L.ort_sync(self.h))
+
+    def launch_count(self):
+        return int(self.L.ort_launch_count(self.h))
+
+    def fp64_peak(self):
+        t, ms = C.c_double(), C.c_double()
+        self._ck(self.L.ort_fp64_peak(self.h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    def set_layout(self, surfaces, K=None):
+        """surfaces: rows x 3 [R t n] (or rows x 4 with K); row 1 = object space."""
+        S = np.asarray(surfaces, dtype=np.float64)
+        if K is None and S.shape[1] > 3:
+            K = S[:, 3]
+        R, t, n = _d(S[:, 0]), _d(S[:, 1]), _d(S[:, 2])
+        Kc = None if K is None else _d(K)
+        self._ck(self.L.ort_set_layout(self.h, len(R), _p(R), _p(t), _p(n), _p(Kc)))
+        self.rows = len(R)
+
+    # ---- 3-D grid ------------------------------------------------------------------------
+    def trace3d_grid(self, fields, ys, xs, stop, a_stop, arith=FAST, compact=False,
+                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None):
+        """Host-pointer grid sweep.  Returns dict of numpy arrays shaped (n_fields, ny*nx)
+        (+ 'stats' structured array).  `out` may supply preallocated (e.g. pinned) arrays."""
+        farr, nf = make_fields(fields)
+        ys, xs = _d(ys), _d(xs)
+        ny, nx = len(ys), len(xs)
+        NN = ny * nx
+        res = dict(out) if out else {}
+        for name in ("ex", "ey", "r", "theta", "wx", "wy"):
+            if name in want and name not in res:
+                res[name] = np.empty((nf, NN), dtype=np.float64)
+        for name in ("mask", "flags"):
+            if name in want and name not in res:
+                res[name] = np.zeros((nf, NN), dtype=np.uint8)
+        stats = np.zeros(nf, dtype=STATS_DTYPE)
+        go = GridOut(*[(res[k].ctypes.data if k in res and res[k] is not None else None)
+                       for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags")],
+                     stats.ctypes.data)
+        nu, lam = wavegrad if wavegrad else (0.0, 1.0)
+        op = Opts(int(arith), int(bool(compact)), float(nu), float(lam))
+        self._ck(self.L.ort_trace3d_grid(self.h, farr, nf, _vp(ys), ny, _vp(xs), nx, int(stop),
+                                         float(a_stop), C.byref(op), C.byref(go)))
+        res["stats"] = stats
+        return res
+
+    def trace3d_grid_dev(self, fields, d_ys, ny, d_xs, nx, stop, a_stop, ptrs, stream=0,
+                         arith=FAST, compact=False, wavegrad=None):
+        """Device-pointer grid sweep (enqueue only).  ptrs: dict name -> device address (int)."""
+        farr, nf = make_fields(fields)
+        go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags", "stats")])
+        nu, lam = wavegrad if wavegrad else (0.0, 1.0)
+        op = Opts(int(arith), int(bool(compact)), float(nu), float(lam))
+        self._ck(self.L.ort_trace3d_grid_dev(self.h, farr, nf, C.c_void_p(d_ys), int(ny), C.c_void_p(d_xs),
+                                             int(nx), int(stop), float(a_stop), C.byref(op), C.byref(go),
+                                             C.c_void_p(stream)))
+
+    # ---- arbitrary rays ------------------------------------------------------------------
+    def trace3d_rays(self, y0, x0, u0, v0, arith=STRICT):
+        y0, x0, u0, v0 = _d(y0), _d(x0), _d(u0), _d(v0)
+        N, ns = len(y0), self.rows - 1
+        xv, yv, k = np.empty((ns, N)), np.empty((ns, N)), np.empty((3, N))
+        fl = np.zeros(N, dtype=np.uint8)
+        self._ck(self.L.ort_trace3d_rays(self.h, N, _p(y0), _p(x0), _p(u0), _p(v0), int(arith), _p(xv),
+                                         _p(yv), _p(k), fl.ctypes.data_as(_u8p)))
+        return xv, yv, k, fl
+
+    def trace2d_batch(self, y0, U0, aspheric=False):
+        y0, U0 = _d(y0), _d(U0)
+        N, rows = len(y0), self.rows
+        yo, Uo, ts = np.empty((rows, N)), np.empty((rows, N)), np.empty((rows, N))
+        fl = np.zeros(N, dtype=np.uint8)
+        self._ck(self.L.ort_trace2d_batch(self.h, N, _p(y0), _p(U0), int(bool(aspheric)), _p(yo), _p(Uo),
+                                          _p(ts), fl.ctypes.data_as(_u8p)))
+        return yo, Uo, ts, fl
+
+    # ---- paraxial / transfer matrix ------------------------------------------------------
+    def paraxial_batch(self, tau, phi, y0, w0, a=None, clip=False, arith=STRICT, table=False):
+        tau, phi, y0, w0 = _d(tau), _d(phi), _d(y0), _d(w0)
+        a_ = None if a is None else _d(a)
+        k, N = len(tau), len(y0)
+        y, w = np.empty(N), np.empty(N)
+        ci = np.zeros(N, dtype=np.int32)
+        ya = np.empty((k + 1, N)) if table else None
+        wa = np.empty((k + 1, N)) if table else None
+        self._ck(self.L.ort_paraxial_batch(self.h, k, _p(tau), _p(phi), _p(a_), int(bool(clip)), int(arith),
+                                           N, _p(y0), _p(w0), _p(y), _p(w), ci.ctypes.data_as(_i32p),
+                                           _p(ya), _p(wa)))
+        return (y, w, ci, ya, wa) if table else (y, w, ci)
+
+    def paraxial_batch_dev(self, tau, phi, N, d_y0, d_w0, d_y, d_w, d_ci=None, a=None, clip=False,
+                           arith=FAST, stream=0):
+        tau, phi = _d(tau), _d(phi)
+        a_ = None if a is None else _d(a)
+        self._ck(self.L.ort_paraxial_batch_dev(self.h, len(tau), _p(tau), _p(phi), _p(a_), int(bool(clip)),
+                                               int(arith), int(N), C.c_void_p(d_y0), C.c_void_p(d_w0),
+                                               C.c_void_p(d_y), C.c_void_p(d_w), C.c_void_p(d_ci or 0),
+                                               None, None, C.c_void_p(stream)))
+
+    def transfer_batch(self, M, tau, taup, v_in, reverse=False):
+        """M: 2x2; v_in: (N, 2) rows [y, nu] (= Julia 2xN column-major)."""
+        Mc = _d(np.asarray(M, dtype=np.float64).T.reshape(-1))
+        v_in = _d(v_in)
+        out = np.empty_like(v_in)
+        self._ck(self.L.ort_transfer_batch(self.h, _p(Mc), float(tau), float(taup), int(bool(reverse)),
+                                           v_in.shape[0], _p(v_in), _p(out)))
+        return out
+
+    def transfer_batch_dev(self, M, tau, taup, N, d_in, d_out, reverse=False, stream=0):
+        Mc = _d(np.asarray(M, dtype=np.float64).T.reshape(-1))
+        self._ck(self.L.ort_transfer_batch_dev(self.h, _p(Mc), float(tau), float(taup), int(bool(reverse)),
+                                               int(N), C.c_void_p(d_in), C.c_void_p(d_out),
+                                               C.c_void_p(stream)))
+
+    # ---- candidates ----------------------------------------------------------------------
+    def trace3d_candidates(self, RtnK, field, ys, xs, stop, a_stop, arith=FAST):
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        assert four == 4
+        farr, _ = make_fields([field])
+        ys, xs = _d(ys), _d(xs)
+        out = np.empty((Cn, 4))
+        self._ck(self.L.ort_trace3d_candidates(self.h, rows, Cn, _p(RtnK), farr, _p(ys), len(ys), _p(xs),
+                                               len(xs), int(stop), float(a_stop), int(arith), _p(out)))
+        return out
+
+    def trace3d_candidates_dev(self, rows, Cn, d_RtnK, field, d_ys, ny, d_xs, nx, stop, a_stop, d_out,
+                               arith=FAST, stream=0):
+        farr, _ = make_fields([field])
+        self._ck(self.L.ort_trace3d_candidates_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), farr,
+                                                   C.c_void_p(d_ys), int(ny), C.c_void_p(d_xs), int(nx),
+                                                   int(stop), float(a_stop), int(arith), C.c_void_p(d_out),
+                                                   C.c_void_p(stream)))

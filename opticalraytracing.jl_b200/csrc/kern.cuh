@@ -1,0 +1,78 @@
+// kern.cuh -- kernel argument blocks and launch wrappers shared between the kernel TUs and ort_api.cu
+#pragma once
+#include "ort_internal.cuh"
+
+struct GridArgs {
+    const double* ys; const double* xs;     // device: grid coordinates (:121-122)
+    int ny, nx;
+    unsigned NN;                            // ny * nx  (< 2^31)
+    int stop;                               // 1-based system.stop
+    double a_stop, a_stop2;
+    double wg_nu, wg_lambda;
+    double *ex, *ey, *r, *theta, *wx, *wy;  // device outputs, [n_fields][NN]; NULL = not wanted
+    uint8_t *mask, *flags;
+    Part* partials;                         // [n_fields][gridDim.x]
+    int* tile_counts;                       // [n_fields][ntiles] or NULL (no compaction requested)
+    ort_field fields[ORT_MAX_FIELDS];
+};
+
+struct CompactArgs {
+    unsigned NN;
+    const uint8_t* mask;
+    const int* tile_offsets;
+    const double* src[6];
+    double* dst[6];
+};
+
+struct RaysArgs {
+    long long N;
+    const double *y0, *x0, *u0, *v0;
+    double *xv, *yv, *kout;
+    uint8_t* flags;
+};
+
+struct CandArgs {
+    int rows; long long C;
+    const double* RtnK;
+    const double *ys, *xs; int ny, nx;
+    int stop; double a_stop, a_stop2, u, v, h_prime;
+    double* out;
+};
+
+struct LensK {                              // paraxial Lens rows in the constant bank
+    int k; int clip;
+    double tau[ORT_MAX_LENS], phi[ORT_MAX_LENS], a[ORT_MAX_LENS];
+};
+
+struct ParaxArgs {
+    long long N;
+    const double *y0, *w0;
+    double *y, *w; int32_t* clip_idx;
+    double *y_all, *w_all;
+};
+
+struct Trace2dArgs {
+    long long N; int aspheric;
+    const double *y0, *U0;
+    double *y_out, *U_out, *ts_out;
+    uint8_t* flags;
+};
+
+struct TransferArgs {
+    long long N; int reverse;
+    double E[4];                            // extend(M, tau, taup), column-major
+    const double2* v_in; double2* v_out;
+};
+
+int grid_blocks_per_sm(int arith);
+cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st);
+cudaError_t launch_grid_finalize(const Part* partials, int nparts, int n_fields, ort_stats* stats,
+                                 cudaStream_t st);
+cudaError_t launch_compact(int* tile_counts, const CompactArgs& C, int n_fields, cudaStream_t st);
+cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream_t st);
+cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st);
+cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st);
+cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st);
+cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
+cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
+                             long long* dfma_per_launch);

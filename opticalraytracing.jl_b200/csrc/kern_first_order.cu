@@ -1,0 +1,204 @@
+// kern_first_order.cu -- the batched 2-D meridional real-ray trace (K2), the paraxial y-nu trace
+// (K3), the transfer-matrix apply (K4) and the FP64 peak microbenchmark (sm_100a).
+#include "kern.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K2: raytrace(surfaces, y, U, RealRay)  src/RayTracing.jl:145-173 (sag :75-88, tilt :98-101)
+// One thread per ray.  The arithmetic keeps the reference's order (never contracted); tan / cos /
+// asin / sin / atan are CUDA's double-precision libm (<= 2 ulp; Julia's own libm differs in the
+// last ulp too), so parity here is 1e-12 relative, not bit-exact.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= A.N) return;
+    const long long N = A.N;
+    double y = A.y0[i], U = A.U0[i];
+    unsigned flags = 0;
+    double sprev = 0.0;
+    if (A.y_out) A.y_out[i] = y;
+    if (A.U_out) A.U_out[i] = U;
+    const int nsurf = P.nsurf;
+    for (int s = 0; s < nsurf; s++) {
+        const SurfK& S = P.s[s];
+        const double tU = tan(U);
+        const double ti = SS(S.t, sprev);                        // ts[i] (:148, :161)
+        y = SA(y, SM(tU, ti));                                   // :152
+        const double Ks = A.aspheric ? S.K : 0.0;
+        double sg;
+        if (isfinite(S.R)) {                                     // sag :75-88
+            double beta = SS(S.R, SM(y, tU));
+            double y2 = SM(y, y);
+            double sec = SD(1.0, cos(U));
+            double D = SS(SM(beta, beta), SM(y2, SA(SM(sec, sec), Ks)));
+            if (D >= 0.0) sg = SA(SD(y2, SA(beta, SM(S.sgnR, SQ(D)))), 0.0);
+            else { if (D < 0.0) flags |= ORT_FLAG_MISS; sg = CUDART_NAN; }
+        } else sg = 0.0;
+        y = SA(y, SM(sg, tU));                                   // :158
+        if (A.ts_out) A.ts_out[(size_t)s * N + i] = SA(ti, sg);  // ts[i] += s  :160
+        sprev = sg;                                              // ts[i+1] -= s :161
+        double theta;
+        if (!A.aspheric) {                                       // asin(tilt(y, R))  :162, :101
+            double q = SD(y, S.R);
+            if (fabs(q) > 1.0) flags |= ORT_FLAG_DOMAIN;
+            theta = asin(q);
+        } else {                                                 // atan(tilt(y, R, K, p))  :98
+            double D2 = SS(SM(S.R, S.R), SM(SM(y, y), SA(1.0, Ks)));
+            if (D2 < 0.0) flags |= ORT_FLAG_DOMAIN;
+            theta = atan(SA(SD(SM(S.sgnR, y), SQ(D2)), 0.0));
+        }
+        const double sin_ip = SD(SM(S.n1, sin(SA(U, theta))), S.n2);   // :163
+        if (fabs(sin_ip) <= 1.0) U = SS(asin(sin_ip), theta);          // :164
+        else { if (fabs(sin_ip) > 1.0) flags |= ORT_FLAG_TIR; U = CUDART_NAN; }
+        if (A.y_out) A.y_out[(size_t)(s + 1) * N + i] = y;
+        if (A.U_out) A.U_out[(size_t)(s + 1) * N + i] = U;
+    }
+    if (A.ts_out) A.ts_out[(size_t)nsurf * N + i] = SS(P.t_last, sprev);
+    if (A.flags) A.flags[i] = (uint8_t)flags;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: raytrace(lens, y, w, a; clip)  src/RayTracing.jl:127-143 with transfer/refract :55-69.
+// Lens rows live in the constant bank.  STRICT = reference order (mul, add); FAST = DFMA.
+// ------------------------------------------------------------------------------------------
+template <int ARITH, bool TABLE>
+__global__ void __launch_bounds__(256)
+k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= A.N) return;
+    const long long N = A.N;
+    double y = A.y0[i], w = A.w0[i];
+    int ci = 0;
+    if (TABLE) {
+        if (A.y_all) A.y_all[i] = y;
+        if (A.w_all) A.w_all[i] = w;
+    }
+    const int k = L.k;
+    int j = 0;
+    for (; j < k; j++) {
+        const double tau = L.tau[j], phi = L.phi[j];
+        if (ARITH == ORT_ARITH_STRICT) {
+            if (isfinite(tau)) y = SA(y, SM(w, tau));            // :62
+            w = SS(w, SM(y, phi));                               // :67
+        } else {
+            if (isfinite(tau)) y = fma(w, tau, y);
+            w = fma(-y, phi, w);
+        }
+        if (L.clip && SS(fabs(y), L.a[j]) > 1e-13) {             // :135
+            ci = j + 1; y = CUDART_NAN; w = CUDART_NAN;
+            break;
+        }
+        if (TABLE) {
+            if (A.y_all) A.y_all[(size_t)(j + 1) * N + i] = y;
+            if (A.w_all) A.w_all[(size_t)(j + 1) * N + i] = w;
+        }
+    }
+    if (TABLE && ci) {                                           // rt[i+1:end,:] .= NaN  :136
+        for (; j < k; j++) {
+            if (A.y_all) A.y_all[(size_t)(j + 1) * N + i] = CUDART_NAN;
+            if (A.w_all) A.w_all[(size_t)(j + 1) * N + i] = CUDART_NAN;
+        }
+    }
+    if (A.y) A.y[i] = y;
+    if (A.w) A.w[i] = w;
+    if (A.clip_idx) A.clip_idx[i] = ci;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: transfer(M, v, tau, taup) = extend(M, tau, taup) * v and reverse_transfer = extend \ v
+// src/TransferMatrix.jl:8-17.  Pure HBM streaming: 16 B in, 16 B out per ray, 128-bit accesses.
+// The reverse path restates the 2x2 partially pivoted LU that Julia's `\` performs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
+{
+    const long long stride = (long long)gridDim.x * 256;
+    const double a11 = A.E[0], a21 = A.E[1], a12 = A.E[2], a22 = A.E[3];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < A.N; i += stride) {
+        const double2 v = A.v_in[i];
+        double2 o;
+        if (!A.reverse) {
+            o.x = SA(SM(a11, v.x), SM(a12, v.y));
+            o.y = SA(SM(a21, v.x), SM(a22, v.y));
+        } else if (a21 == 0.0) {
+            o.y = SD(v.y, a22); o.x = SD(SS(v.x, SM(a12, o.y)), a11);
+        } else if (a12 == 0.0) {
+            o.x = SD(v.x, a11); o.y = SD(SS(v.y, SM(a21, o.x)), a22);
+        } else {
+            double p11 = a11, p12 = a12, p21 = a21, p22 = a22, b1 = v.x, b2 = v.y;
+            if (fabs(a21) > fabs(a11)) { p11 = a21; p12 = a22; p21 = a11; p22 = a12; b1 = v.y; b2 = v.x; }
+            const double l = SD(p21, p11);
+            const double u22 = SS(p22, SM(l, p12));
+            const double y2 = SS(b2, SM(l, b1));
+            o.y = SD(y2, u22);
+            o.x = SD(SS(b1, SM(p12, o.y)), p11);
+        }
+        A.v_out[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 roofline denominator: 8 independent DFMA chains per thread, register resident.
+// ------------------------------------------------------------------------------------------
+#define PEAK_CHAINS 8
+#define PEAK_UNROLL 16
+__global__ void __launch_bounds__(512) k_fp64_peak(double* sink, long long iters)
+{
+    double a[PEAK_CHAINS];
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; j++) a[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double b = 0.9999999, c = 1e-7;
+    for (long long it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < PEAK_UNROLL; u++)
+#pragma unroll
+            for (int j = 0; j < PEAK_CHAINS; j++) a[j] = fma(a[j], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; j++) s += a[j];
+    if (s == 123456.789) sink[0] = s;       // never true; defeats dead-code elimination
+}
+
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st)
+{
+    const unsigned nb = (unsigned)((A.N + 255) / 256);
+    if (nb == 0) return cudaSuccess;
+    k_trace2d<<<nb, 256, 0, st>>>(P, A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st)
+{
+    const unsigned nb = (unsigned)((A.N + 255) / 256);
+    if (nb == 0) return cudaSuccess;
+    const bool table = A.y_all || A.w_all;
+    if (arith == ORT_ARITH_FAST) {
+        if (table) k_paraxial<ORT_ARITH_FAST, true><<<nb, 256, 0, st>>>(L, A);
+        else k_paraxial<ORT_ARITH_FAST, false><<<nb, 256, 0, st>>>(L, A);
+    } else {
+        if (table) k_paraxial<ORT_ARITH_STRICT, true><<<nb, 256, 0, st>>>(L, A);
+        else k_paraxial<ORT_ARITH_STRICT, false><<<nb, 256, 0, st>>>(L, A);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st)
+{
+    if (A.N == 0) return cudaSuccess;
+    long long nb = (A.N + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    k_transfer<<<(unsigned)nb, 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
+                             long long* dfma_per_launch)
+{
+    const int blocks = sm_count * 2;
+    k_fp64_peak<<<blocks, 512, 0, st>>>(d_sink, iters);
+    if (dfma_per_launch) *dfma_per_launch = (long long)blocks * 512 * iters * PEAK_UNROLL * PEAK_CHAINS;
+    return cudaGetLastError();
+}

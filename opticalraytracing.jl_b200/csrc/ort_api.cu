@@ -1,0 +1,640 @@
+// ort_api.cu -- the C ABI of libort_b200.so (include/ort_b200.h): context, prescription upload,
+// host-pointer (synchronous, staged through device scratch) and device-pointer (enqueue-only)
+// entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "kern.cuh"
+
+namespace {
+
+enum Slot {
+    SL_YS, SL_XS, SL_PARTIALS, SL_TILES, SL_STATS,
+    SL_EX, SL_EY, SL_R, SL_TH, SL_WX, SL_WY, SL_MASK, SL_FLAGS,     // trace outputs (full grid)
+    SL_CEX, SL_CEY, SL_CR, SL_CTH, SL_CWX, SL_CWY,                  // compacted outputs
+    SL_IN0, SL_IN1, SL_IN2, SL_IN3, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3, SL_OUT4, SL_SINK,
+    SL_COUNT
+};
+
+thread_local char g_init_err[512] = "";
+
+}  // namespace
+
+struct ort_ctx {
+    int device;
+    int sm_count, cc_major, cc_minor;
+    char name[128];
+    cudaStream_t stream;        // compute stream of the host-pointer entry points
+    cudaStream_t copy_stream;   // D2H stream (overlaps the next field's trace)
+    cudaEvent_t ev_a, ev_b;
+    cudaEvent_t ev_field[ORT_MAX_FIELDS];
+    Presc presc;
+    int rows;
+    bool have_layout;
+    int bps[2];                 // resident CTAs/SM of k_grid<STRICT>, <FAST>
+    void* slot[SL_COUNT];
+    size_t slot_bytes[SL_COUNT];
+    long long launches;
+    char err[512];
+};
+
+namespace {
+
+int fail(ort_ctx* c, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_init_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, ORT_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                        cudaGetErrorString(e_));                                              \
+    } while (0)
+
+// grow-only device scratch
+int ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
+{
+    if (bytes == 0) bytes = 8;
+    if (ctx->slot_bytes[id] < bytes) {
+        if (ctx->slot[id]) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaFree(ctx->slot[id]); }
+        ctx->slot[id] = nullptr; ctx->slot_bytes[id] = 0;
+        cudaError_t e = cudaMalloc(&ctx->slot[id], bytes);
+        if (e != cudaSuccess) return fail(ctx, ORT_ENOMEM, "cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+        ctx->slot_bytes[id] = bytes;
+    }
+    *out = ctx->slot[id];
+    return ORT_OK;
+}
+#define ENSURE(id, bytes, ptr)                                                     \
+    do { void* p_; int rc_ = ensure(ctx, (id), (bytes), &p_); if (rc_) return rc_; \
+         (ptr) = (decltype(ptr))p_; } while (0)
+
+void derive_surface_host(SurfK& S, double R, double K, double t, double n1, double n2)
+{
+    S.R = R; S.K = K; S.t = t; S.n1 = n1; S.n2 = n2;
+    S.sgnR = (R < 0.0) ? -1.0 : ((R > 0.0) ? 1.0 : R);          // Julia sign()
+    S.c = isfinite(R) ? 1.0 / R : 0.0;
+    S.eta = n1 / n2;
+    S.eta2 = S.eta * S.eta;
+    S.ome2 = 1.0 - S.eta2;
+    S.onepK = 1.0 + K;
+    S.kind = !isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC);
+    S.refr = (n1 != n2);
+}
+
+int resolve_arith(const ort_ctx* ctx, int arith)
+{
+    if (arith == ORT_ARITH_FAST && !ctx->presc.fast_ok) return ORT_ARITH_STRICT;
+    return arith;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ort_version(void) { return ORT_VERSION; }
+
+int ort_init(ort_ctx** out, int device)
+{
+    ort_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, ORT_EINVAL, "ort_init: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ORT_ECUDA, "ort_init: no CUDA device (%s); libort_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, ORT_EINVAL, "ort_init: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, ORT_ECUDA, "cudaGetDeviceProperties -> %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, ORT_EUNSUPPORTED, "ort_init: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    ctx = new (std::nothrow) ort_ctx();
+    if (!ctx) return fail(nullptr, ORT_ENOMEM, "ort_init: out of host memory");
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+    snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+#define CKI(call)                                                                                   \
+    do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) {                                        \
+             fail(nullptr, ORT_ECUDA, "ort_init: %s -> %s", #call, cudaGetErrorString(e2_));         \
+             delete ctx; return ORT_ECUDA; } } while (0)
+    CKI(cudaSetDevice(device));
+    CKI(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKI(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CKI(cudaEventCreate(&ctx->ev_a));
+    CKI(cudaEventCreate(&ctx->ev_b));
+    for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
+#undef CKI
+    ctx->bps[ORT_ARITH_STRICT] = grid_blocks_per_sm(ORT_ARITH_STRICT);
+    ctx->bps[ORT_ARITH_FAST] = grid_blocks_per_sm(ORT_ARITH_FAST);
+    *out = ctx;
+    return ORT_OK;
+}
+
+void ort_free(ort_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < SL_COUNT; i++) if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+    for (int i = 0; i < ORT_MAX_FIELDS; i++) cudaEventDestroy(ctx->ev_field[i]);
+    cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char* ort_last_error(ort_ctx* ctx) { return ctx ? ctx->err : g_init_err; }
+
+int ort_sync(ort_ctx* ctx)
+{
+    if (!ctx) return ORT_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return ORT_OK;
+}
+
+int ort_device_info(ort_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", ctx->name);
+    return ORT_OK;
+}
+
+void* ort_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void ort_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int64_t ort_launch_count(ort_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, const double* n, const double* K)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!R || !t || !n) return fail(ctx, ORT_EINVAL, "ort_set_layout: NULL column");
+    if (rows < 2 || rows > ORT_MAX_ROWS) return fail(ctx, ORT_EINVAL, "ort_set_layout: rows = %d not in [2, %d]", rows, ORT_MAX_ROWS);
+    Presc& P = ctx->presc;
+    memset(&P, 0, sizeof P);
+    P.nsurf = rows - 1;
+    P.fast_ok = 1;
+    P.t_last = t[rows - 1];
+    for (int i = 0; i + 1 < rows; i++) {
+        const double Ri = R[i + 1], Ki = K ? K[i + 1] : 0.0;
+        derive_surface_host(P.s[i], Ri, Ki, t[i], n[i], n[i + 1]);
+        if (Ri == 0.0 || isnan(Ri) || !isfinite(Ki) || !isfinite(t[i]) || !isfinite(P.s[i].eta) ||
+            P.s[i].eta == 0.0)
+            P.fast_ok = 0;
+    }
+    ctx->rows = rows;
+    ctx->have_layout = true;
+    return ORT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pupil-grid sweep
+// ------------------------------------------------------------------------------------------
+static int grid_check(ort_ctx* ctx, const ort_field* fields, int n_fields, const void* ys, int ny,
+                      const void* xs, int nx, int stop, const ort_opts* opts, const ort_grid_out* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "trace3d_grid: call ort_set_layout first");
+    if (!fields || n_fields < 1 || n_fields > ORT_MAX_FIELDS) return fail(ctx, ORT_EINVAL, "trace3d_grid: n_fields = %d not in [1, %d]", n_fields, ORT_MAX_FIELDS);
+    if (!ys || !xs || ny < 0 || nx < 0) return fail(ctx, ORT_EINVAL, "trace3d_grid: bad grid");
+    if ((long long)ny * nx >= (1LL << 31)) return fail(ctx, ORT_EINVAL, "trace3d_grid: ny*nx = %lld exceeds 2^31-1 per call", (long long)ny * nx);
+    if (stop < 1 || stop > ctx->presc.nsurf) return fail(ctx, ORT_EINVAL, "trace3d_grid: stop = %d not in [1, %d]", stop, ctx->presc.nsurf);
+    if (!opts || !out) return fail(ctx, ORT_EINVAL, "trace3d_grid: opts/out is NULL");
+    if (opts->arith != ORT_ARITH_STRICT && opts->arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "trace3d_grid: arith = %d", opts->arith);
+    for (int f = 0; f < n_fields; f++)
+        if (fields[f].mode != 0 && fields[f].mode != 1) return fail(ctx, ORT_EINVAL, "trace3d_grid: field %d mode = %d", f, fields[f].mode);
+    return ORT_OK;
+}
+
+// Enqueue trace (+ compaction) + finalize for fields [0, n_fields) on `st`.  All pointers are
+// device pointers.  `full` receives the full-grid trace outputs; when compacting, `full` is
+// scratch and `dst` the compacted destination.
+static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
+                        const double* d_xs, int nx, int stop, double a_stop, const ort_opts* opts,
+                        const ort_grid_out& full, const ort_grid_out* dst, ort_stats* d_stats,
+                        Part* d_partials, int* d_tiles, int gx, cudaStream_t st)
+{
+    const unsigned NN = (unsigned)((long long)ny * nx);
+    GridArgs A;
+    memset(&A, 0, sizeof A);
+    A.ys = d_ys; A.xs = d_xs; A.ny = ny; A.nx = nx; A.NN = NN; A.stop = stop;
+    A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
+    A.wg_nu = opts->wg_nu; A.wg_lambda = opts->wg_lambda;
+    A.ex = full.ex; A.ey = full.ey; A.r = full.r; A.theta = full.theta; A.wx = full.wx; A.wy = full.wy;
+    A.mask = full.mask; A.flags = full.flags;
+    A.partials = d_partials;
+    A.tile_counts = dst ? d_tiles : nullptr;
+    memcpy(A.fields, fields, sizeof(ort_field) * (size_t)n_fields);
+    const int arith = resolve_arith(ctx, opts->arith);
+    if (NN > 0) {
+        CK(launch_grid(ctx->presc, A, arith, dim3((unsigned)gx, (unsigned)n_fields), st));
+        ctx->launches++;
+    } else {
+        CK(cudaMemsetAsync(d_partials, 0, sizeof(Part) * (size_t)gx * n_fields, st));
+    }
+    CK(launch_grid_finalize(d_partials, gx, n_fields, d_stats, st));
+    ctx->launches++;
+    if (dst && NN > 0) {
+        CompactArgs C;
+        memset(&C, 0, sizeof C);
+        C.NN = NN; C.mask = full.mask; C.tile_offsets = d_tiles;
+        const double* src[6] = {full.ex, full.ey, full.r, full.theta, full.wx, full.wy};
+        double* dd[6] = {dst->ex, dst->ey, dst->r, dst->theta, dst->wx, dst->wy};
+        for (int a = 0; a < 6; a++) { C.src[a] = dd[a] ? src[a] : nullptr; C.dst[a] = dd[a]; }
+        CK(launch_compact(d_tiles, C, n_fields, st));
+        ctx->launches += 2;
+    }
+    return ORT_OK;
+}
+
+static int grid_dims(const ort_ctx* ctx, int arith, int n_fields, unsigned NN)
+{
+    const unsigned ntiles = (NN + ORT_TILE - 1) / ORT_TILE;
+    long long gx = (long long)ctx->sm_count * ctx->bps[arith] / n_fields;
+    if (gx < 1) gx = 1;
+    if (gx > (long long)ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    return (int)gx;
+}
+
+int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
+                         const double* d_xs, int nx, int stop, double a_stop, const ort_opts* opts,
+                         const ort_grid_out* d_out, void* stream)
+{
+    int rc = grid_check(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, opts, d_out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned NN = (unsigned)((long long)ny * nx);
+    const int arith = resolve_arith(ctx, opts->arith);
+    const int gx = grid_dims(ctx, arith, n_fields, NN);
+    Part* d_partials; ENSURE(SL_PARTIALS, sizeof(Part) * (size_t)gx * n_fields, d_partials);
+    ort_stats* d_stats = d_out->stats;
+    if (!d_stats) ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
+    if (!opts->compact)
+        return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, *d_out, nullptr,
+                            d_stats, d_partials, nullptr, gx, st);
+    // compaction: trace into scratch, scatter into the caller's arrays
+    const size_t tot = (size_t)NN * n_fields;
+    ort_grid_out full = *d_out;
+    if (d_out->ex) ENSURE(SL_EX, tot * 8, full.ex);
+    if (d_out->ey) ENSURE(SL_EY, tot * 8, full.ey);
+    if (d_out->r) ENSURE(SL_R, tot * 8, full.r);
+    if (d_out->theta) ENSURE(SL_TH, tot * 8, full.theta);
+    if (d_out->wx) ENSURE(SL_WX, tot * 8, full.wx);
+    if (d_out->wy) ENSURE(SL_WY, tot * 8, full.wy);
+    if (!d_out->mask) ENSURE(SL_MASK, tot, full.mask);
+    int* d_tiles; ENSURE(SL_TILES, sizeof(int) * (size_t)((NN + ORT_TILE - 1) / ORT_TILE + 1) * n_fields, d_tiles);
+    return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full, d_out, d_stats,
+                        d_partials, d_tiles, gx, st);
+}
+
+int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* ys, int ny,
+                     const double* xs, int nx, int stop, double a_stop, const ort_opts* opts,
+                     ort_grid_out* out)
+{
+    int rc = grid_check(ctx, fields, n_fields, ys, ny, xs, nx, stop, opts, out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned NN = (unsigned)((long long)ny * nx);
+    const size_t tot = (size_t)NN * n_fields;
+    const int arith = resolve_arith(ctx, opts->arith);
+    // one launch per field so the D2H of field f overlaps the trace of field f+1
+    const int gx = grid_dims(ctx, arith, 1, NN);
+    double *d_ys, *d_xs;
+    ENSURE(SL_YS, sizeof(double) * (size_t)ny, d_ys);
+    ENSURE(SL_XS, sizeof(double) * (size_t)nx, d_xs);
+    Part* d_partials; ENSURE(SL_PARTIALS, sizeof(Part) * (size_t)gx * n_fields, d_partials);
+    ort_stats* d_stats; ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
+    const unsigned ntiles = (NN + ORT_TILE - 1) / ORT_TILE;
+    int* d_tiles = nullptr;
+    ort_grid_out full; memset(&full, 0, sizeof full);
+    ort_grid_out comp; memset(&comp, 0, sizeof comp);
+    if (out->ex) ENSURE(SL_EX, tot * 8, full.ex);
+    if (out->ey) ENSURE(SL_EY, tot * 8, full.ey);
+    if (out->r) ENSURE(SL_R, tot * 8, full.r);
+    if (out->theta) ENSURE(SL_TH, tot * 8, full.theta);
+    if (out->wx) ENSURE(SL_WX, tot * 8, full.wx);
+    if (out->wy) ENSURE(SL_WY, tot * 8, full.wy);
+    if (out->mask || opts->compact) ENSURE(SL_MASK, tot, full.mask);
+    if (out->flags) ENSURE(SL_FLAGS, tot, full.flags);
+    if (opts->compact) {
+        ENSURE(SL_TILES, sizeof(int) * (size_t)(ntiles + 1) * n_fields, d_tiles);
+        if (out->ex) ENSURE(SL_CEX, tot * 8, comp.ex);
+        if (out->ey) ENSURE(SL_CEY, tot * 8, comp.ey);
+        if (out->r) ENSURE(SL_CR, tot * 8, comp.r);
+        if (out->theta) ENSURE(SL_CTH, tot * 8, comp.theta);
+        if (out->wx) ENSURE(SL_CWX, tot * 8, comp.wx);
+        if (out->wy) ENSURE(SL_CWY, tot * 8, comp.wy);
+    }
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * (size_t)ny, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_xs, xs, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
+    ort_stats hstats[ORT_MAX_FIELDS];
+    for (int f = 0; f < n_fields; f++) {
+        const size_t o = (size_t)f * NN;
+        ort_grid_out ff = full, cc = comp;
+#define OFF(p) if (p) p += o
+        OFF(ff.ex); OFF(ff.ey); OFF(ff.r); OFF(ff.theta); OFF(ff.wx); OFF(ff.wy); OFF(ff.mask); OFF(ff.flags);
+        OFF(cc.ex); OFF(cc.ey); OFF(cc.r); OFF(cc.theta); OFF(cc.wx); OFF(cc.wy);
+#undef OFF
+        rc = grid_enqueue(ctx, fields + f, 1, d_ys, ny, d_xs, nx, stop, a_stop, opts, ff,
+                          opts->compact ? &cc : nullptr, d_stats + f, d_partials + (size_t)f * gx,
+                          d_tiles ? d_tiles + (size_t)f * (ntiles + 1) : nullptr, gx, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_field[f], st));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_field[f], 0));
+        CK(cudaMemcpyAsync(&hstats[f], d_stats + f, sizeof(ort_stats), cudaMemcpyDeviceToHost, cs));
+        if (out->mask) CK(cudaMemcpyAsync(out->mask + o, ff.mask, NN, cudaMemcpyDeviceToHost, cs));
+        if (out->flags) CK(cudaMemcpyAsync(out->flags + o, ff.flags, NN, cudaMemcpyDeviceToHost, cs));
+        size_t cnt = NN;
+        const ort_grid_out& src = opts->compact ? cc : ff;
+        if (opts->compact) {           // copy only the kept prefix: needs this field's count
+            CK(cudaStreamSynchronize(cs));
+            cnt = (size_t)hstats[f].n_kept;
+        }
+        if (out->ex) CK(cudaMemcpyAsync(out->ex + o, src.ex, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->ey) CK(cudaMemcpyAsync(out->ey + o, src.ey, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->r) CK(cudaMemcpyAsync(out->r + o, src.r, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->theta) CK(cudaMemcpyAsync(out->theta + o, src.theta, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->wx) CK(cudaMemcpyAsync(out->wx + o, src.wx, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->wy) CK(cudaMemcpyAsync(out->wy + o, src.wy, cnt * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(cs));
+    if (out->stats) memcpy(out->stats, hstats, sizeof(ort_stats) * (size_t)n_fields);
+    return ORT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// arbitrary rays / 2-D / paraxial / transfer / candidates: host wrappers stage through scratch
+// ------------------------------------------------------------------------------------------
+int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0, const double* u0,
+                     const double* v0, int arith, double* xv, double* yv, double* kout, uint8_t* flags)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "trace3d_rays: call ort_set_layout first");
+    if (N < 0 || !y0 || !x0 || !u0 || !v0) return fail(ctx, ORT_EINVAL, "trace3d_rays: bad input");
+    if (arith != ORT_ARITH_STRICT && arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "trace3d_rays: arith = %d", arith);
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N, ns = (size_t)ctx->presc.nsurf;
+    RaysArgs A; memset(&A, 0, sizeof A);
+    A.N = N;
+    double *d0, *d1, *d2, *d3;
+    ENSURE(SL_IN0, n * 8, d0); ENSURE(SL_IN1, n * 8, d1); ENSURE(SL_IN2, n * 8, d2); ENSURE(SL_IN3, n * 8, d3);
+    if (xv) ENSURE(SL_OUT0, ns * n * 8, A.xv);
+    if (yv) ENSURE(SL_OUT1, ns * n * 8, A.yv);
+    if (kout) ENSURE(SL_OUT2, 3 * n * 8, A.kout);
+    if (flags) ENSURE(SL_OUT3, n, A.flags);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d1, x0, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, u0, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d3, v0, n * 8, cudaMemcpyHostToDevice, st));
+    A.y0 = d0; A.x0 = d1; A.u0 = d2; A.v0 = d3;
+    CK(launch_rays(ctx->presc, A, resolve_arith(ctx, arith), st));
+    ctx->launches++;
+    if (xv) CK(cudaMemcpyAsync(xv, A.xv, ns * n * 8, cudaMemcpyDeviceToHost, st));
+    if (yv) CK(cudaMemcpyAsync(yv, A.yv, ns * n * 8, cudaMemcpyDeviceToHost, st));
+    if (kout) CK(cudaMemcpyAsync(kout, A.kout, 3 * n * 8, cudaMemcpyDeviceToHost, st));
+    if (flags) CK(cudaMemcpyAsync(flags, A.flags, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+int ort_trace2d_batch(ort_ctx* ctx, int64_t N, const double* y0, const double* U0, int aspheric,
+                      double* y_out, double* U_out, double* ts_out, uint8_t* flags)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "trace2d_batch: call ort_set_layout first");
+    if (N < 0 || !y0 || !U0) return fail(ctx, ORT_EINVAL, "trace2d_batch: bad input");
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N, rows = (size_t)ctx->rows;
+    Trace2dArgs A; memset(&A, 0, sizeof A);
+    A.N = N; A.aspheric = aspheric ? 1 : 0;
+    double *d0, *d1;
+    ENSURE(SL_IN0, n * 8, d0); ENSURE(SL_IN1, n * 8, d1);
+    if (y_out) ENSURE(SL_OUT0, rows * n * 8, A.y_out);
+    if (U_out) ENSURE(SL_OUT1, rows * n * 8, A.U_out);
+    if (ts_out) ENSURE(SL_OUT2, rows * n * 8, A.ts_out);
+    if (flags) ENSURE(SL_OUT3, n, A.flags);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d1, U0, n * 8, cudaMemcpyHostToDevice, st));
+    A.y0 = d0; A.U0 = d1;
+    CK(launch_trace2d(ctx->presc, A, st));
+    ctx->launches++;
+    if (y_out) CK(cudaMemcpyAsync(y_out, A.y_out, rows * n * 8, cudaMemcpyDeviceToHost, st));
+    if (U_out) CK(cudaMemcpyAsync(U_out, A.U_out, rows * n * 8, cudaMemcpyDeviceToHost, st));
+    if (ts_out) CK(cudaMemcpyAsync(ts_out, A.ts_out, rows * n * 8, cudaMemcpyDeviceToHost, st));
+    if (flags) CK(cudaMemcpyAsync(flags, A.flags, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+static int lens_fill(ort_ctx* ctx, LensK& L, int k, const double* tau, const double* phi, const double* a, int clip)
+{
+    if (k < 0 || k > ORT_MAX_LENS) return fail(ctx, ORT_EINVAL, "paraxial_batch: k = %d not in [0, %d]", k, ORT_MAX_LENS);
+    if (k > 0 && (!tau || !phi)) return fail(ctx, ORT_EINVAL, "paraxial_batch: NULL tau/phi");
+    memset(&L, 0, sizeof L);
+    L.k = k; L.clip = (clip && a) ? 1 : 0;
+    for (int i = 0; i < k; i++) { L.tau[i] = tau[i]; L.phi[i] = phi[i]; L.a[i] = a ? a[i] : INFINITY; }
+    return ORT_OK;
+}
+
+int ort_paraxial_batch_dev(ort_ctx* ctx, int k, const double* tau, const double* phi, const double* a, int clip,
+                           int arith, int64_t N, const double* d_y0, const double* d_w0, double* d_y,
+                           double* d_w, int32_t* d_clip_idx, double* d_y_all, double* d_w_all, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (N < 0 || !d_y0 || !d_w0) return fail(ctx, ORT_EINVAL, "paraxial_batch: bad input");
+    if (arith != ORT_ARITH_STRICT && arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "paraxial_batch: arith = %d", arith);
+    LensK L;
+    int rc = lens_fill(ctx, L, k, tau, phi, a, clip);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ParaxArgs A; memset(&A, 0, sizeof A);
+    A.N = N; A.y0 = d_y0; A.w0 = d_w0; A.y = d_y; A.w = d_w; A.clip_idx = d_clip_idx;
+    A.y_all = d_y_all; A.w_all = d_w_all;
+    CK(launch_paraxial(L, A, arith, (cudaStream_t)stream));
+    if (N > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_paraxial_batch(ort_ctx* ctx, int k, const double* tau, const double* phi, const double* a, int clip,
+                       int arith, int64_t N, const double* y0, const double* w0, double* y, double* w,
+                       int32_t* clip_idx, double* y_all, double* w_all)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (N < 0 || !y0 || !w0) return fail(ctx, ORT_EINVAL, "paraxial_batch: bad input");
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N, kk = (size_t)k + 1;
+    double *d0, *d1, *dy = nullptr, *dw = nullptr, *dya = nullptr, *dwa = nullptr;
+    int32_t* dci = nullptr;
+    ENSURE(SL_IN0, n * 8, d0); ENSURE(SL_IN1, n * 8, d1);
+    if (y) ENSURE(SL_OUT0, n * 8, dy);
+    if (w) ENSURE(SL_OUT1, n * 8, dw);
+    if (clip_idx) ENSURE(SL_OUT2, n * 4, dci);
+    if (y_all) ENSURE(SL_OUT3, kk * n * 8, dya);
+    if (w_all) ENSURE(SL_OUT4, kk * n * 8, dwa);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d1, w0, n * 8, cudaMemcpyHostToDevice, st));
+    int rc = ort_paraxial_batch_dev(ctx, k, tau, phi, a, clip, arith, N, d0, d1, dy, dw, dci, dya, dwa, st);
+    if (rc) return rc;
+    if (y) CK(cudaMemcpyAsync(y, dy, n * 8, cudaMemcpyDeviceToHost, st));
+    if (w) CK(cudaMemcpyAsync(w, dw, n * 8, cudaMemcpyDeviceToHost, st));
+    if (clip_idx) CK(cudaMemcpyAsync(clip_idx, dci, n * 4, cudaMemcpyDeviceToHost, st));
+    if (y_all) CK(cudaMemcpyAsync(y_all, dya, kk * n * 8, cudaMemcpyDeviceToHost, st));
+    if (w_all) CK(cudaMemcpyAsync(w_all, dwa, kk * n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+// extend(M, tau, taup) = [1 taup; 0 1] * M * [1 tau; 0 1]  (src/TransferMatrix.jl:8), evaluated on the
+// host with Julia's generic 2x2 matmul order (C[i,j] = A[i,1]*B[1,j] + A[i,2]*B[2,j]); volatile keeps
+// the host compiler from contracting.
+static void mm2_host(const double* A, const double* B, double* C)
+{
+    volatile double p, q;
+    double c[4];
+    p = A[0] * B[0]; q = A[2] * B[1]; c[0] = p + q;
+    p = A[1] * B[0]; q = A[3] * B[1]; c[1] = p + q;
+    p = A[0] * B[2]; q = A[2] * B[3]; c[2] = p + q;
+    p = A[1] * B[2]; q = A[3] * B[3]; c[3] = p + q;
+    memcpy(C, c, sizeof c);
+}
+
+int ort_transfer_batch_dev(ort_ctx* ctx, const double M[4], double tau, double taup, int reverse, int64_t N,
+                           const double* d_v_in, double* d_v_out, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!M || N < 0 || !d_v_in || !d_v_out) return fail(ctx, ORT_EINVAL, "transfer_batch: bad input");
+    if (((uintptr_t)d_v_in | (uintptr_t)d_v_out) & 15) return fail(ctx, ORT_EINVAL, "transfer_batch: device pointers must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    TransferArgs A; memset(&A, 0, sizeof A);
+    const double Lm[4] = {1.0, 0.0, taup, 1.0}, Rm[4] = {1.0, 0.0, tau, 1.0};
+    double T[4];
+    mm2_host(Lm, M, T);
+    mm2_host(T, Rm, A.E);
+    A.N = N; A.reverse = reverse ? 1 : 0;
+    A.v_in = (const double2*)d_v_in; A.v_out = (double2*)d_v_out;
+    CK(launch_transfer(A, (cudaStream_t)stream));
+    if (N > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_transfer_batch(ort_ctx* ctx, const double M[4], double tau, double taup, int reverse, int64_t N,
+                       const double* v_in, double* v_out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!M || N < 0 || !v_in || !v_out) return fail(ctx, ORT_EINVAL, "transfer_batch: bad input");
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N;
+    double *d0, *d1;
+    ENSURE(SL_IN0, n * 16, d0); ENSURE(SL_OUT0, n * 16, d1);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d0, v_in, n * 16, cudaMemcpyHostToDevice, st));
+    int rc = ort_transfer_batch_dev(ctx, M, tau, taup, reverse, N, d0, d1, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(v_out, d1, n * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+int ort_trace3d_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const ort_field* field,
+                               const double* d_ys, int ny, const double* d_xs, int nx, int stop, double a_stop,
+                               int arith, double* d_out, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS) return fail(ctx, ORT_EINVAL, "candidates: rows = %d", rows);
+    if (C < 0 || C >= (1LL << 31) || !d_RtnK || !field || !d_ys || !d_xs || !d_out) return fail(ctx, ORT_EINVAL, "candidates: bad input");
+    if (field->mode != 0) return fail(ctx, ORT_EUNSUPPORTED, "candidates: only collimated fields (mode 0)");
+    if (stop < 1 || stop > rows - 1) return fail(ctx, ORT_EINVAL, "candidates: stop = %d", stop);
+    if ((long long)ny * nx >= (1LL << 31) || ny < 0 || nx < 0) return fail(ctx, ORT_EINVAL, "candidates: bad grid");
+    if (arith != ORT_ARITH_STRICT && arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "candidates: arith = %d", arith);
+    CK(cudaSetDevice(ctx->device));
+    CandArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.ys = d_ys; A.xs = d_xs; A.ny = ny; A.nx = nx;
+    A.stop = stop; A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
+    A.u = field->u; A.v = field->v; A.h_prime = field->h_prime; A.out = d_out;
+    CK(launch_candidates(A, arith, (cudaStream_t)stream));
+    if (C > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_trace3d_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, const ort_field* field,
+                           const double* ys, int ny, const double* xs, int nx, int stop, double a_stop,
+                           int arith, double* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (C < 0 || !RtnK || !ys || !xs || !out || rows < 2 || ny < 0 || nx < 0) return fail(ctx, ORT_EINVAL, "candidates: bad input");
+    if (C == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)C * 4 * (size_t)rows * 8;
+    double *d_p, *d_ys, *d_xs, *d_o;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_YS, (size_t)ny * 8, d_ys); ENSURE(SL_XS, (size_t)nx * 8, d_xs);
+    ENSURE(SL_OUT0, (size_t)C * 32, d_o);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ys, ys, (size_t)ny * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_xs, xs, (size_t)nx * 8, cudaMemcpyHostToDevice, st));
+    int rc = ort_trace3d_candidates_dev(ctx, rows, C, d_p, field, d_ys, ny, d_xs, nx, stop, a_stop, arith, d_o, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, (size_t)C * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+int ort_fp64_peak(ort_ctx* ctx, double* tflops, double* ms)
+{
+    if (!ctx || !tflops) return ORT_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    double* sink; ENSURE(SL_SINK, 8, sink);
+    cudaStream_t st = ctx->stream;
+    long long dfma = 0;
+    CK(launch_fp64_peak(sink, ctx->sm_count, 256, st, &dfma));           // warm-up
+    double best = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev_a, st));
+        CK(launch_fp64_peak(sink, ctx->sm_count, 4096, st, &dfma));
+        CK(cudaEventRecord(ctx->ev_b, st));
+        CK(cudaEventSynchronize(ctx->ev_b));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ctx->ev_a, ctx->ev_b));
+        if (t < best) best = t;
+    }
+    ctx->launches += 4;
+    *tflops = 2.0 * (double)dfma / (best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    return ORT_OK;
+}
+
+}  // extern "C"

@@ -204,6 +204,18 @@ def trace3d_batch(surfaces, y0, x0, u0, v0, K=None, threads=0):
     return xv, yv, k, fl
 
 
+def trace3d_ld_batch(surfaces, y0, x0, u0, v0, K=None):
+    """Extended-precision (80-bit) evaluation of the same trace: the 'truth' for conditioning checks."""
+    R, t, n, Kc = _cols(surfaces, K)
+    rows = len(R)
+    y0, x0, u0, v0 = _d(y0), _d(x0), _d(u0), _d(v0)
+    N = len(y0)
+    xv, yv, k = np.empty((rows - 1, N)), np.empty((rows - 1, N)), np.empty((3, N))
+    lib().orc_trace3d_ld_batch(C.c_int(rows), _p(R), _p(t), _p(n), _p(Kc), C.c_int64(N), _p(y0),
+                               _p(x0), _p(u0), _p(v0), _p(xv), _p(yv), _p(k))
+    return xv, yv, k
+
+
 def grid_trace(ext_surfaces, ys, xs, stop, a_stop, h_prime, u=0.0, v=0.0, mode=0, ybar=0.0,
                z0=1.0, K=None, want=("ex", "ey", "r", "theta", "mask", "flags"), threads=0):
     """The hot loop of full_trace (PupilSampling.jl:115-138) on the EXTENDED surfaces.

@@ -423,6 +423,66 @@ ORC_API void orc_trace3d_batch(int rows, const double *R, const double *t, const
     }
 }
 
+
+/* ------------------------------------------------------------------------------------
+ * Extended-precision (x87 long double, 64-bit mantissa) evaluation of the same 3-D trace
+ * (src/PupilSampling.jl:34-65).  NOT a restatement of the reference's rounding: it is the
+ * "truth" used by tests to tell ill-conditioned rays (where the reference's own Float64
+ * result is uncertain at the 1e-12 level) from kernel error.
+ * ---------------------------------------------------------------------------------- */
+ORC_API void orc_trace3d_ld(int rows, const double *R, const double *t, const double *n,
+                            const double *K, double y0, double x0, double u0, double v0,
+                            double *xv, double *yv, double *kout)
+{
+    long double y = y0, x = x0, u = u0, v = v0;
+    long double k1 = v, k2 = u, k3 = 1.0L;
+    { long double inv = 1.0L / sqrtl(k1 * k1 + k2 * k2 + k3 * k3); k1 *= inv; k2 *= inv; k3 *= inv; }
+    long double s_prev = 0.0L;
+    for (int i = 0; i + 1 < rows; i++) {
+        long double ti = (long double)t[i] - s_prev;
+        y += u * ti; x += v * ti;
+        long double Rs = R[i + 1], Ks = K ? K[i + 1] : 0.0, s;
+        if (isfinite(R[i + 1])) {
+            long double beta = Rs - y * u - x * v, r2 = x * x + y * y;
+            long double D = beta * beta - r2 * (1.0L + Ks + u * u + v * v);
+            s = (D >= 0.0L) ? r2 / (beta + (long double)jl_sign(R[i + 1]) * sqrtl(D)) : (long double)NAN;
+        } else s = 0.0L;
+        y += s * u; x += s * v; s_prev = s;
+        long double m1, m2, m3 = -1.0L;
+        if (isfinite(R[i + 1])) {
+            long double sq = sqrtl(Rs * Rs - (x * x + y * y) * (1.0L + Ks));
+            m1 = (long double)jl_sign(R[i + 1]) * x / sq; m2 = (long double)jl_sign(R[i + 1]) * y / sq;
+        } else { m1 = (x != x) ? x : 0.0L; m2 = (y != y) ? y : 0.0L; }
+        { long double inv = 1.0L / sqrtl(m1 * m1 + m2 * m2 + m3 * m3); m1 *= inv; m2 *= inv; m3 *= inv; }
+        long double eta = (long double)n[i] / (long double)n[i + 1];
+        long double gam = -(k1 * m1 + k2 * m2 + k3 * m3);
+        long double Dr = 1.0L - eta * eta * (1.0L - gam * gam);
+        if (Dr >= 0.0L) {
+            long double c = eta * gam - sqrtl(Dr);
+            k1 = eta * k1 + c * m1; k2 = eta * k2 + c * m2; k3 = eta * k3 + c * m3;
+        }
+        u = k2 / k3; v = k1 / k3;
+        if (xv) xv[i] = (double)x;
+        if (yv) yv[i] = (double)y;
+    }
+    if (kout) { kout[0] = (double)k1; kout[1] = (double)k2; kout[2] = (double)k3; }
+}
+
+ORC_API void orc_trace3d_ld_batch(int rows, const double *R, const double *t, const double *n,
+                                  const double *K, int64_t N, const double *y0, const double *x0,
+                                  const double *u0, const double *v0, double *xv, double *yv,
+                                  double *kout)
+{
+    double *bx = (double *)malloc(sizeof(double) * 2 * rows), *by = bx + rows;
+    for (int64_t r = 0; r < N; r++) {
+        double kk[3];
+        orc_trace3d_ld(rows, R, t, n, K, y0[r], x0[r], u0[r], v0[r], bx, by, kk);
+        for (int i = 0; i + 1 < rows; i++) { xv[(int64_t)i * N + r] = bx[i]; yv[(int64_t)i * N + r] = by[i]; }
+        if (kout) { kout[r] = kk[0]; kout[N + r] = kk[1]; kout[2 * N + r] = kk[2]; }
+    }
+    free(bx);
+}
+
 /* ------------------------------------------------------------------------------------
  * Pupil grid driver -- src/PupilSampling.jl:115-138 (the hot loop).
  *

@@ -1,0 +1,126 @@
+"""GPU parity of the 2-D meridional tracer (K2), paraxial y-nu trace (K3) and transfer-matrix
+apply (K4) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from util import bits_equal, n_bits_differ, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name,aspheric", [("COOKE", False), ("DOUBLE_GAUSS", False), ("REFLECTIVE", False),
+                                           ("PARABOLA", True), ("COOKE", True)])
+def test_trace2d_batch(ctx, orc, ort, name, aspheric):
+    P = getattr(ort.prescriptions, name)
+    S = P["surfaces"]
+    K = S[:, 3] if S.shape[1] > 3 else None
+    amax = float(P["a"][0])
+    rng = np.random.default_rng(5)
+    N = 4000
+    y0 = rng.uniform(-1.2 * amax, 1.2 * amax, N)
+    U0 = rng.uniform(-0.25, 0.25, N)
+    y0[:3] = [0.0, amax, -amax]; U0[:3] = 0.0
+    yo, Uo, tso, fo = orc.trace2d_batch(S[:, :3], y0, U0, K=K, aspheric=aspheric)
+    ctx.set_layout(S[:, :3], K)
+    yg, Ug, tsg, fg = ctx.trace2d_batch(y0, U0, aspheric=aspheric)
+    # libm (tan/sin/asin/atan) differs by <= 2 ulp between CUDA and glibc (and Julia): a decision
+    # sitting exactly on a branch (TIR / miss) may flip for a handful of rays -> compare where flags agree
+    same = fg == fo
+    assert same.mean() > 0.999
+    scale = np.maximum(np.nanmax(np.abs(yo), axis=0), 1.0)
+    for a, b, s in ((yg, yo, scale), (Ug, Uo, 1.0), (tsg, tso, np.maximum(np.nanmax(np.abs(tso), axis=0), 1.0))):
+        a, b = a[:, same], b[:, same]
+        ss = s[same] if isinstance(s, np.ndarray) else s
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.nanmax(np.abs(a - b) / ss) < TOL
+
+
+def test_parabola_focus_exact(ctx, ort):
+    """test/runtests.jl:334-344: a parabolic mirror has zero spherical aberration; the marginal
+    real ray crosses the axis at exactly -50.0."""
+    S = ort.prescriptions.PARABOLA["surfaces"]
+    ctx.set_layout(S[:, :3], S[:, 3])
+    y, U, ts, f = ctx.trace2d_batch(np.array([30.0, 10.0, 1.0]), np.zeros(3), aspheric=True)
+    z = np.cumsum(ts, axis=0)
+    zf = z[-2] - y[-1] / np.tan(U[-1])
+    assert np.max(np.abs(zf + 50.0)) < 1e-12
+
+
+def test_paraxial_batch(ctx, orc, ort):
+    S = ort.prescriptions.zoom20()
+    tau, phi, n = orc.lens(S)
+    assert len(tau) == 40
+    rng = np.random.default_rng(42)
+    N = 100_003
+    y0, w0 = rng.uniform(-10, 10, N), rng.uniform(-0.2, 0.2, N)
+    a = np.full(len(tau), 40.0)
+    for clip in (False, True):
+        yo, wo, co = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=clip)
+        y, w, c = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=clip, arith=ort.STRICT)
+        assert np.array_equal(c, co)
+        assert n_bits_differ(y, yo) == 0 and n_bits_differ(w, wo) == 0
+        yf, wf, cf = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=clip, arith=ort.FAST)
+        agree = cf == co                      # FMA rounding can flip a ray sitting on the 1e-13 clip edge
+        assert agree.mean() > 0.9999
+        sc = np.maximum(np.abs(y0) + 400 * np.abs(w0), 1.0)
+        ok = agree & ~np.isnan(yo)
+        assert np.max(np.abs(yf[ok] - yo[ok]) / sc[ok]) < TOL
+        assert np.max(np.abs(wf[ok] - wo[ok])) < TOL
+    # full table == the reference's rt matrix, incl. NaN fill after the clip row
+    y, w, c, ya, wa = ctx.paraxial_batch(tau, phi, y0[:500], w0[:500], a=a, clip=True, arith=ort.STRICT, table=True)
+    for j in range(0, 500, 37):
+        rt, ci = orc.paraxial_trace(tau, phi, y0[j], w0[j], a=a, clip=True)
+        assert ci == c[j]
+        assert bits_equal(ya[:, j], rt[:, 0]) and bits_equal(wa[:, j], rt[:, 1])
+
+
+def test_paraxial_clip_threshold(ctx, orc, pre, ort):
+    """test/runtests.jl:252-257: the half-vignetted chief ray passes; lowered by 1e-12 it is clipped."""
+    P = ort.prescriptions.COOKE
+    s = pre.solve(P["surfaces"], P["a"], P["h"])
+    a = P["a"]
+    ybar = np.abs(s.chief.y[1:-1])
+    slope = abs(s.chief.u[0] * np.min(a / ybar))
+    y = -slope * s.EP.t
+    yv, wv, c = ctx.paraxial_batch(s.tau, s.phi, np.array([y, y - 1e-12]), np.array([slope, slope]), a=a,
+                                   clip=True, arith=ort.STRICT)
+    assert c[0] == 0 and not np.isnan(yv[0])
+    assert c[1] != 0 and np.isnan(yv[1])
+
+
+def test_transfer_batch(ctx, orc, pre, ort):
+    P = ort.prescriptions.COOKE
+    s = pre.solve(P["surfaces"], P["a"], P["h"])
+    rng = np.random.default_rng(3)
+    N = 200_001
+    v = np.column_stack([rng.uniform(-20, 20, N), rng.uniform(-0.3, 0.3, N)])
+    for tau, taup in ((0.0, 0.0), (-123.4, 77.4), (50.0, 0.0)):
+        ref = orc.transfer_batch(s.M, tau, taup, v)
+        out = ctx.transfer_batch(s.M, tau, taup, v)
+        assert n_bits_differ(out, ref) == 0
+        refr = orc.transfer_batch(s.M, tau, taup, v, reverse=True)
+        outr = ctx.transfer_batch(s.M, tau, taup, v, reverse=True)
+        assert n_bits_differ(outr, refr) == 0
+        # round trip: reverse(forward(v)) == v  (size-independent property)
+        back = ctx.transfer_batch(s.M, tau, taup, out, reverse=True)
+        assert np.max(np.abs(back - v)) < 1e-9
+    # matrix == surface-by-surface paraxial trace (test/runtests.jl:133-145)
+    y, w, _ = ctx.paraxial_batch(s.tau, s.phi, v[:1000, 0], v[:1000, 1], arith=ort.STRICT)
+    out = ctx.transfer_batch(s.M, 0.0, 0.0, v[:1000])
+    assert np.allclose(out[:, 0], y, rtol=1e-12, atol=1e-12) and np.allclose(out[:, 1], w, rtol=1e-12, atol=1e-12)
+
+
+def test_error_paths(ctx, ort):
+    with pytest.raises(ort.OrtError):
+        ctx.set_layout(np.zeros((1, 3)))                      # rows < 2
+    ctx.set_layout(ort.prescriptions.COOKE["surfaces"])
+    with pytest.raises(ort.OrtError):
+        ctx.trace3d_grid([dict(u=0.0)], np.zeros(4), np.zeros(4), 99, 1.0)   # stop out of range
+    with pytest.raises(ort.OrtError):
+        ctx.trace3d_grid([dict(u=0.0)] * 40, np.zeros(4), np.zeros(4), 5, 1.0)   # too many fields
+
+
+def test_fp64_peak(ctx):
+    tf, ms = ctx.fp64_peak()
+    assert 10.0 < tf < 60.0, tf

@@ -1,0 +1,219 @@
+"""GPU parity of the 3-D skew tracer (K1 grid sweep, arbitrary rays, candidates) against the CPU
+oracle, called through the C ABI.  STRICT must be bit-identical (positions, mask, flags); FAST
+within 1e-12 relative (north_star tolerance) with mask and flags bit-identical."""
+import math
+
+import numpy as np
+import pytest
+
+from util import abs_rel_err, bits_equal, n_bits_differ, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12   # north_star: positions, direction cosines, OPD within 1e-12 relative in Float64
+
+
+def _inputs(pre, ort, name, H, k_rays=64):
+    P = getattr(ort.prescriptions, name)
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    return sysm, pre.full_trace_inputs(sysm, H, k_rays)
+
+
+def _oracle_grid(orc, p):
+    return orc.grid_trace(p.ext, p.ys, p.xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
+
+
+@pytest.mark.parametrize("name,H", [("COOKE", 0.0), ("COOKE", 0.7), ("COOKE", 1.0),
+                                    ("SINGLET", 0.7), ("DOUBLE_GAUSS", 0.5), ("TESSAR", 1.0)])
+def test_grid_strict_bit_exact(ctx, orc, pre, ort, name, H):
+    _, p = _inputs(pre, ort, name, H)
+    g = _oracle_grid(orc, p)
+    ctx.set_layout(p.ext, p.K)
+    r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop,
+                         arith=ort.STRICT, want=("ex", "ey", "r", "theta", "mask", "flags", "stats"))
+    assert np.array_equal(r["mask"][0], g["mask"])
+    assert np.array_equal(r["flags"][0], g["flags"])
+    assert bits_equal(r["ex"][0], g["ex"])
+    assert bits_equal(r["ey"][0], g["ey"])
+    assert bits_equal(r["r"][0], g["r"])
+    assert relerr(r["theta"][0], g["theta"]) < TOL      # atan2: CUDA libm vs glibc
+    assert int(r["stats"]["n_kept"][0]) == g["n_kept"]
+
+
+@pytest.mark.parametrize("name,H", [("COOKE", 0.0), ("COOKE", 0.7), ("COOKE", 1.0),
+                                    ("SINGLET", 1.0), ("DOUBLE_GAUSS", 0.0), ("DOUBLE_GAUSS", 1.0),
+                                    ("TESSAR", 0.7)])
+def test_grid_fast_within_tolerance_mask_exact(ctx, orc, pre, ort, name, H):
+    _, p = _inputs(pre, ort, name, H)
+    g = _oracle_grid(orc, p)
+    ctx.set_layout(p.ext, p.K)
+    r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop,
+                         arith=ort.FAST, want=("ex", "ey", "r", "theta", "mask", "flags", "stats"))
+    assert np.array_equal(r["mask"][0], g["mask"]), "clip mask must be bit-exact in FAST mode too"
+    assert np.array_equal(r["flags"][0], g["flags"])
+    scale = max(abs(p.h_prime), p.y_EP)          # positions at the image plane are O(h', y_EP)
+    # ex = xf is a position; ey = yf - h' is a difference of positions: error relative to position scale
+    assert abs_rel_err(r["ex"][0], g["ex"], scale) < TOL
+    assert abs_rel_err(r["ey"][0], g["ey"], scale) < TOL
+    assert relerr(r["r"][0], g["r"]) < TOL or abs_rel_err(r["r"][0], g["r"], p.a_stop) < TOL
+    m = g["mask"].astype(bool)
+    assert abs_rel_err(r["theta"][0][m], g["theta"][m], math.pi) < 1e-11
+
+
+def test_grid_multi_field_compact_and_stats(ctx, orc, pre, ort):
+    """Config 1: Cooke triplet, 64x64 grid (64 x 32 half pupil), 3 fields, spot RMS."""
+    P = ort.prescriptions.COOKE
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    Hs = (0.0, 0.7, 1.0)
+    ps = [pre.full_trace_inputs(sysm, H, 64) for H in Hs]
+    for arith in (ort.STRICT, ort.FAST):
+        for p, H in zip(ps, Hs):
+            g = _oracle_grid(orc, p)
+            ref = pre.full_trace(sysm, H, 64)
+            ctx.set_layout(p.ext, p.K)
+            nu = sysm.marginal.nu[-1]
+            r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop,
+                                 arith=arith, compact=True,
+                                 want=("ex", "ey", "r", "theta", "wx", "wy", "mask", "stats"),
+                                 wavegrad=(nu, 587.5618e-6))
+            st = r["stats"][0]
+            n = int(st["n_kept"])
+            assert n == g["n_kept"]
+            m = g["mask"].astype(bool)
+            scale = max(abs(p.h_prime), p.y_EP)
+            for key in ("ex", "ey", "r"):
+                assert abs_rel_err(r[key][0][:n], g[key][m], scale) < TOL, key
+            assert abs_rel_err(r["theta"][0][:n], g["theta"][m], math.pi) < 1e-11
+            # wavegrad (src/PupilSampling.jl:165-167)
+            wx = orc.wavegrad(g["ex"][m], nu)
+            assert abs_rel_err(r["wx"][0][:n], wx, scale * abs(nu) / 587.5618e-6) < TOL
+            # statistics: mirrored RMS of the reference (:139-146,169-173) from the mergeable moments
+            sxx = st["m2_x"] + n * st["mean_x"] ** 2          # mirrored x: mean 0, sum sq doubles
+            rms = math.sqrt((2 * sxx + 2 * st["m2_y"]) / (2 * n))
+            assert abs(rms / ref.RMS - 1) < TOL
+            assert abs(st["r_max"] / g["r"][m].max() - 1) < TOL
+
+
+def test_grid_edge_cases(ctx, orc, pre, ort):
+    P = ort.prescriptions.COOKE
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    p = pre.full_trace_inputs(sysm, 0.7, 64)
+    ctx.set_layout(p.ext, p.K)
+    fld = [dict(u=p.u, v=p.v, h_prime=p.h_prime)]
+    # empty grid
+    r = ctx.trace3d_grid(fld, np.zeros(0), p.xs, p.stop, p.a_stop)
+    assert int(r["stats"]["n_kept"][0]) == 0 and r["ex"].shape == (1, 0)
+    # ragged: sizes that are not multiples of the 256-ray tile, 1 x 1 grid, rays that miss / clip
+    for ys, xs in [(p.ys[:1], p.xs[:1]), (p.ys[:7], p.xs[:13]), (np.linspace(-60, 60, 33), np.linspace(0, 60, 17))]:
+        g = orc.grid_trace(p.ext, ys, xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
+        for arith in (ort.STRICT, ort.FAST):
+            r = ctx.trace3d_grid(fld, ys, xs, p.stop, p.a_stop, arith=arith, want=("ex", "ey", "mask", "flags", "stats"))
+            assert np.array_equal(r["mask"][0], g["mask"])
+            assert np.array_equal(r["flags"][0], g["flags"])
+            assert int(r["stats"]["n_kept"][0]) == g["n_kept"]
+            if arith == ort.STRICT:
+                assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
+            else:
+                assert abs_rel_err(r["ex"][0], g["ex"], 25.0) < TOL
+                assert abs_rel_err(r["ey"][0], g["ey"], 25.0) < TOL
+    # NaN coordinates propagate as NaN and are dropped
+    ys = p.ys[:4].copy(); ys[2] = np.nan
+    g = orc.grid_trace(p.ext, ys, p.xs[:4], p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
+    for arith in (ort.STRICT, ort.FAST):
+        r = ctx.trace3d_grid(fld, ys, p.xs[:4], p.stop, p.a_stop, arith=arith, want=("ex", "ey", "mask", "flags", "stats"))
+        assert np.array_equal(r["mask"][0], g["mask"])
+        assert np.array_equal(np.isnan(r["ex"][0]), np.isnan(g["ex"]))
+
+
+def test_grid_point_mode_raybasis(ctx, orc, pre, ort):
+    """RayBasis mode (src/PupilSampling.jl:124-127): per-ray slopes through tan()."""
+    P = ort.prescriptions.COOKE
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    p = pre.full_trace_inputs(sysm, 0.0, 32)
+    z0, ybar = -500.0, 12.0
+    g = orc.grid_trace(p.ext, p.ys, p.xs, p.stop, p.a_stop, 0.3, mode=1, ybar=ybar, z0=z0, K=p.K)
+    ctx.set_layout(p.ext, p.K)
+    for arith in (ort.STRICT, ort.FAST):
+        r = ctx.trace3d_grid([dict(mode=1, ybar=ybar, z0=z0, h_prime=0.3)], p.ys, p.xs, p.stop, p.a_stop,
+                             arith=arith, want=("ex", "ey", "mask", "flags", "stats"))
+        assert np.array_equal(r["mask"][0], g["mask"])
+        assert abs_rel_err(r["ex"][0], g["ex"], 25.0) < TOL     # CUDA tan vs glibc tan: <= 2 ulp
+        assert abs_rel_err(r["ey"][0], g["ey"], 25.0) < TOL
+
+
+@pytest.mark.parametrize("name", ["COOKE", "DOUBLE_GAUSS", "REFLECTIVE", "PARABOLA"])
+def test_rays_all_surfaces(ctx, orc, ort, name):
+    """raytrace(surfaces, y, x, U, V, Vector{RealRay}): every surface, direction cosines, flags."""
+    P = getattr(ort.prescriptions, name)
+    S = P["surfaces"]
+    amax = float(P["a"][0])
+    rng = np.random.default_rng(11)
+    N = 5000
+    y0 = rng.uniform(-1.3 * amax, 1.3 * amax, N)     # beyond the aperture: some rays miss
+    x0 = rng.uniform(-1.3 * amax, 1.3 * amax, N)
+    u0 = rng.uniform(-0.3, 0.3, N)
+    v0 = rng.uniform(-0.3, 0.3, N)
+    y0[:4] = [0.0, 1.0, 0.0, amax]; x0[:4] = 0.0; u0[:4] = 0.0; v0[:4] = 0.0     # on-axis rays
+    K = S[:, 3] if S.shape[1] > 3 else None
+    xo, yo, ko, fo = orc.trace3d_batch(S[:, :3], y0, x0, u0, v0, K=K)
+    ctx.set_layout(S[:, :3], K)
+    xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+    assert np.array_equal(fs, fo)
+    assert n_bits_differ(xs, xo) == 0 and n_bits_differ(ys, yo) == 0 and n_bits_differ(ks, ko) == 0
+    xf, yf, kf, ff = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
+    assert np.array_equal(ff, fo)
+    with np.errstate(all="ignore"):
+        scale = np.maximum(np.nan_to_num(np.nanmax(np.abs(np.stack([xo, yo])), axis=(0, 1)), nan=1.0), 1.0)
+    assert np.array_equal(np.isnan(xf), np.isnan(xo)) and np.array_equal(np.isnan(yf), np.isnan(yo))
+
+    def err(a, b):      # per-ray max over surfaces of |a - b| / position scale
+        with np.errstate(all="ignore"):
+            return np.nan_to_num(np.nanmax(np.abs(a - b), axis=0), nan=0.0) / scale
+
+    # These rays are deliberately wild (1.3 x aperture, slopes to 0.3): some graze a surface and are
+    # ill-conditioned -- the reference's own Float64 result is then uncertain at the 1e-12 level.
+    # Conditioning is measured against an 80-bit evaluation of the same formulas.
+    xl, yl, kl = orc.trace3d_ld_batch(S[:, :3], y0, x0, u0, v0, K=K)
+    cond = np.maximum(err(xo, xl), err(yo, yl))              # strict (= reference arithmetic) vs truth
+    e_fast = np.maximum(err(xf, xo), err(yf, yo))            # fast vs reference arithmetic
+    e_true = np.maximum(err(xf, xl), err(yf, yl))            # fast vs truth
+    well = cond < 1e-13
+    assert well.mean() > 0.99
+    assert e_fast[well].max() < TOL
+    assert np.all(e_true <= TOL / 2 + 2 * cond), "FAST must be as accurate as the reference arithmetic"
+    ok = ((fo & ort.FLAG_MISS) == 0) & well
+    assert np.max(np.abs(kf[:, ok] - ko[:, ok])) < TOL        # direction cosines are O(1)
+
+
+def test_three_d_equals_two_d(ctx, orc, ort):
+    """test/runtests.jl:355-358, 376-387: the 3-D tracer reproduces the 2-D tracer on meridional rays."""
+    for name in ("COOKE", "REFLECTIVE"):
+        S = getattr(ort.prescriptions, name)["surfaces"]
+        ctx.set_layout(S)
+        y0 = np.array([15.0 if name == "REFLECTIVE" else 14.6, 5.0, 1.0])
+        U0 = np.array([0.0, 0.05, -0.02])
+        y2, U2, ts, f2 = ctx.trace2d_batch(y0, U0)
+        xv, yv, k, f3 = ctx.trace3d_rays(y0, np.zeros(3), np.tan(U0), np.zeros(3), arith=ort.STRICT)
+        assert np.allclose(yv, y2[1:], rtol=1e-13, atol=1e-13)
+        assert np.all(xv == 0.0)
+
+
+def test_candidates(ctx, orc, pre, ort):
+    P = ort.prescriptions.COOKE
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    p = pre.full_trace_inputs(sysm, 0.7, 64)
+    C = 96
+    base = ort.prescriptions.perturbed_triplets(C)
+    rows = p.ext.shape[0]
+    RtnK = np.zeros((C, 4, rows))
+    RtnK[:, :, :-1] = base
+    RtnK[:, 0, -1] = np.inf; RtnK[:, 2, -1] = 1.0
+    RtnK[:, 1, -2] = p.focus
+    ys = np.linspace(p.y1, p.y2, 32)
+    xs = np.linspace(-p.y_EP, p.y_EP, 32)
+    ref = orc.candidates(RtnK, ys, xs, p.stop, p.a_stop, p.h_prime, p.u)
+    for arith in (ort.STRICT, ort.FAST):
+        out = ctx.trace3d_candidates(RtnK, dict(u=p.u, v=0.0, h_prime=p.h_prime), ys, xs, p.stop, p.a_stop, arith=arith)
+        assert np.array_equal(out[:, 0], ref[:, 0])                 # kept counts exact
+        assert np.max(np.abs(out[:, 1:3] - ref[:, 1:3])) / 25.0 < TOL
+        assert np.max(np.abs(out[:, 3] / ref[:, 3] - 1)) < 1e-11     # RMS about the centroid
