@@ -77,6 +77,9 @@ typedef struct ort_opts {
                          1: ex, ey, r, theta (and wx, wy) are compacted per field in the reference's push!
                             order (PupilSampling.jl:134-137); field f's segment still starts at f*ny*nx and
                             holds stats[f].n_kept entries. */
+    int32_t ys_per_field; /* 0: ys[ny] shared by all fields.  1: ys[n_fields][ny], each field has its own
+                             aimed y-range (the reference aims y1, y2 per field, PupilSampling.jl:99-100,121) */
+    int32_t reserved;
     double  wg_nu;    /* wavegrad (PupilSampling.jl:165-167): wx = ex*wg_nu/wg_lambda.  Used iff wx/wy given. */
     double  wg_lambda;
 } ort_opts;
@@ -112,6 +115,12 @@ int         ort_device_info(ort_ctx *ctx, int *sm_count, int *cc_major, int *cc_
 void       *ort_host_alloc(size_t bytes);                  /* pinned host memory for fast D2H/H2D */
 void        ort_host_free(void *p);
 int64_t     ort_launch_count(ort_ctx *ctx);                /* kernels launched by this context so far */
+/* Measurement: when enabled, the dominant kernel of every trace3d_grid / paraxial / transfer /
+ * candidates call is bracketed by a CUDA event pair on the launching stream (ring of 64).
+ * ort_profile_read synchronises those events and returns the most recent n <= max_n durations (ms,
+ * oldest first), then clears the ring. */
+int         ort_profile_enable(ort_ctx *ctx, int on);
+int         ort_profile_read(ort_ctx *ctx, double *ms_out, int max_n);
 
 /* Prescription = the data contract of Layout (src/Types.jl:82-95): rows x [R t n K], row 1 = object
  * space.  K may be NULL (zeros, Layout{Spherical}).  Aspheric polynomial terms `p` are Julia closures

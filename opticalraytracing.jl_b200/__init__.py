@@ -6,9 +6,18 @@ libort_b200.so (include/ort_b200.h).  The Julia shim a maintainer would add is i
 julia/OpticalRayTracingB200.jl; Julia is not installed in this environment, so this Python
 mirror is what drives the same ABI in tests and benchmarks.
 """
-from . import _lib, prescriptions
+from . import _lib, host, prescriptions
 from ._lib import (FAST, STRICT, FLAG_CLIP, FLAG_DOMAIN, FLAG_MISS, FLAG_TIR, Context, OrtError,
                    PinnedArray, STATS_DTYPE)
+from .host import (LAMBDA, SA, TSA, Layout, Lens, RayBasis, RealRay, RealRayError, System,
+                   VectorRealRay, flatten, full_trace, full_trace_fields, make_lens, merge_stats,
+                   raytrace, reverse_transfer, rms_from_stats, set_default_backend, solve,
+                   trace_chief_ray, trace_edge_rays, trace_marginal_ray, transfer, transfer_matrix,
+                   wavegrad)
 
-__all__ = ["_lib", "prescriptions", "Context", "OrtError", "PinnedArray", "STATS_DTYPE", "FAST",
-           "STRICT", "FLAG_MISS", "FLAG_TIR", "FLAG_DOMAIN", "FLAG_CLIP"]
+__all__ = ["_lib", "host", "prescriptions", "Context", "OrtError", "PinnedArray", "STATS_DTYPE", "FAST",
+           "STRICT", "FLAG_MISS", "FLAG_TIR", "FLAG_DOMAIN", "FLAG_CLIP", "LAMBDA", "SA", "TSA",
+           "Layout", "Lens", "RayBasis", "RealRay", "RealRayError", "System", "VectorRealRay",
+           "flatten", "full_trace", "full_trace_fields", "make_lens", "merge_stats", "raytrace",
+           "reverse_transfer", "rms_from_stats", "set_default_backend", "solve", "trace_chief_ray",
+           "trace_edge_rays", "trace_marginal_ray", "transfer", "transfer_matrix", "wavegrad"]

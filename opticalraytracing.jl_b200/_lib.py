@@ -19,7 +19,8 @@ STRICT, FAST = 0, 1
 # every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
-    "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_set_layout",
+    "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
+    "ort_set_layout",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace2d_batch",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_fp64_peak",
@@ -42,8 +43,8 @@ class Field(C.Structure):
 
 
 class Opts(C.Structure):
-    _fields_ = [("arith", C.c_int32), ("compact", C.c_int32), ("wg_nu", C.c_double),
-                ("wg_lambda", C.c_double)]
+    _fields_ = [("arith", C.c_int32), ("compact", C.c_int32), ("ys_per_field", C.c_int32),
+                ("reserved", C.c_int32), ("wg_nu", C.c_double), ("wg_lambda", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -93,6 +94,8 @@ def load():
     L.ort_host_free.restype = None
     L.ort_launch_count.argtypes = [C.c_void_p]
     L.ort_launch_count.restype = C.c_int64
+    L.ort_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.ort_profile_read.argtypes = [C.c_void_p, _dp, C.c_int]
     L.ort_set_layout.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
     grid_args = [C.c_void_p, C.POINTER(Field), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                  C.c_int, C.c_double, C.POINTER(Opts), C.POINTER(GridOut)]
@@ -211,6 +214,17 @@ class Context:
     def launch_count(self):
         return int(self.L.ort_launch_count(self.h))
 
+    def profile_enable(self, on=True):
+        self._ck(self.L.ort_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """kernel durations (ms) of the dominant kernel of the calls since the last read (<= 64)"""
+        buf = np.empty(64)
+        n = self.L.ort_profile_read(self.h, _p(buf), 64)
+        if n < 0:
+            self._ck(n)
+        return buf[:n].copy()
+
     def fp64_peak(self):
         t, ms = C.c_double(), C.c_double()
         self._ck(self.L.ort_fp64_peak(self.h, C.byref(t), C.byref(ms)))
@@ -233,7 +247,10 @@ class Context:
         (+ 'stats' structured array).  `out` may supply preallocated (e.g. pinned) arrays."""
         farr, nf = make_fields(fields)
         ys, xs = _d(ys), _d(xs)
-        ny, nx = len(ys), len(xs)
+        per_field = ys.ndim == 2          # ys[n_fields][ny]: every field has its own aimed y-range
+        if per_field and ys.shape[0] != nf:
+            raise ValueError("ys must be (ny,) or (n_fields, ny)")
+        ny, nx = ys.shape[-1], len(xs)
         NN = ny * nx
         res = dict(out) if out else {}
         for name in ("ex", "ey", "r", "theta", "wx", "wy"):
@@ -247,19 +264,19 @@ class Context:
                        for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags")],
                      stats.ctypes.data)
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
-        op = Opts(int(arith), int(bool(compact)), float(nu), float(lam))
+        op = Opts(int(arith), int(bool(compact)), int(per_field), 0, float(nu), float(lam))
         self._ck(self.L.ort_trace3d_grid(self.h, farr, nf, _vp(ys), ny, _vp(xs), nx, int(stop),
                                          float(a_stop), C.byref(op), C.byref(go)))
         res["stats"] = stats
         return res
 
     def trace3d_grid_dev(self, fields, d_ys, ny, d_xs, nx, stop, a_stop, ptrs, stream=0,
-                         arith=FAST, compact=False, wavegrad=None):
+                         arith=FAST, compact=False, wavegrad=None, ys_per_field=False):
         """Device-pointer grid sweep (enqueue only).  ptrs: dict name -> device address (int)."""
         farr, nf = make_fields(fields)
         go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags", "stats")])
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
-        op = Opts(int(arith), int(bool(compact)), float(nu), float(lam))
+        op = Opts(int(arith), int(bool(compact)), int(bool(ys_per_field)), 0, float(nu), float(lam))
         self._ck(self.L.ort_trace3d_grid_dev(self.h, farr, nf, C.c_void_p(d_ys), int(ny), C.c_void_p(d_xs),
                                              int(nx), int(stop), float(a_stop), C.byref(op), C.byref(go),
                                              C.c_void_p(stream)))

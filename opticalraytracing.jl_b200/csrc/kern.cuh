@@ -5,6 +5,7 @@
 struct GridArgs {
     const double* ys; const double* xs;     // device: grid coordinates (:121-122)
     int ny, nx;
+    int ys_stride;                          // 0: ys shared by all fields; ny: one ys row per field
     unsigned NN;                            // ny * nx  (< 2^31)
     int stop;                               // 1-based system.stop
     double a_stop, a_stop2;

@@ -127,7 +127,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         int kept = 0;
         if (i < NN) {
             const unsigned iy = i / (unsigned)A.nx, ix = i - iy * (unsigned)A.nx;   // y outer, x inner (:123)
-            const double y0 = __ldg(A.ys + iy), x0 = __ldg(A.xs + ix);
+            const double y0 = __ldg(A.ys + (size_t)f * A.ys_stride + iy), x0 = __ldg(A.xs + ix);
             double u = fld.u, v = fld.v;
             if (fld.mode == 1) {                         // RayBasis: :124-127 then tan at :38-39
                 u = tan(SD(SS(fld.ybar, y0), fld.z0));

@@ -39,6 +39,9 @@ struct ort_ctx {
     void* slot[SL_COUNT];
     size_t slot_bytes[SL_COUNT];
     long long launches;
+    int prof_on;
+    long long prof_n;               // event pairs recorded since the last read
+    cudaEvent_t prof_ev[64][2];
     char err[512];
 };
 
@@ -92,6 +95,19 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     S.refr = (n1 != n2);
 }
 
+// bracket the dominant kernel with an event pair (measurement only)
+struct ProfScope {
+    ort_ctx* c; cudaStream_t st; int slot;
+    ProfScope(ort_ctx* c_, cudaStream_t st_) : c(c_), st(st_), slot(-1)
+    {
+        if (c->prof_on) { slot = (int)(c->prof_n % 64); cudaEventRecord(c->prof_ev[slot][0], st); }
+    }
+    ~ProfScope()
+    {
+        if (slot >= 0) { cudaEventRecord(c->prof_ev[slot][1], st); c->prof_n++; }
+    }
+};
+
 int resolve_arith(const ort_ctx* ctx, int arith)
 {
     if (arith == ORT_ARITH_FAST && !ctx->presc.fast_ok) return ORT_ARITH_STRICT;
@@ -138,6 +154,7 @@ int ort_init(ort_ctx** out, int device)
     CKI(cudaEventCreate(&ctx->ev_a));
     CKI(cudaEventCreate(&ctx->ev_b));
     for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
+    for (int i = 0; i < 64; i++) { CKI(cudaEventCreate(&ctx->prof_ev[i][0])); CKI(cudaEventCreate(&ctx->prof_ev[i][1])); }
 #undef CKI
     ctx->bps[ORT_ARITH_STRICT] = grid_blocks_per_sm(ORT_ARITH_STRICT);
     ctx->bps[ORT_ARITH_FAST] = grid_blocks_per_sm(ORT_ARITH_FAST);
@@ -153,6 +170,7 @@ void ort_free(ort_ctx* ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < SL_COUNT; i++) if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     for (int i = 0; i < ORT_MAX_FIELDS; i++) cudaEventDestroy(ctx->ev_field[i]);
+    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -187,6 +205,31 @@ void* ort_host_alloc(size_t bytes)
 void ort_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int64_t ort_launch_count(ort_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ort_profile_enable(ort_ctx* ctx, int on)
+{
+    if (!ctx) return ORT_EINVAL;
+    ctx->prof_on = on ? 1 : 0;
+    ctx->prof_n = 0;
+    return ORT_OK;
+}
+
+int ort_profile_read(ort_ctx* ctx, double* ms_out, int max_n)
+{
+    if (!ctx || !ms_out || max_n < 0) return ORT_EINVAL;
+    long long n = ctx->prof_n < 64 ? ctx->prof_n : 64;
+    if (n > max_n) n = max_n;
+    const long long first = ctx->prof_n - n;
+    for (long long j = 0; j < n; j++) {
+        const int slot = (int)((first + j) % 64);
+        if (cudaEventSynchronize(ctx->prof_ev[slot][1]) != cudaSuccess) return ORT_ECUDA;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->prof_ev[slot][0], ctx->prof_ev[slot][1]) != cudaSuccess) return ORT_ECUDA;
+        ms_out[j] = (double)t;
+    }
+    ctx->prof_n = 0;
+    return (int)n;
+}
 
 int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, const double* n, const double* K)
 {
@@ -241,6 +284,7 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
     GridArgs A;
     memset(&A, 0, sizeof A);
     A.ys = d_ys; A.xs = d_xs; A.ny = ny; A.nx = nx; A.NN = NN; A.stop = stop;
+    A.ys_stride = opts->ys_per_field ? ny : 0;
     A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
     A.wg_nu = opts->wg_nu; A.wg_lambda = opts->wg_lambda;
     A.ex = full.ex; A.ey = full.ey; A.r = full.r; A.theta = full.theta; A.wx = full.wx; A.wy = full.wy;
@@ -250,6 +294,7 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
     memcpy(A.fields, fields, sizeof(ort_field) * (size_t)n_fields);
     const int arith = resolve_arith(ctx, opts->arith);
     if (NN > 0) {
+        ProfScope prof(ctx, st);
         CK(launch_grid(ctx->presc, A, arith, dim3((unsigned)gx, (unsigned)n_fields), st));
         ctx->launches++;
     } else {
@@ -325,7 +370,8 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     // one launch per field so the D2H of field f overlaps the trace of field f+1
     const int gx = grid_dims(ctx, arith, 1, NN);
     double *d_ys, *d_xs;
-    ENSURE(SL_YS, sizeof(double) * (size_t)ny, d_ys);
+    const size_t nys = (size_t)ny * (opts->ys_per_field ? n_fields : 1);
+    ENSURE(SL_YS, sizeof(double) * nys, d_ys);
     ENSURE(SL_XS, sizeof(double) * (size_t)nx, d_xs);
     Part* d_partials; ENSURE(SL_PARTIALS, sizeof(Part) * (size_t)gx * n_fields, d_partials);
     ort_stats* d_stats; ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
@@ -351,7 +397,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         if (out->wy) ENSURE(SL_CWY, tot * 8, comp.wy);
     }
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-    CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * (size_t)ny, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * nys, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_xs, xs, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
     ort_stats hstats[ORT_MAX_FIELDS];
     for (int f = 0; f < n_fields; f++) {
@@ -361,7 +407,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         OFF(ff.ex); OFF(ff.ey); OFF(ff.r); OFF(ff.theta); OFF(ff.wx); OFF(ff.wy); OFF(ff.mask); OFF(ff.flags);
         OFF(cc.ex); OFF(cc.ey); OFF(cc.r); OFF(cc.theta); OFF(cc.wx); OFF(cc.wy);
 #undef OFF
-        rc = grid_enqueue(ctx, fields + f, 1, d_ys, ny, d_xs, nx, stop, a_stop, opts, ff,
+        rc = grid_enqueue(ctx, fields + f, 1, d_ys + (opts->ys_per_field ? (size_t)f * ny : 0), ny, d_xs, nx, stop, a_stop, opts, ff,
                           opts->compact ? &cc : nullptr, d_stats + f, d_partials + (size_t)f * gx,
                           d_tiles ? d_tiles + (size_t)f * (ntiles + 1) : nullptr, gx, st);
         if (rc) return rc;
@@ -481,7 +527,10 @@ int ort_paraxial_batch_dev(ort_ctx* ctx, int k, const double* tau, const double*
     ParaxArgs A; memset(&A, 0, sizeof A);
     A.N = N; A.y0 = d_y0; A.w0 = d_w0; A.y = d_y; A.w = d_w; A.clip_idx = d_clip_idx;
     A.y_all = d_y_all; A.w_all = d_w_all;
-    CK(launch_paraxial(L, A, arith, (cudaStream_t)stream));
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_paraxial(L, A, arith, (cudaStream_t)stream));
+    }
     if (N > 0) ctx->launches++;
     return ORT_OK;
 }
@@ -545,7 +594,10 @@ int ort_transfer_batch_dev(ort_ctx* ctx, const double M[4], double tau, double t
     mm2_host(T, Rm, A.E);
     A.N = N; A.reverse = reverse ? 1 : 0;
     A.v_in = (const double2*)d_v_in; A.v_out = (double2*)d_v_out;
-    CK(launch_transfer(A, (cudaStream_t)stream));
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_transfer(A, (cudaStream_t)stream));
+    }
     if (N > 0) ctx->launches++;
     return ORT_OK;
 }
@@ -585,7 +637,10 @@ int ort_trace3d_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* 
     A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.ys = d_ys; A.xs = d_xs; A.ny = ny; A.nx = nx;
     A.stop = stop; A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
     A.u = field->u; A.v = field->v; A.h_prime = field->h_prime; A.out = d_out;
-    CK(launch_candidates(A, arith, (cudaStream_t)stream));
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_candidates(A, arith, (cudaStream_t)stream));
+    }
     if (C > 0) ctx->launches++;
     return ORT_OK;
 }

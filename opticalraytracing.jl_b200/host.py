@@ -1,0 +1,639 @@
+"""Host-side mirror of the reference's public API for the hot path.
+
+Same names, argument meaning and error behaviour as Sagnac/OpticalRayTracing.jl
+(src/OpticalRayTracing.jl:6-50): solve, raytrace, trace_marginal_ray, trace_chief_ray,
+full_trace, transfer, reverse_transfer, flatten, wavegrad, TSA, SA, Layout, Lens, TransferMatrix.
+Every ray that is traced -- single rays of the prelude included -- goes through the C ABI of
+libort_b200.so (`backend`, default: a GPU Context).  There is no CPU fallback; tests may inject
+another backend object to exercise the host logic without a GPU.
+
+Julia is 1-based; the `stop` fields here keep the reference's 1-based value.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+EPS = math.sqrt(np.finfo(np.float64).eps)   # const eps = sqrt(eps())          src/RayTracing.jl:1
+K_RAYS = 22                                 # const k_rays                     src/RayTracing.jl:4
+SPOT_RAYS = 64                              # const spot_rays                  src/RayTracing.jl:7
+LAMBDA = 587.5618e-6                        # He d-line, mm                    src/SeidelAberrations.jl:2
+
+
+class RealRay:            # dispatch tag: raytrace(surfaces, y, U, RealRay)            RayTracing.jl:145
+    pass
+
+
+class VectorRealRay:      # dispatch tag: raytrace(surfaces, y, x, U, V, Vector{RealRay})  PupilSampling.jl:34
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# backend
+# ------------------------------------------------------------------------------------------------
+_default_backend = None
+
+
+def default_backend():
+    """The process-wide GPU context (device = LOCAL_RANK or 0).  Raises if no B200 is usable."""
+    global _default_backend
+    if _default_backend is None:
+        import os
+        _default_backend = _lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_backend
+
+
+def set_default_backend(b):
+    global _default_backend
+    _default_backend = b
+
+
+def _be(backend):
+    return backend if backend is not None else default_backend()
+
+
+# ------------------------------------------------------------------------------------------------
+# types (src/Types.jl)
+# ------------------------------------------------------------------------------------------------
+class Layout:
+    """Layout{Spherical|Aspheric} (src/Types.jl:82-112): columns R, t, n, K.  Polynomial terms `p`
+    are arbitrary Julia closures in the reference and cannot cross the C ABI: only p == zero."""
+
+    def __init__(self, M, K=None, aspheric=None, p=None):
+        if p is not None and any(pi is not None for pi in np.atleast_1d(p)):
+            raise ValueError("ort_b200: aspheric polynomial terms p != zero are not supported on the GPU path")
+        M = np.array(M, dtype=np.float64)
+        if M.ndim != 2 or M.shape[1] < 3:
+            raise ValueError("Layout needs rows of [R t n] or [R t n K]")
+        if K is None and M.shape[1] > 3:
+            K = M[:, 3]
+            if aspheric is None:
+                aspheric = True
+        self.R, self.t, self.n = M[:, 0].copy(), M[:, 1].copy(), M[:, 2].copy()
+        self.K = np.zeros(len(self.R)) if K is None else np.array(K, dtype=np.float64)
+        self.aspheric = bool(aspheric)
+
+    @property
+    def M3(self):
+        return np.column_stack([self.R, self.t, self.n])
+
+    def __len__(self):
+        return len(self.R)
+
+
+def _as_layout(surfaces):
+    return surfaces if isinstance(surfaces, Layout) else Layout(surfaces)
+
+
+@dataclass
+class Lens:
+    """Lens (src/Types.jl:77-80): k x 2 [tau phi] and n."""
+    M: np.ndarray
+    n: np.ndarray
+
+    @property
+    def tau(self):
+        return self.M[:, 0]
+
+    @property
+    def phi(self):
+        return self.M[:, 1]
+
+
+def make_lens(surfaces):
+    """Lens(surfaces) -- src/RayTracing.jl:38-53 (O(k) host arithmetic, no rays)."""
+    L = _as_layout(surfaces)
+    R, t, n = L.R, L.t.copy(), L.n
+    rows = len(R)
+    if not math.isfinite(t[0]):
+        t[0] = 0.0
+    M = np.empty((rows, 2))
+    M[:, 0] = t / n
+    for i in range(rows - 1):
+        M[i, 1] = (n[i + 1] - n[i]) / R[i + 1]
+    if t[-1] == 0.0 or not math.isfinite(t[-1]):
+        M = M[:-1, :].copy()
+    else:
+        M[-1, 1] = 0.0
+    return Lens(M, n.copy())
+
+
+class ParaxialRay:
+    """ParaxialRay{T}(ynu, tau, n) -- src/Types.jl:29-51"""
+
+    def __init__(self, ynu, tau, n, fundamental):
+        ynu = np.array(ynu, dtype=np.float64)
+        y, nu = ynu[:, 0].copy(), ynu[:, 1].copy()
+        n_ext = np.append(n, n[-1])
+        m = min(len(nu), len(n_ext))
+        u = nu[:m] / n_ext[:m]
+        mt = min(len(tau), len(n_ext) - 2)
+        t = np.asarray(tau[:mt]) * n_ext[:mt]
+        if fundamental:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = np.append(t, -y[-2] / u[-2])
+        z = np.cumsum(t)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z0 = (z.min() - z.max()) * 0.1 if u[0] == 0.0 else -y[1] / u[0]
+        self.y, self.n, self.u, self.nu, self.ynu = y, n_ext, u, nu, ynu
+        self.yu = np.column_stack([y[:m], u])
+        self.z = np.concatenate([[z0], z])
+
+
+@dataclass
+class RealRayData:
+    """RealRay{T} (src/Types.jl:53-63)"""
+    y: np.ndarray
+    u: np.ndarray
+    yu: np.ndarray
+    n: np.ndarray
+    z: np.ndarray
+    flags: int = 0
+
+
+@dataclass
+class Pupil:
+    D: float
+    t: float
+
+
+@dataclass
+class System:
+    """System (src/Types.jl:119-139)"""
+    f: float
+    EBFD: float
+    EFFD: float
+    N: float
+    FOV: float
+    stop: int
+    EP: Pupil
+    XP: Pupil
+    marginal: ParaxialRay
+    chief: ParaxialRay
+    trace: np.ndarray
+    H: float
+    P1: float
+    P2: float
+    PN: float
+    M: np.ndarray
+    lens: Lens
+    a: np.ndarray
+    layout: Layout
+
+
+@dataclass
+class RayBasis:
+    """RayBasis (src/Types.jl:65-71)"""
+    marginal: ParaxialRay
+    chief: ParaxialRay
+    H: float
+    a: np.ndarray
+    stop: int
+
+
+@dataclass
+class RealRayError:
+    """RealRayError (src/Types.jl:184-192)"""
+    x: np.ndarray
+    y: np.ndarray
+    nu: float
+    r: np.ndarray
+    t: np.ndarray
+    H: float
+    RMS: float
+    stats: Optional[np.ndarray] = field(default=None, repr=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# paraxial path
+# ------------------------------------------------------------------------------------------------
+def raytrace_paraxial(lens, y, w, a=None, clip=False, backend=None):
+    """raytrace(lens::Lens, y, w, a; clip) -- src/RayTracing.jl:127-143.  Scalars -> one
+    ParaxialRay{Tangential}; arrays -> (y_table, nu_table, clip_idx) with shape (k+1, N)."""
+    if not isinstance(lens, Lens):
+        lens = make_lens(lens)                                   # :175-178
+    be = _be(backend)
+    scalar = np.isscalar(y) and np.isscalar(w)
+    y0, w0 = np.atleast_1d(np.asarray(y, dtype=np.float64)), np.atleast_1d(np.asarray(w, dtype=np.float64))
+    y0, w0 = np.broadcast_arrays(y0, w0)
+    yf, wf, ci, ya, wa = be.paraxial_batch(lens.tau, lens.phi, y0, w0, a=a, clip=clip and a is not None,
+                                           arith=_lib.STRICT, table=True)
+    if scalar:
+        return ParaxialRay(np.column_stack([ya[:, 0], wa[:, 0]]), lens.tau, lens.n, False)
+    return ya, wa, ci
+
+
+def transfer_matrix(lens):
+    """TransferMatrix(lens) -- src/TransferMatrix.jl:1-6: M_k * ... * M_1 (left fold); O(k) host."""
+    tau, phi = lens.tau, lens.phi
+    acc = None
+    for i in range(len(tau) - 1, -1, -1):
+        Mi = np.array([[1.0, tau[i]], [-phi[i], 1.0 - tau[i] * phi[i]]])
+        acc = Mi if acc is None else _mm2(acc, Mi)
+    return acc
+
+
+def _mm2(A, B):
+    return np.array([[A[0, 0] * B[0, 0] + A[0, 1] * B[1, 0], A[0, 0] * B[0, 1] + A[0, 1] * B[1, 1]],
+                     [A[1, 0] * B[0, 0] + A[1, 1] * B[1, 0], A[1, 0] * B[0, 1] + A[1, 1] * B[1, 1]]])
+
+
+def _matrix_of(M):
+    return M.M if isinstance(M, System) else np.asarray(M, dtype=np.float64)
+
+
+def transfer(M, v, tau, taup, backend=None):
+    """transfer(M | system, v, tau, taup) -- src/TransferMatrix.jl:8-11.  v: [y, nu] or (N, 2)."""
+    v = np.asarray(v, dtype=np.float64)
+    out = _be(backend).transfer_batch(_matrix_of(M), tau, taup, np.atleast_2d(v))
+    return out[0] if v.ndim == 1 else out
+
+
+def reverse_transfer(M, v, taup, tau, backend=None):
+    """reverse_transfer(M | system, v, taup, tau) -- src/TransferMatrix.jl:13-17"""
+    v = np.asarray(v, dtype=np.float64)
+    out = _be(backend).transfer_batch(_matrix_of(M), tau, taup, np.atleast_2d(v), reverse=True)
+    return out[0] if v.ndim == 1 else out
+
+
+def flatten(M):
+    """flatten(M) -- cardinal points, src/TransferMatrix.jl:19-28"""
+    M = _matrix_of(M)
+    f = -1.0 / M[1, 0]
+    EFFD = -M[1, 1] * f
+    EBFD = M[0, 0] * f
+    return dict(f=f, EFFD=EFFD, EBFD=EBFD, P1=EFFD + f, P2=EBFD - f)
+
+
+def solve(surfaces, a, h_prime=-0.5, backend=None):
+    """solve(surfaces | layout, a, h') -- src/RayTracing.jl:302-335.  The two fundamental paraxial
+    rays are traced by the paraxial kernel; the rest is O(k) host algebra."""
+    layout = _as_layout(surfaces)
+    a = np.asarray(a, dtype=np.float64)
+    lens = make_lens(layout)
+    tau, phi, n = lens.tau, lens.phi, lens.n
+    be = _be(backend)
+    # both fundamental rays in one launch: (y, w) = (1, 0) and (0, 1)   :209, :252
+    _, _, _, ya, wa = be.paraxial_batch(tau, phi, np.array([1.0, 0.0]), np.array([0.0, 1.0]),
+                                        arith=_lib.STRICT, table=True)
+    rt = np.column_stack([ya[:, 0], wa[:, 0]])
+    rt2 = np.column_stack([ya[:, 1], wa[:, 1]])
+    y, w = rt[:, 0], rt[:, 1]
+    f = -1.0 / w[-1]                                             # :213
+    EBFD = y[-1] * f
+    sv = a / y[1:]
+    stop = int(np.argmin(sv)) + 1                                # findmin :216
+    s = sv[stop - 1]
+    mr = rt * s
+    wf = mr[-1, 1]
+    yf = mr[-1, 0] if wf == 0.0 else 0.0                         # extend :202-206
+    mr = np.vstack([mr, [yf, wf]])
+    marginal = ParaxialRay(mr, tau, n, True)
+    ys_, ynu_s = marginal.y[1:-1], marginal.ynu[1:-1, :]         # trace_chief_ray :246-263
+    y_stop = ys_[stop - 1]
+    ynu2 = rt2[1:, :]
+    y2_stop = ynu2[stop - 1, 0]
+    nub = -marginal.nu[-1] * h_prime / ys_[0]
+    cr = np.empty_like(marginal.ynu)
+    cr[1:-1, :] = nub * (ynu2 - ynu_s * y2_stop / y_stop)
+    cr[0, :] = (0.0, nub)
+    cr[-1, :] = (h_prime, cr[-2, 1])
+    chief = ParaxialRay(cr, tau, n, True)
+    yb, nub0, nup = chief.y[1], chief.nu[0], chief.nu[-1]        # _solve :302-323
+    ym, ypb = marginal.y[0], chief.y[-2]
+    dp = EBFD - f
+    d = (h_prime - nup * f - yb) / nub0
+    EFFD = d - f
+    PN = (n[-1] - n[0]) * f
+    EP = Pupil(abs(ym) * 2, -yb / nub0)
+    H = nub0 * ym
+    XP = Pupil(abs(2 * H / nup), -ypb / nup)
+    Nn = abs(f / EP.D)
+    FOV = 2 * math.degrees(math.atan(abs(chief.u[0])))
+    M = transfer_matrix(lens)
+    return System(f, EBFD, EFFD, Nn, FOV, stop, EP, XP, marginal, chief,
+                  np.column_stack([marginal.yu, chief.yu]), H, d, dp, PN, M, lens, a, layout)
+
+
+def raybasis(system, ybar, s):
+    """raytrace(system::System, ybar, s) -- finite-conjugate RayBasis, src/RayTracing.jl:180-200"""
+    y = system.marginal.y[0]
+    EP_O = s - system.EP.t
+    nu = -y / EP_O
+    nub = ybar / EP_O
+    al = y * nu / system.H
+    be = y * nub / system.H
+    mr = system.marginal.ynu + al * system.chief.ynu
+    cr = be * system.chief.ynu
+    H = nub * y
+    mr[-1, 0] = 0.0
+    cr[-1, 0] = -H / mr[-1, 1]
+    tau = system.lens.tau
+    return RayBasis(ParaxialRay(mr, tau, system.lens.n, True), ParaxialRay(cr, tau, system.lens.n, True),
+                    H, system.a, system.stop)
+
+
+# ------------------------------------------------------------------------------------------------
+# real rays
+# ------------------------------------------------------------------------------------------------
+def _trace2d(layout, y, U, aspheric, backend):
+    be = _be(backend)
+    be.set_layout(layout.M3, layout.K)
+    return be.trace2d_batch(np.atleast_1d(y), np.atleast_1d(U), aspheric=aspheric)
+
+
+def _real_ray(layout, yo, Uo, ts, fl, j):
+    yu = np.column_stack([yo[:, j], Uo[:, j]])
+    return RealRayData(yu[:, 0].copy(), yu[:, 1].copy(), yu, layout.n.copy(), np.cumsum(ts[:, j]), int(fl[j]))
+
+
+def raytrace(surfaces, *args, a=None, clip=False, backend=None):
+    """The reference's `raytrace` generic, dispatched on the trailing tag like Julia dispatches on type:
+       raytrace(lens | surfaces, y, w[, a]; clip)               paraxial          RayTracing.jl:127-143,175-178
+       raytrace(surfaces, y, U, RealRay)                        2-D meridional    RayTracing.jl:145-173
+       raytrace(surfaces, y, x, U, V, VectorRealRay)            3-D skew          PupilSampling.jl:34-65
+       raytrace(system, ybar, s)                                RayBasis          RayTracing.jl:180-200
+    y, U, ... may be arrays: the batch is traced in one kernel launch."""
+    if isinstance(surfaces, System) and len(args) == 2:
+        return raybasis(surfaces, *args)
+    if args and args[-1] is RealRay:
+        y, U = args[0], args[1]
+        layout = _as_layout(surfaces)
+        # Layout{Aspheric} method (:171-173) -> K from the layout, atan branch; else asin branch (:162)
+        yo, Uo, ts, fl = _trace2d(layout, y, U, layout.aspheric, backend)
+        if np.isscalar(y) and np.isscalar(U):
+            return _real_ray(layout, yo, Uo, ts, fl, 0)
+        return yo, Uo, ts, fl
+    if args and args[-1] is VectorRealRay:
+        y, x, U, V = args[:4]
+        layout = _as_layout(surfaces)
+        be = _be(backend)
+        be.set_layout(layout.M3, layout.K)
+        y0, x0, U0, V0 = np.broadcast_arrays(*(np.atleast_1d(np.asarray(q, dtype=np.float64)) for q in (y, x, U, V)))
+        xv, yv, k, fl = be.trace3d_rays(y0, x0, np.tan(U0), np.tan(V0), arith=_lib.STRICT)   # tan: :38-39
+        if all(np.isscalar(q) for q in (y, x, U, V)):
+            return xv[:, 0], yv[:, 0]
+        return xv, yv
+    if len(args) in (2, 3):
+        aa = args[2] if len(args) == 3 else a
+        return raytrace_paraxial(surfaces, args[0], args[1], a=aa, clip=clip, backend=backend)
+    raise TypeError("raytrace: no method matching the given arguments")
+
+
+def trace_marginal_ray(surfaces, system, atol=EPS, backend=None):
+    """Real marginal ray aimed at the stop edge -- src/RayTracing.jl:223-240.  Each secant step
+    traces (y, y + eps) as one 2-ray batch."""
+    layout = _as_layout(surfaces)
+    stop = system.stop
+    y = system.marginal.y[0]
+    a_stop = system.a[stop - 1]
+    for _ in range(100):
+        yo, Uo, ts, fl = _trace2d(layout, np.array([y, y + EPS]), np.zeros(2), layout.aspheric, backend)
+        d = yo[stop, 0] - a_stop
+        if not abs(d) > atol:
+            break
+        dy = yo[stop, 1] - a_stop
+        y -= d * EPS / (dy - d)
+    else:
+        raise RuntimeError("trace_marginal_ray did not converge")
+    ray = _real_ray(layout, yo, Uo, ts, fl, 0)
+    z = ray.z.copy()
+    z[-1] = z[-2] - ray.y[-1] / math.tan(ray.u[-1])              # :234
+    z = np.concatenate([[(z.min() - z.max()) * 0.1], z])         # :235
+    yv, uv = np.append(ray.y, 0.0), np.append(ray.u, ray.u[-1])
+    return RealRayData(yv, uv, np.vstack([ray.yu, [0.0, ray.u[-1]]]), ray.n, z)
+
+
+def trace_chief_ray(surfaces, system, atol=EPS, backend=None):
+    """Real chief ray through the stop centre, traced backwards -- src/RayTracing.jl:265-296.
+    `surfaces isa Layout` (:272-277) makes the reversed system a Layout{Aspheric} whose K is
+    reverse(K) -- shifted one row against rev_R -- exactly as the reference does."""
+    is_layout = isinstance(surfaces, Layout)
+    L = _as_layout(surfaces)
+    rows = len(L)
+    rev_R = -np.concatenate([[np.inf], L.R[:0:-1]])
+    rev_t = L.t[::-1].copy()
+    rev_n = L.n[::-1].copy()
+    m = system.marginal
+    rev_t[0] = m.z[-1] - m.z[-2]
+    rev = Layout(np.column_stack([rev_R, rev_t, rev_n]), K=L.K[::-1].copy() if is_layout else None,
+                 aspheric=is_layout)
+    stop = rows - system.stop
+    ybp = system.chief.y[-1]
+    ubp = -system.chief.u[-1]
+    for _ in range(100):
+        yo, Uo, ts, fl = _trace2d(rev, np.array([ybp, ybp]), np.array([ubp, ubp + EPS]), rev.aspheric, backend)
+        ys = yo[stop, 0]
+        if not abs(ys) > atol:
+            break
+        ubp -= ys * EPS / (yo[stop, 1] - ys)
+    else:
+        raise RuntimeError("trace_chief_ray did not converge")
+    ray = _real_ray(rev, yo, Uo, ts, fl, 0)
+    yb = np.concatenate([[0.0], ray.y[::-1]])
+    yb[-1] = ybp
+    ub = np.concatenate([-ray.u[::-1], [-ray.u[0]]])
+    z = ray.z[-1] - ray.z[::-1]
+    z[0] = -yb[1] / math.tan(ub[0]) + z[1]                       # EP distance from vertex :293
+    z = np.append(z, z[-1] - yb[-2] / math.tan(ub[-2]))
+    return RealRayData(yb, ub, np.column_stack([yb, ub]), L.n.copy(), z)
+
+
+def trace_edge_rays(surfaces, y1, y2, U, stop, a_stop, backend=None):
+    """src/PupilSampling.jl:67-83.  The reference minimises |y_stop -/+ a_stop| with Optim.BFGS; the
+    same two roots are found here by a secant iteration (2-ray batches).  U may be an array of
+    field angles: all fields are aimed together."""
+    layout = _as_layout(surfaces)
+    U = np.atleast_1d(np.asarray(U, dtype=np.float64))
+    nf = len(U)
+    y = np.concatenate([np.broadcast_to(y1, nf), np.broadcast_to(y2, nf)]).astype(np.float64)
+    tgt = np.concatenate([np.full(nf, a_stop), np.full(nf, -a_stop)])
+    UU = np.concatenate([U, U])
+    fx_prev = None
+    for _ in range(60):
+        h = EPS * np.maximum(1.0, np.abs(y))
+        yo, _, _, _ = _trace2d(layout, np.concatenate([y, y + h]), np.concatenate([UU, UU]), layout.aspheric, backend)
+        fx = yo[stop, :2 * nf] - tgt
+        fh = yo[stop, 2 * nf:] - tgt
+        if not np.all(np.isfinite(fx)):
+            raise RuntimeError("trace_edge_rays left the domain")
+        done = np.abs(fx) <= 4e-16 * a_stop
+        if fx_prev is not None:
+            done |= (np.abs(fx) >= np.abs(fx_prev)) & (np.abs(fx_prev) <= 1e-13 * a_stop)
+        if np.all(done):
+            break
+        step = fx * h / (fh - fx)
+        y = np.where(done, y, y - step)
+        fx_prev = fx
+    return y[:nf], y[nf:]
+
+
+def _full_trace_setup(surfaces, system, H, k_rays, focus, backend):
+    """Host prelude of full_trace, src/PupilSampling.jl:85-122, vectorised over field points H."""
+    layout = _as_layout(surfaces)
+    Hs = np.abs(np.atleast_1d(np.asarray(H, dtype=np.float64)))
+    if not np.all(Hs <= 1.0):
+        raise ValueError("DomainError: Domain: |H| <= 1.0")                      # :89
+    if focus is None:
+        focus = system.marginal.z[-1] - system.marginal.z[-2]                    # :87
+    stop = system.stop
+    a_stop = abs(system.a[stop - 1])
+    # full_trace is reached with surfaces::Layout (:85), so trace_chief_ray takes its Layout branch
+    real_chief = trace_chief_ray(layout, system, backend=backend)
+    real_marginal = trace_marginal_ray(layout, system, backend=backend)
+    EP_t = real_chief.z[0]
+    Ubar = real_chief.u[0]
+    U = Hs * Ubar
+    u = np.tan(U)
+    y_EP = abs(real_marginal.y[0])
+    y1, y2 = y_EP - u * EP_t, -y_EP - u * EP_t                                   # :99
+    y1, y2 = trace_edge_rays(layout, y1, y2, U, stop, a_stop, backend=backend)   # :100
+    rb = isinstance(system, RayBasis)
+    if not rb:
+        h_prime = u * system.f                                                   # :103
+        z0 = ybar = None
+    else:
+        h_prime = np.full(len(Hs), system.chief.y[-1])                           # :105-108
+        z0 = system.marginal.z[0]
+        ybar = system.chief.y[1] + system.chief.u[0] * z0
+    ext = np.vstack([layout.M3, [np.inf, 0.0, 1.0]])                             # :111
+    Kx = np.append(layout.K, 0.0)                                                # :112
+    ext[-2, 1] = focus                                                           # :114
+    return dict(ext=ext, K=Kx, Hs=Hs, U=U, u=u, y1=y1, y2=y2, y_EP=y_EP, EP_t=EP_t, h_prime=h_prime,
+                stop=stop, a_stop=a_stop, focus=focus, z0=z0, ybar=ybar, k_rays=k_rays,
+                nu=system.marginal.nu[-1])
+
+
+def full_trace(*args, backend=None, arith=_lib.FAST):
+    """full_trace(system, H[, k_rays, focus]) / full_trace(surfaces, system, H[, k_rays, focus]) /
+    full_trace(surfaces, raybasis[, k_rays, focus]) -- src/PupilSampling.jl:85-163.
+    Returns RealRayError (one field) exactly as the reference lays it out: mirrored vectors
+    x = [ex; -ex], y = [ey; ey], r = [r; r] / max(r), t = [theta; pi - theta], RMS = sigma(x, y)."""
+    if isinstance(args[0], System):
+        system, rest = args[0], args[1:]
+        surfaces = system.layout
+    else:
+        surfaces, system, rest = args[0], args[1], args[2:]
+    if isinstance(system, RayBasis):
+        H, rest = 1.0, rest                                                      # :149-152
+    else:
+        H, rest = rest[0], rest[1:]
+    k_rays = int(rest[0]) if len(rest) > 0 else SPOT_RAYS
+    focus = rest[1] if len(rest) > 1 else None
+    if not np.isscalar(H):
+        raise TypeError("full_trace takes one field point H; use full_trace_fields for a sweep")
+    return full_trace_fields(surfaces, system, [float(H)], k_rays, focus, backend=backend, arith=arith)[0]
+
+
+def full_trace_fields(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, backend=None, arith=_lib.FAST):
+    """All field points of a spot-diagram sweep in ONE device call (fields are a grid dimension of the
+    kernel).  Each field has its own aimed y-range (:99-100), so every field gets its own ys."""
+    be = _be(backend)
+    p = _full_trace_setup(surfaces, system, Hs, k_rays, focus, backend)
+    be.set_layout(p["ext"], p["K"])
+    k2 = k_rays // 2                                                             # :116
+    xs = np.linspace(0.0, p["y_EP"], k2)                                         # :122
+    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], k_rays) for j in range(len(p["Hs"]))])   # :121
+    if p["z0"] is None:
+        flds = [dict(mode=0, u=float(p["u"][j]), v=math.tan(0.0), h_prime=float(p["h_prime"][j]))
+                for j in range(len(p["Hs"]))]
+    else:
+        flds = [dict(mode=1, ybar=float(p["ybar"]), z0=float(p["z0"]), h_prime=float(p["h_prime"][j]))
+                for j in range(len(p["Hs"]))]
+    out = []
+    for j0 in range(0, len(flds), _lib.MAX_FIELDS):
+        sl = slice(j0, j0 + _lib.MAX_FIELDS)
+        r = be.trace3d_grid(flds[sl], ys[sl], xs, p["stop"], p["a_stop"], arith=arith, compact=True,
+                            want=("ex", "ey", "r", "theta", "mask", "stats"))
+        out += [_mirror(r, j, p["nu"], float(H)) for j, H in enumerate(p["Hs"][sl])]
+    return out
+
+
+def _mirror(r, f, nu, H):
+    """take advantage of symmetry -- src/PupilSampling.jl:139-146; RMS = sigma(:169-173) evaluated
+    from the kernel's mergeable moments (mirrored x has mean exactly 0)."""
+    st = r["stats"][f]
+    n = int(st["n_kept"])
+    ex, ey, rr, th = (r[k][f][:n] for k in ("ex", "ey", "r", "theta"))
+    x2 = np.concatenate([ex, -ex])
+    y2 = np.concatenate([ey, ey])
+    rho = rr / st["r_max"] if n else rr
+    rho2 = np.concatenate([rho, rho])
+    t2 = np.concatenate([th, math.pi - th])
+    return RealRayError(x2, y2, nu, rho2, t2, H, rms_from_stats(st), stats=r["stats"][f:f + 1].copy())
+
+
+def rms_from_stats(st):
+    """sigma of the mirrored spot (src/PupilSampling.jl:140-141,169-173) from (n, mean, M2):
+    x -> [x; -x] has mean 0 and sum of squares 2 (M2x + n mean_x^2); y -> [y; y] doubles M2y."""
+    n = float(st["n_kept"])
+    if n == 0:
+        return float("nan")
+    sxx = float(st["m2_x"]) + n * float(st["mean_x"]) ** 2
+    return math.sqrt((2.0 * sxx + 2.0 * float(st["m2_y"])) / (2.0 * n))
+
+
+def merge_stats(records):
+    """Chan merge of per-shard ort_stats records in the given (rank) order: the multi-GPU combine
+    step after the all-gather.  records: structured array (n_shards,) -> one record."""
+    out = np.zeros(1, dtype=_lib.STATS_DTYPE)[0]
+    out["r_max"] = -np.inf
+    for rec in records:
+        for k in ("n_miss", "n_tir", "n_domain", "n_clip"):
+            out[k] += rec[k]
+        nb = float(rec["n_kept"])
+        if nb == 0:
+            continue
+        na = float(out["n_kept"])
+        if na == 0:
+            for k in ("n_kept", "mean_x", "mean_y", "m2_x", "m2_y", "r_max"):
+                out[k] = rec[k]
+            continue
+        n = na + nb
+        w = nb / n
+        for mk, vk in (("mean_x", "m2_x"), ("mean_y", "m2_y")):
+            d = float(rec[mk]) - float(out[mk])
+            out[mk] = float(out[mk]) + d * w
+            out[vk] = float(out[vk]) + float(rec[vk]) + d * d * (na * w)
+        out["n_kept"] += rec["n_kept"]
+        out["r_max"] = max(float(out["r_max"]), float(rec["r_max"]))
+    return out
+
+
+def wavegrad(eps, lam=LAMBDA):
+    """wavegrad(eps::RealRayError, lambda) -- src/PupilSampling.jl:165-167"""
+    return eps.x * eps.nu / lam, eps.y * eps.nu / lam
+
+
+def TSA(surfaces, system, k_rays=K_RAYS, backend=None):
+    """TSA -- transverse spherical aberration fan, src/SeidelAberrations.jl:116-135.  The k_rays-1
+    meridional rays are one batch of the 2-D kernel."""
+    layout = _as_layout(surfaces)
+    pm = system.marginal
+    rm = trace_marginal_ray(surfaces, system, backend=backend)
+    rc = trace_chief_ray(surfaces, system, backend=backend)
+    XP_t = rc.z[-1] - rc.z[-2]
+    y_EP = np.linspace(rm.y[0] / k_rays, rm.y[0], k_rays)
+    y_XP, eps_ = np.empty(k_rays), np.empty(k_rays)
+    BFD = pm.z[-1] - pm.z[-2]
+    t = BFD - (rm.z[-2] - pm.z[-2])                              # surface_to_focus :105 with sag :93-95
+    y_XP[-1] = rm.y[-2] + math.tan(rm.u[-1]) * XP_t
+    eps_[-1] = rm.y[-2] + math.tan(rm.u[-2]) * t
+    yo, Uo, ts, _ = _trace2d(layout, y_EP[:-1], np.zeros(k_rays - 1), layout.aspheric, backend)
+    z = np.cumsum(ts, axis=0)
+    tt = BFD - (z[-2] - z[-1])                                   # sag(ray::RealRay{Tangential}) :91
+    y_XP[:-1] = yo[-1] + np.tan(Uo[-1]) * XP_t
+    eps_[:-1] = yo[-1] + np.tan(Uo[-1]) * tt
+    return y_XP, eps_
+
+
+def SA(y, eps_, degree):
+    """SA -- odd-polynomial least-squares fit, src/SeidelAberrations.jl:139-146"""
+    if degree % 2 == 0 or degree < 3:
+        raise ValueError("DomainError: Required: isodd(degree) && degree >= 3")
+    yp = np.asarray(y) / np.max(y)
+    A = np.column_stack([yp ** k for k in range(3, degree + 1, 2)])
+    return np.linalg.lstsq(A, np.asarray(eps_), rcond=None)[0]

@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE: a backend with the same methods as ort_b200.Context, answered by the CPU
+oracle, so the host logic (solve, ray aiming, full_trace assembly, stats merge) can be tested
+without a GPU.  The product never selects this backend; only tests inject it."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+class OracleBackend:
+    def __init__(self):
+        self.S = None
+        self.K = None
+        self.rows = 0
+
+    def set_layout(self, surfaces, K=None):
+        S = np.asarray(surfaces, dtype=np.float64)
+        self.S = S[:, :3].copy()
+        self.K = None if K is None else np.asarray(K, dtype=np.float64).copy()
+        self.rows = S.shape[0]
+
+    def trace2d_batch(self, y0, U0, aspheric=False):
+        return orc.trace2d_batch(self.S, y0, U0, K=self.K, aspheric=aspheric)
+
+    def trace3d_rays(self, y0, x0, u0, v0, arith=0):
+        return orc.trace3d_batch(self.S, y0, x0, u0, v0, K=self.K)
+
+    def paraxial_batch(self, tau, phi, y0, w0, a=None, clip=False, arith=0, table=False):
+        y, w, ci = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=clip)
+        if not table:
+            return y, w, ci
+        k, N = len(tau), len(y0)
+        ya, wa = np.empty((k + 1, N)), np.empty((k + 1, N))
+        for j in range(N):
+            rt, _ = orc.paraxial_trace(tau, phi, float(y0[j]), float(w0[j]), a=a, clip=clip)
+            ya[:, j], wa[:, j] = rt[:, 0], rt[:, 1]
+        return y, w, ci, ya, wa
+
+    def transfer_batch(self, M, tau, taup, v_in, reverse=False):
+        return orc.transfer_batch(M, tau, taup, v_in, reverse=reverse)
+
+    def trace3d_grid(self, fields, ys, xs, stop, a_stop, arith=1, compact=False,
+                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None):
+        from ort_b200 import STATS_DTYPE
+        ys = np.asarray(ys, dtype=np.float64)
+        nf, NN = len(fields), ys.shape[-1] * len(xs)
+        res = {k: np.full((nf, NN), np.nan) for k in ("ex", "ey", "r", "theta")}
+        res["mask"] = np.zeros((nf, NN), dtype=np.uint8)
+        res["flags"] = np.zeros((nf, NN), dtype=np.uint8)
+        stats = np.zeros(nf, dtype=STATS_DTYPE)
+        for f, fld in enumerate(fields):
+            g = orc.grid_trace(self.S, ys[f] if ys.ndim == 2 else ys, xs, stop, a_stop, fld.get("h_prime", 0.0), u=fld.get("u", 0.0),
+                               v=fld.get("v", 0.0), mode=fld.get("mode", 0), ybar=fld.get("ybar", 0.0),
+                               z0=fld.get("z0", 1.0), K=self.K)
+            m = g["mask"].astype(bool)
+            n = int(m.sum())
+            for k in ("ex", "ey", "r", "theta"):
+                if compact:
+                    res[k][f, :n] = g[k][m]
+                else:
+                    res[k][f] = g[k]
+            res["mask"][f], res["flags"][f] = g["mask"], g["flags"]
+            st = stats[f]
+            st["n_kept"] = n
+            if n:
+                ex, ey = g["ex"][m], g["ey"][m]
+                st["mean_x"], st["mean_y"] = ex.mean(), ey.mean()
+                st["m2_x"], st["m2_y"] = ((ex - ex.mean()) ** 2).sum(), ((ey - ey.mean()) ** 2).sum()
+                st["r_max"] = g["r"][m].max()
+            for k, bit in (("n_miss", 1), ("n_tir", 2), ("n_domain", 4), ("n_clip", 8)):
+                st[k] = int(((g["flags"] & bit) != 0).sum())
+        res["stats"] = stats
+        return res
