@@ -2,6 +2,13 @@
 #pragma once
 #include "ort_internal.cuh"
 
+// shifted raw moments of one CTA / field (all CTAs of a field share the shift (cx, cy))
+struct RawPart {
+    long long n;
+    double s1x, s2x, s1y, s2y, rmax, cx, cy;
+    int nmiss, ntir, ndom, nclip;
+};
+
 struct GridArgs {
     const double* ys; const double* xs;     // device: grid coordinates (:121-122)
     int ny, nx;
@@ -12,7 +19,7 @@ struct GridArgs {
     double wg_nu, wg_lambda;
     double *ex, *ey, *r, *theta, *wx, *wy;  // device outputs, [n_fields][NN]; NULL = not wanted
     uint8_t *mask, *flags;
-    Part* partials;                         // [n_fields][gridDim.x]
+    RawPart* partials;                      // [n_fields][gridDim.x]
     int* tile_counts;                       // [n_fields][ntiles] or NULL (no compaction requested)
     ort_field fields[ORT_MAX_FIELDS];
 };
@@ -65,9 +72,13 @@ struct TransferArgs {
     const double2* v_in; double2* v_out;
 };
 
+#ifndef ORT_FAST_RPT
+#define ORT_FAST_RPT 1                      // rays per thread of k_grid<FAST>
+#endif
+int grid_rays_per_thread(int arith);
 int grid_blocks_per_sm(int arith);
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st);
-cudaError_t launch_grid_finalize(const Part* partials, int nparts, int n_fields, ort_stats* stats,
+cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fields, ort_stats* stats,
                                  cudaStream_t st);
 cudaError_t launch_compact(int* tile_counts, const CompactArgs& C, int n_fields, cudaStream_t st);
 cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream_t st);

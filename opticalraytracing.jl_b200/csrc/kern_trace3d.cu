@@ -1,10 +1,10 @@
 // kern_trace3d.cu -- the 3-D skew real-ray trace kernels (sm_100a, FP64 CUDA cores).
 //
-//   k_grid<ARITH>      K1: pupil-grid sweep, replaces the hot loop of full_trace
-//                      (src/PupilSampling.jl:115-138): one thread per ray, whole surface loop in
+//   k_grid<ARITH,RPT>  K1: pupil-grid sweep, replaces the hot loop of full_trace
+//                      (src/PupilSampling.jl:115-138): RPT rays per thread, whole surface loop in
 //                      registers, prescription in the constant bank (__grid_constant__ kernel
 //                      parameter), fused mask / eps / r / theta / wavegrad epilogue, per-thread
-//                      shifted-moment accumulation + warp-shuffle Chan merge for the spot statistics.
+//                      shifted-moment accumulation + warp-shuffle reduction for the spot statistics.
 //                      Persistent: gridDim.x * gridDim.y CTAs = SMs * resident CTAs/SM, tile-strided.
 //   k_grid_finalize    K6: deterministic fold of the per-CTA partials into ort_stats per field.
 //   k_tile_scan / k_compact   ordered compaction in the reference's push! order (:134-137).
@@ -36,21 +36,6 @@ __device__ __forceinline__ Hit trace_strict(const SurfArray& S, int nsurf, int s
     return h;
 }
 
-template <class SurfArray>
-__device__ __forceinline__ Hit trace_fast(const SurfArray& S, int nsurf, int stop,
-                                          double y, double x, double u, double v, bool& amb)
-{
-    RayF r;
-    fast_init(r, y, x, u, v);
-    Hit h; h.xs = h.ys = CUDART_NAN;
-    for (int i = 0; i < nsurf; i++) {
-        fast_step(S[i], r);
-        if (i == stop - 1) { h.xs = r.x; h.ys = r.y; }
-    }
-    h.xf = r.x; h.yf = r.y; h.flags = r.flags; amb = r.amb;
-    return h;
-}
-
 // the strict re-trace of guard-band rays lives out of line so it does not bloat the hot loop
 template <class SurfArray>
 __device__ __noinline__ Hit trace_strict_cold(const SurfArray& S, int nsurf, int stop,
@@ -59,140 +44,239 @@ __device__ __noinline__ Hit trace_strict_cold(const SurfArray& S, int nsurf, int
     return trace_strict(S, nsurf, stop, y, x, u, v);
 }
 
+// sign bit set iff a is NaN or +-Inf (exponent field all ones)
+__device__ __forceinline__ int nonfinite_bit(double a) { return 0x7FEFFFFF - (hi32(a) & 0x7FFFFFFF); }
+
 __device__ __forceinline__ bool is_nan_bits(double a)
 {
     return (hi32(a) & 0x7FFFFFFF) > 0x7FF00000 ||
            ((hi32(a) & 0x7FFFFFFF) == 0x7FF00000 && __double2loint(a) != 0);
 }
 
-// per-thread running moments about the first kept sample (cheap: 2 DADD + 2 DFMA per ray and axis)
-struct Acc {
-    int n;
-    double cx, cy, s1x, s2x, s1y, s2y, rmax;   // rmax holds r (strict) or r^2 (fast)
-    int nmiss, ntir, ndom, nclip;
-};
-__device__ __forceinline__ void acc_zero(Acc& a)
+// RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
+// (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
+// (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
+template <int RPT, class SurfArray>
+__device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
+                                           const double* y, const double* x, const double* u,
+                                           const double* v, Hit* h, int* amb)
 {
-    a.n = 0; a.cx = a.cy = a.s1x = a.s2x = a.s1y = a.s2y = 0.0; a.rmax = -CUDART_INF;
-    a.nmiss = a.ntir = a.ndom = a.nclip = 0;
-}
-__device__ __forceinline__ void acc_add(Acc& a, double ex, double ey, double rr)
-{
-    if (a.n == 0) { a.cx = ex; a.cy = ey; }
-    double dx = ex - a.cx, dy = ey - a.cy;
-    a.s1x += dx; a.s2x = fma(dx, dx, a.s2x);
-    a.s1y += dy; a.s2y = fma(dy, dy, a.s2y);
-    a.rmax = fmax(a.rmax, rr);
-    a.n++;
-}
-__device__ __forceinline__ void acc_flags(Acc& a, unsigned f)
-{
-    a.nmiss += (f & ORT_FLAG_MISS) ? 1 : 0; a.ntir += (f & ORT_FLAG_TIR) ? 1 : 0;
-    a.ndom += (f & ORT_FLAG_DOMAIN) ? 1 : 0; a.nclip += (f & ORT_FLAG_CLIP) ? 1 : 0;
-}
-__device__ __forceinline__ Part acc_to_part(const Acc& a, bool rmax_is_squared)
-{
-    Part p; part_zero(p);
-    p.nmiss = a.nmiss; p.ntir = a.ntir; p.ndom = a.ndom; p.nclip = a.nclip;
-    if (a.n > 0) {
-        double n = (double)a.n;
-        p.n = a.n;
-        p.mx = a.cx + a.s1x / n;
-        p.my = a.cy + a.s1y / n;
-        p.m2x = fmax(a.s2x - a.s1x * a.s1x / n, 0.0);
-        p.m2y = fmax(a.s2y - a.s1y * a.s1y / n, 0.0);
-        p.rmax = rmax_is_squared ? sqrt(a.rmax) : a.rmax;
+    RaysF<RPT> r;
+#pragma unroll
+    for (int j = 0; j < RPT; j++) fast_init(r, j, n0, y[j], x[j], u[j], v[j]);
+    int i = 0;
+    for (; i < stop; i++) fast_step<RPT>(S[i], r);
+#pragma unroll
+    for (int j = 0; j < RPT; j++) { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
+    for (; i < nsurf; i++) fast_step<RPT>(S[i], r);
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        h[j].xf = r.x[j]; h[j].yf = r.y[j]; h[j].flags = 0;
+        amb[j] = r.amb[j] | nonfinite_bit(r.x[j]) | nonfinite_bit(r.y[j]) | nonfinite_bit(r.Kz[j]);
     }
-    return p;
 }
 
 // ------------------------------------------------------------------------------------------
 // K1: pupil-grid sweep
 // ------------------------------------------------------------------------------------------
-template <int ARITH>
-__global__ void __launch_bounds__(ORT_TILE)
-k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
-{
-    __shared__ Part s_part[ORT_TILE / 32];
-    const int f = blockIdx.y;
-    const ort_field fld = A.fields[f];
-    const int nsurf = P.nsurf;
-    const unsigned NN = A.NN;
-    const unsigned ntiles = (NN + ORT_TILE - 1) / ORT_TILE;
-    const size_t fbase = (size_t)f * NN;
-    Acc acc; acc_zero(acc);
+// Spot statistics: every CTA first traces the field's centre ray (row ny/2, column 0) and uses its
+// (ex, ey) as a common shift c, so the per-thread accumulation is 2 DADD + 2 DFMA per axis on
+// d = e - c (no cancellation: |mean - c| is of the order of the spot size) and all partial sums of
+// a field are plain sums -- folded in a fixed order, hence bit-reproducible run to run.
+struct RawAcc {
+    int n, nflag_lo, nflag_hi;                  // counts; nflag_* pack (miss, tir) and (domain, clip) as 16+16 bits
+    double s1x, s2x, s1y, s2y, rmax;            // rmax holds r (strict) or r^2 (fast)
+};
 
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const unsigned i = tile * ORT_TILE + threadIdx.x;
-        int kept = 0;
-        if (i < NN) {
-            const unsigned iy = i / (unsigned)A.nx, ix = i - iy * (unsigned)A.nx;   // y outer, x inner (:123)
-            const double y0 = __ldg(A.ys + (size_t)f * A.ys_stride + iy), x0 = __ldg(A.xs + ix);
-            double u = fld.u, v = fld.v;
-            if (fld.mode == 1) {                         // RayBasis: :124-127 then tan at :38-39
-                u = tan(SD(SS(fld.ybar, y0), fld.z0));
-                v = tan(SD(-x0, fld.z0));
-            }
-            Hit h;
-            bool amb = false;
-            double ri, r2 = 0.0;
-            bool clip;
-            if (ARITH == ORT_ARITH_FAST) {
-                h = trace_fast(P.s, nsurf, A.stop, y0, x0, u, v, amb);
-                r2 = fma(h.xs, h.xs, h.ys * h.ys);
-                if (tiny_vs(r2 - A.a_stop2, A.a_stop2)) amb = true;     // within 2^-30 of the stop edge
-                clip = r2 > A.a_stop2;
-                ri = 0.0;
-            }
-            if (ARITH == ORT_ARITH_STRICT || amb) {
-                h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(P.s, nsurf, A.stop, y0, x0, u, v)
-                                                : trace_strict_cold(P.s, nsurf, A.stop, y0, x0, u, v);
-                ri = jl_hypot(h.xs, h.ys);                              // :131
-                clip = ri > A.a_stop;
-                r2 = ri * ri;
-            } else if (A.r || A.theta) {
-                ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
-            }
-            const bool drop = clip || is_nan_bits(h.xf) || is_nan_bits(h.yf);   // :132
-            unsigned flags = h.flags | (clip ? ORT_FLAG_CLIP : 0u);
-            kept = !drop;
-            const double ex = h.xf;                                             // :135
-            const double ey = (ARITH == ORT_ARITH_STRICT || amb) ? SS(h.yf, fld.h_prime)
-                                                                 : h.yf - fld.h_prime;   // :134
-            const size_t o = fbase + i;
-            if (A.ex) A.ex[o] = ex;
-            if (A.ey) A.ey[o] = ey;
-            if (A.r) A.r[o] = ri;                                               // :136
-            if (A.theta) A.theta[o] = atan2(h.ys, h.xs);                        // :133
-            if (A.wx) A.wx[o] = SD(SM(ex, A.wg_nu), A.wg_lambda);               // :166
-            if (A.wy) A.wy[o] = SD(SM(ey, A.wg_nu), A.wg_lambda);
-            if (A.mask) A.mask[o] = (uint8_t)kept;
-            if (A.flags) A.flags[o] = (uint8_t)flags;
-            acc_flags(acc, flags);
-            if (kept) acc_add(acc, ex, ey, (ARITH == ORT_ARITH_STRICT) ? ri : r2);
-        }
-        if (A.tile_counts) {
-            int c = __syncthreads_count(kept);
-            if (threadIdx.x == 0) A.tile_counts[(size_t)f * ntiles + tile] = c;
-        }
-    }
-    Part p = acc_to_part(acc, ARITH != ORT_ARITH_STRICT);
-    part_block_reduce<ORT_TILE / 32>(p, s_part);
-    if (threadIdx.x == 0) A.partials[(size_t)f * gridDim.x + blockIdx.x] = p;
+__device__ __forceinline__ void raw_add(RawPart& p, const RawPart& q)
+{
+    p.n += q.n; p.s1x += q.s1x; p.s2x += q.s2x; p.s1y += q.s1y; p.s2y += q.s2y;
+    p.rmax = fmax(p.rmax, q.rmax);
+    p.nmiss += q.nmiss; p.ntir += q.ntir; p.ndom += q.ndom; p.nclip += q.nclip;
 }
 
-// K6: fold the per-CTA partials of one field in a fixed order (bit-reproducible run to run).
-__global__ void __launch_bounds__(256) k_grid_finalize(const Part* partials, int nparts, ort_stats* stats)
+__device__ __forceinline__ void raw_warp_reduce(RawPart& p)
 {
-    __shared__ Part s_part[8];
-    const int f = blockIdx.x;
-    Part p; part_zero(p);
-    for (int j = threadIdx.x; j < nparts; j += 256) part_merge(p, partials[(size_t)f * nparts + j]);
-    part_block_reduce<8>(p, s_part);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        p.n += __shfl_down_sync(0xffffffffu, p.n, d);
+        p.s1x += __shfl_down_sync(0xffffffffu, p.s1x, d);
+        p.s2x += __shfl_down_sync(0xffffffffu, p.s2x, d);
+        p.s1y += __shfl_down_sync(0xffffffffu, p.s1y, d);
+        p.s2y += __shfl_down_sync(0xffffffffu, p.s2y, d);
+        p.rmax = fmax(p.rmax, __shfl_down_sync(0xffffffffu, p.rmax, d));
+        p.nmiss += __shfl_down_sync(0xffffffffu, p.nmiss, d);
+        p.ntir += __shfl_down_sync(0xffffffffu, p.ntir, d);
+        p.ndom += __shfl_down_sync(0xffffffffu, p.ndom, d);
+        p.nclip += __shfl_down_sync(0xffffffffu, p.nclip, d);
+    }
+}
+
+// deterministic: shuffle tree inside each warp, then thread 0 folds the warp leaders in warp order
+template <int NWARPS>
+__device__ __forceinline__ void raw_block_reduce(RawPart& p, RawPart* smem /* [NWARPS] */)
+{
+    raw_warp_reduce(p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = p;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < NWARPS; w++) raw_add(p, smem[w]);
+}
+
+// everything after the trace for one ray: stop-radius mask (:131-132), strict re-trace of guard-band
+// rays, outputs (:133-137, :165-167) and statistics
+template <int ARITH>
+__device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
+                                             Hit h, int amb, double y0, double x0, double u, double v,
+                                             bool valid, size_t o, double cx, double cy, RawAcc& acc)
+{
+    double ri = 0.0, r2 = 0.0;
+    bool clip = false;
+    if (ARITH == ORT_ARITH_FAST) {
+        r2 = fma(h.xs, h.xs, h.ys * h.ys);
+        amb |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);                  // within 2^-30 of the stop edge
+        clip = r2 > A.a_stop2;
+    }
+    const bool sv = (ARITH == ORT_ARITH_STRICT) || amb < 0;
+    if (sv) {
+        h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(P.s, P.nsurf, A.stop, y0, x0, u, v)
+                                        : trace_strict_cold(P.s, P.nsurf, A.stop, y0, x0, u, v);
+        ri = jl_hypot(h.xs, h.ys);                                      // :131
+        clip = ri > A.a_stop;
+        r2 = ri * ri;
+    } else if (A.r) {
+        ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
+    }
+    const bool drop = clip || is_nan_bits(h.xf) || is_nan_bits(h.yf);   // :132
+    const unsigned flags = h.flags | (clip ? ORT_FLAG_CLIP : 0u);
+    const int kept = valid && !drop;
+    const double ex = h.xf;                                             // :135
+    const double ey = sv ? SS(h.yf, fld.h_prime) : h.yf - fld.h_prime;  // :134
+    if (valid) {
+        if (A.ex) A.ex[o] = ex;
+        if (A.ey) A.ey[o] = ey;
+        if (A.r) A.r[o] = ri;                                           // :136
+        if (A.theta) A.theta[o] = atan2(h.ys, h.xs);                    // :133
+        if (A.wx) A.wx[o] = SD(SM(ex, A.wg_nu), A.wg_lambda);           // :166
+        if (A.wy) A.wy[o] = SD(SM(ey, A.wg_nu), A.wg_lambda);
+        if (A.mask) A.mask[o] = (uint8_t)kept;
+        if (A.flags) A.flags[o] = (uint8_t)flags;
+        acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
+        acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0) + (flags & ORT_FLAG_CLIP ? 0x10000 : 0);
+    }
+    if (kept) {
+        const double dx = ex - cx, dy = ey - cy;
+        acc.s1x += dx; acc.s2x = fma(dx, dx, acc.s2x);
+        acc.s1y += dy; acc.s2y = fma(dy, dy, acc.s2y);
+        acc.rmax = fmax(acc.rmax, (ARITH == ORT_ARITH_STRICT) ? ri : r2);
+        acc.n++;
+    }
+    return kept;
+}
+
+__device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, double x0, double& u, double& v)
+{
+    u = fld.u; v = fld.v;
+    if (fld.mode == 1) {                         // RayBasis: :124-127 then tan at :38-39
+        u = tan(SD(SS(fld.ybar, y0), fld.z0));
+        v = tan(SD(-x0, fld.z0));
+    }
+}
+
+template <int ARITH, int RPT>
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? 4 : 2) : 2)
+k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
+{
+    __shared__ RawPart s_part[ORT_TILE / 32];
+    __shared__ double s_shift[2];
+    const int f = blockIdx.y;
+    const ort_field& fld = A.fields[f];
+    const unsigned NN = A.NN;
+    const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;            // 256-ray sub-tiles (compaction unit)
+    const unsigned ntiles = (nsub + RPT - 1) / RPT;
+    const size_t fbase = (size_t)f * NN;
+    const double* ysf = A.ys + (size_t)f * A.ys_stride;
+
+    RawAcc acc;
+    acc.n = acc.nflag_lo = acc.nflag_hi = 0;
+    acc.s1x = acc.s2x = acc.s1y = acc.s2y = 0.0; acc.rmax = -CUDART_INF;
+
+    if (threadIdx.x == 0) {                      // common shift of this field: its centre ray
+        const double y0 = __ldg(ysf + A.ny / 2), x0 = __ldg(A.xs);
+        double u, v; field_slopes(fld, y0, x0, u, v);
+        Hit h; int amb = 0;
+        if (ARITH == ORT_ARITH_FAST) trace_fast<1>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb);
+        if (ARITH == ORT_ARITH_STRICT || amb < 0) h = trace_strict_cold(P.s, P.nsurf, A.stop, y0, x0, u, v);
+        const double ey = h.yf - fld.h_prime;
+        const bool bad = nonfinite_bit(h.xf) < 0 || nonfinite_bit(ey) < 0;
+        s_shift[0] = bad ? 0.0 : h.xf;
+        s_shift[1] = bad ? 0.0 : ey;
+    }
+    __syncthreads();
+    const double cx = s_shift[0], cy = s_shift[1];
+
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        double y0[RPT], x0[RPT], u[RPT], v[RPT];
+        unsigned idx[RPT];
+        bool valid[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            const unsigned i0 = (tile * RPT + j) * ORT_TILE + threadIdx.x;
+            valid[j] = i0 < NN;
+            idx[j] = valid[j] ? i0 : NN - 1;     // padded lanes re-trace the last ray: the warp stays convergent
+            const unsigned iy = idx[j] / (unsigned)A.nx, ix = idx[j] - iy * (unsigned)A.nx;   // y outer, x inner (:123)
+            y0[j] = __ldg(ysf + iy); x0[j] = __ldg(A.xs + ix);
+            field_slopes(fld, y0[j], x0[j], u[j], v[j]);
+        }
+        Hit h[RPT];
+        int amb[RPT];
+        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb);
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
+            const int kept = grid_epilogue<ARITH>(P, A, fld, h[j], amb[j], y0[j], x0[j], u[j], v[j], valid[j],
+                                                  fbase + idx[j], cx, cy, acc);
+            if (A.tile_counts) {
+                const int c = __syncthreads_count(kept);
+                const unsigned sub = tile * RPT + j;
+                if (threadIdx.x == 0 && sub < nsub) A.tile_counts[(size_t)f * nsub + sub] = c;
+            }
+        }
+    }
+    RawPart p;
+    p.n = acc.n; p.s1x = acc.s1x; p.s2x = acc.s2x; p.s1y = acc.s1y; p.s2y = acc.s2y; p.rmax = acc.rmax;
+    p.cx = cx; p.cy = cy;
+    p.nmiss = acc.nflag_lo & 0xFFFF; p.ntir = acc.nflag_lo >> 16; p.ndom = acc.nflag_hi & 0xFFFF; p.nclip = acc.nflag_hi >> 16;
+    raw_block_reduce<ORT_TILE / 32>(p, s_part);
     if (threadIdx.x == 0) {
+        if (ARITH != ORT_ARITH_STRICT) p.rmax = sqrt(p.rmax);
+        A.partials[(size_t)f * gridDim.x + blockIdx.x] = p;
+    }
+}
+
+// K6: fold the per-CTA partial sums of one field in a fixed order (bit-reproducible run to run) and
+// convert the shifted raw moments to (n, mean, M2).
+__global__ void __launch_bounds__(256) k_grid_finalize(const RawPart* partials, int nparts, ort_stats* stats)
+{
+    __shared__ RawPart s_part[8];
+    const int f = blockIdx.x;
+    RawPart p;
+    p.n = 0; p.s1x = p.s2x = p.s1y = p.s2y = 0.0; p.rmax = -CUDART_INF; p.cx = p.cy = 0.0;
+    p.nmiss = p.ntir = p.ndom = p.nclip = 0;
+    for (int j = threadIdx.x; j < nparts; j += 256) raw_add(p, partials[(size_t)f * nparts + j]);
+    raw_block_reduce<8>(p, s_part);
+    if (threadIdx.x == 0) {
+        const double cx = partials[(size_t)f * nparts].cx, cy = partials[(size_t)f * nparts].cy;
         ort_stats s;
-        s.n_kept = p.n; s.mean_x = p.mx; s.mean_y = p.my; s.m2_x = p.m2x; s.m2_y = p.m2y;
-        s.r_max = p.rmax;
+        s.n_kept = p.n;
+        if (p.n > 0) {
+            const double n = (double)p.n;
+            s.mean_x = cx + p.s1x / n; s.mean_y = cy + p.s1y / n;
+            s.m2_x = fmax(p.s2x - p.s1x * p.s1x / n, 0.0);
+            s.m2_y = fmax(p.s2y - p.s1y * p.s1y / n, 0.0);
+            s.r_max = p.rmax;
+        } else { s.mean_x = s.mean_y = s.m2_x = s.m2_y = 0.0; s.r_max = -CUDART_INF; }
         s.n_miss = p.nmiss; s.n_tir = p.ntir; s.n_domain = p.ndom; s.n_clip = p.nclip;
         stats[f] = s;
     }
@@ -255,16 +339,21 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
     const int nsurf = P.nsurf;
     bool strict = (ARITH == ORT_ARITH_STRICT);
     if (!strict) {
-        RayF r;
-        fast_init(r, y0, x0, u0, v0);
+        RaysF<1> r;
+        fast_init(r, 0, P.n0, y0, x0, u0, v0);
         for (int s = 0; s < nsurf; s++) {
-            fast_step(P.s[s], r);
-            if (A.xv) A.xv[(size_t)s * A.N + i] = r.x;
-            if (A.yv) A.yv[(size_t)s * A.N + i] = r.y;
+            fast_step<1>(P.s[s], r);
+            if (A.xv) A.xv[(size_t)s * A.N + i] = r.x[0];
+            if (A.yv) A.yv[(size_t)s * A.N + i] = r.y[0];
         }
-        if (!r.amb) {
-            if (A.kout) { A.kout[i] = r.L; A.kout[A.N + i] = r.M; A.kout[2 * A.N + i] = r.N; }
-            if (A.flags) A.flags[i] = (uint8_t)r.flags;
+        const int amb = r.amb[0] | nonfinite_bit(r.x[0]) | nonfinite_bit(r.y[0]) | nonfinite_bit(r.Kz[0]);
+        if (amb >= 0) {
+            if (A.kout) {   // K = n k -> direction cosines; the reference's k is a LINE direction with k3 > 0
+                const double inv = 1.0 / sqrt(fma(r.Kx[0], r.Kx[0], fma(r.Ky[0], r.Ky[0], r.Kz[0] * r.Kz[0])));
+                const double sg = (r.Kz[0] < 0.0) ? -inv : inv;
+                A.kout[i] = r.Kx[0] * sg; A.kout[A.N + i] = r.Ky[0] * sg; A.kout[2 * A.N + i] = r.Kz[0] * sg;
+            }
+            if (A.flags) A.flags[i] = 0;
         } else strict = true;
     }
     if (strict) {
@@ -280,6 +369,40 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
     }
 }
 
+// per-thread running moments about the first kept sample + Chan merge (candidate kernel: every
+// CTA owns one prescription, so there is no common shift to share across CTAs)
+struct Acc {
+    int n;
+    double cx, cy, s1x, s2x, s1y, s2y, rmax;
+};
+__device__ __forceinline__ void acc_zero(Acc& a)
+{
+    a.n = 0; a.cx = a.cy = a.s1x = a.s2x = a.s1y = a.s2y = 0.0; a.rmax = -CUDART_INF;
+}
+__device__ __forceinline__ void acc_add(Acc& a, double ex, double ey, double rr)
+{
+    if (a.n == 0) { a.cx = ex; a.cy = ey; }
+    double dx = ex - a.cx, dy = ey - a.cy;
+    a.s1x += dx; a.s2x = fma(dx, dx, a.s2x);
+    a.s1y += dy; a.s2y = fma(dy, dy, a.s2y);
+    a.rmax = fmax(a.rmax, rr);
+    a.n++;
+}
+__device__ __forceinline__ Part acc_to_part(const Acc& a, bool rmax_is_squared)
+{
+    Part p; part_zero(p);
+    if (a.n > 0) {
+        double n = (double)a.n;
+        p.n = a.n;
+        p.mx = a.cx + a.s1x / n;
+        p.my = a.cy + a.s1y / n;
+        p.m2x = fmax(a.s2x - a.s1x * a.s1x / n, 0.0);
+        p.m2y = fmax(a.s2y - a.s1y * a.s1y / n, 0.0);
+        p.rmax = rmax_is_squared ? sqrt(a.rmax) : a.rmax;
+    }
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------
 // K5: candidate prescriptions, one CTA each, prescription staged in shared memory
 // ------------------------------------------------------------------------------------------
@@ -288,12 +411,13 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.R = R; S.K = K; S.t = t; S.n1 = n1; S.n2 = n2;
     S.sgnR = (R < 0.0) ? -1.0 : ((R > 0.0) ? 1.0 : R);
     S.c = isfinite(R) ? 1.0 / R : 0.0;
-    S.eta = n1 / n2;
-    S.eta2 = S.eta * S.eta;
-    S.ome2 = 1.0 - S.eta2;
+    S.n1sq = n1 * n1;
+    S.cn1sq = S.c * S.n1sq;
+    S.dn2 = (n2 - n1) * (n2 + n1);
     S.onepK = 1.0 + K;
-    S.kind = !isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC);
-    S.refr = (n1 != n2);
+    S.kind = (!isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC)) | (n1 != n2 ? SURF_REFR : 0) |
+             (n2 < 0.0 ? SURF_N2NEG : 0);
+    S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
 }
 
 template <int ARITH>
@@ -316,14 +440,14 @@ k_candidates(CandArgs A)
     for (unsigned i = threadIdx.x; i < NN; i += ORT_TILE) {
         const unsigned iy = i / (unsigned)A.nx, ix = i - iy * (unsigned)A.nx;
         const double y0 = __ldg(A.ys + iy), x0 = __ldg(A.xs + ix);
-        Hit h; bool amb = false; double ri = 0.0, r2 = 0.0; bool clip;
+        Hit h; int amb = 0; double ri = 0.0, r2 = 0.0; bool clip;
         if (ARITH == ORT_ARITH_FAST) {
-            h = trace_fast(s_surf, nsurf, A.stop, y0, x0, A.u, A.v, amb);
+            { const double uu = A.u, vv = A.v; trace_fast<1>(s_surf, nsurf, A.stop, Rc[2 * rows], &y0, &x0, &uu, &vv, &h, &amb); }
             r2 = fma(h.xs, h.xs, h.ys * h.ys);
-            if (tiny_vs(r2 - A.a_stop2, A.a_stop2)) amb = true;
+            amb |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);
             clip = r2 > A.a_stop2;
         }
-        if (ARITH == ORT_ARITH_STRICT || amb) {
+        if (ARITH == ORT_ARITH_STRICT || amb < 0) {
             h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(s_surf, nsurf, A.stop, y0, x0, A.u, A.v)
                                             : trace_strict_cold(s_surf, nsurf, A.stop, y0, x0, A.u, A.v);
             ri = jl_hypot(h.xs, h.ys);
@@ -346,24 +470,26 @@ k_candidates(CandArgs A)
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from ort_api.cu)
 // ------------------------------------------------------------------------------------------
+int grid_rays_per_thread(int arith) { return arith == ORT_ARITH_FAST ? ORT_FAST_RPT : 1; }
+
 int grid_blocks_per_sm(int arith)
 {
     int nb = 0;
     cudaError_t e = (arith == ORT_ARITH_FAST)
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST>, ORT_TILE, 0)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT>, ORT_TILE, 0);
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT>, ORT_TILE, 0)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st)
 {
-    if (arith == ORT_ARITH_FAST) k_grid<ORT_ARITH_FAST><<<grid, ORT_TILE, 0, st>>>(P, A);
-    else k_grid<ORT_ARITH_STRICT><<<grid, ORT_TILE, 0, st>>>(P, A);
+    if (arith == ORT_ARITH_FAST) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT><<<grid, ORT_TILE, 0, st>>>(P, A);
+    else k_grid<ORT_ARITH_STRICT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
     return cudaGetLastError();
 }
 
-cudaError_t launch_grid_finalize(const Part* partials, int nparts, int n_fields, ort_stats* stats,
+cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fields, ort_stats* stats,
                                  cudaStream_t st)
 {
     k_grid_finalize<<<n_fields, 256, 0, st>>>(partials, nparts, stats);

@@ -87,12 +87,15 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     S.R = R; S.K = K; S.t = t; S.n1 = n1; S.n2 = n2;
     S.sgnR = (R < 0.0) ? -1.0 : ((R > 0.0) ? 1.0 : R);          // Julia sign()
     S.c = isfinite(R) ? 1.0 / R : 0.0;
-    S.eta = n1 / n2;
-    S.eta2 = S.eta * S.eta;
-    S.ome2 = 1.0 - S.eta2;
+    S.n1sq = n1 * n1;
+    S.cn1sq = S.c * S.n1sq;
+    S.dn2 = (n2 - n1) * (n2 + n1);
     S.onepK = 1.0 + K;
-    S.kind = !isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC);
-    S.refr = (n1 != n2);
+    S.kind = (!isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC)) | (n1 != n2 ? SURF_REFR : 0) |
+             (n2 < 0.0 ? SURF_N2NEG : 0);
+    const double thr = n2 * n2 * 9.313225746154785e-10;         // 2^-30 n2^2
+    int64_t bits; memcpy(&bits, &thr, 8);
+    S.tir_thr = (int32_t)(bits >> 32);
 }
 
 // bracket the dominant kernel with an event pair (measurement only)
@@ -241,11 +244,13 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
     P.nsurf = rows - 1;
     P.fast_ok = 1;
     P.t_last = t[rows - 1];
+    P.n0 = n[0];
+    P.nlast = n[rows - 1];
     for (int i = 0; i + 1 < rows; i++) {
         const double Ri = R[i + 1], Ki = K ? K[i + 1] : 0.0;
         derive_surface_host(P.s[i], Ri, Ki, t[i], n[i], n[i + 1]);
-        if (Ri == 0.0 || isnan(Ri) || !isfinite(Ki) || !isfinite(t[i]) || !isfinite(P.s[i].eta) ||
-            P.s[i].eta == 0.0)
+        if (Ri == 0.0 || isnan(Ri) || !isfinite(Ki) || !isfinite(t[i]) || !isfinite(n[i]) || !isfinite(n[i + 1]) ||
+            n[i] == 0.0 || n[i + 1] == 0.0)
             P.fast_ok = 0;
     }
     ctx->rows = rows;
@@ -278,7 +283,7 @@ static int grid_check(ort_ctx* ctx, const ort_field* fields, int n_fields, const
 static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
                         const double* d_xs, int nx, int stop, double a_stop, const ort_opts* opts,
                         const ort_grid_out& full, const ort_grid_out* dst, ort_stats* d_stats,
-                        Part* d_partials, int* d_tiles, int gx, cudaStream_t st)
+                        RawPart* d_partials, int* d_tiles, int gx, cudaStream_t st)
 {
     const unsigned NN = (unsigned)((long long)ny * nx);
     GridArgs A;
@@ -298,7 +303,7 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
         CK(launch_grid(ctx->presc, A, arith, dim3((unsigned)gx, (unsigned)n_fields), st));
         ctx->launches++;
     } else {
-        CK(cudaMemsetAsync(d_partials, 0, sizeof(Part) * (size_t)gx * n_fields, st));
+        CK(cudaMemsetAsync(d_partials, 0, sizeof(RawPart) * (size_t)gx * n_fields, st));
     }
     CK(launch_grid_finalize(d_partials, gx, n_fields, d_stats, st));
     ctx->launches++;
@@ -317,7 +322,9 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
 
 static int grid_dims(const ort_ctx* ctx, int arith, int n_fields, unsigned NN)
 {
-    const unsigned ntiles = (NN + ORT_TILE - 1) / ORT_TILE;
+    const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;
+    const unsigned rpt = (unsigned)grid_rays_per_thread(arith);
+    const unsigned ntiles = (nsub + rpt - 1) / rpt;
     long long gx = (long long)ctx->sm_count * ctx->bps[arith] / n_fields;
     if (gx < 1) gx = 1;
     if (gx > (long long)ntiles) gx = ntiles;
@@ -336,7 +343,7 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     const unsigned NN = (unsigned)((long long)ny * nx);
     const int arith = resolve_arith(ctx, opts->arith);
     const int gx = grid_dims(ctx, arith, n_fields, NN);
-    Part* d_partials; ENSURE(SL_PARTIALS, sizeof(Part) * (size_t)gx * n_fields, d_partials);
+    RawPart* d_partials; ENSURE(SL_PARTIALS, sizeof(RawPart) * (size_t)gx * n_fields, d_partials);
     ort_stats* d_stats = d_out->stats;
     if (!d_stats) ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
     if (!opts->compact)
@@ -373,7 +380,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     const size_t nys = (size_t)ny * (opts->ys_per_field ? n_fields : 1);
     ENSURE(SL_YS, sizeof(double) * nys, d_ys);
     ENSURE(SL_XS, sizeof(double) * (size_t)nx, d_xs);
-    Part* d_partials; ENSURE(SL_PARTIALS, sizeof(Part) * (size_t)gx * n_fields, d_partials);
+    RawPart* d_partials; ENSURE(SL_PARTIALS, sizeof(RawPart) * (size_t)gx * n_fields, d_partials);
     ort_stats* d_stats; ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
     const unsigned ntiles = (NN + ORT_TILE - 1) / ORT_TILE;
     int* d_tiles = nullptr;

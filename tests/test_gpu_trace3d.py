@@ -90,7 +90,12 @@ def test_grid_multi_field_compact_and_stats(ctx, orc, pre, ort):
             # statistics: mirrored RMS of the reference (:139-146,169-173) from the mergeable moments
             sxx = st["m2_x"] + n * st["mean_x"] ** 2          # mirrored x: mean 0, sum sq doubles
             rms = math.sqrt((2 * sxx + 2 * st["m2_y"]) / (2 * n))
-            assert abs(rms / ref.RMS - 1) < TOL
+            # STRICT: eps is bit-identical, only the summation order differs -> 1e-12 relative.
+            # FAST: eps = yf - h' is a ~0.03 mm difference of ~20 mm positions that are themselves
+            # good to 1e-12 relative, so the RMS is good to 1e-12 x the position scale (absolute).
+            if arith == ort.STRICT:
+                assert abs(rms / ref.RMS - 1) < TOL
+            assert abs(rms - ref.RMS) < TOL * scale
             assert abs(st["r_max"] / g["r"][m].max() - 1) < TOL
 
 
