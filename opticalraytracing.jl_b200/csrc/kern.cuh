@@ -73,7 +73,13 @@ struct TransferArgs {
 };
 
 #ifndef ORT_FAST_RPT
-#define ORT_FAST_RPT 1                      // rays per thread of k_grid<FAST>
+#define ORT_FAST_RPT 2                      // rays per thread of k_grid<FAST>
+#endif
+#ifndef ORT_BPS1
+#define ORT_BPS1 4                          // min resident CTAs/SM requested for k_grid<FAST,1>
+#endif
+#ifndef ORT_BPS2
+#define ORT_BPS2 3                          // ... for k_grid<FAST,2>
 #endif
 int grid_rays_per_thread(int arith);
 int grid_blocks_per_sm(int arith);

@@ -126,9 +126,18 @@ __device__ __forceinline__ void raw_block_reduce(RawPart& p, RawPart* smem /* [N
 
 // everything after the trace for one ray: stop-radius mask (:131-132), strict re-trace of guard-band
 // rays, outputs (:133-137, :165-167) and statistics
+__device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, double x0, double& u, double& v)
+{
+    u = fld.u; v = fld.v;
+    if (fld.mode == 1) {                         // RayBasis: :124-127 then tan at :38-39
+        u = tan(SD(SS(fld.ybar, y0), fld.z0));
+        v = tan(SD(-x0, fld.z0));
+    }
+}
+
 template <int ARITH>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
-                                             Hit h, int amb, double y0, double x0, double u, double v,
+                                             const double* ysf, Hit h, int amb, unsigned idx,
                                              bool valid, size_t o, double cx, double cy, RawAcc& acc)
 {
     double ri = 0.0, r2 = 0.0;
@@ -139,7 +148,10 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         clip = r2 > A.a_stop2;
     }
     const bool sv = (ARITH == ORT_ARITH_STRICT) || amb < 0;
-    if (sv) {
+    if (sv) {                                       // rare in FAST mode: recompute the ray's inputs here
+        const unsigned iy = idx / (unsigned)A.nx, ix = idx - iy * (unsigned)A.nx;
+        const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
+        double u, v; field_slopes(fld, y0, x0, u, v);
         h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(P.s, P.nsurf, A.stop, y0, x0, u, v)
                                         : trace_strict_cold(P.s, P.nsurf, A.stop, y0, x0, u, v);
         ri = jl_hypot(h.xs, h.ys);                                      // :131
@@ -175,17 +187,8 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     return kept;
 }
 
-__device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, double x0, double& u, double& v)
-{
-    u = fld.u; v = fld.v;
-    if (fld.mode == 1) {                         // RayBasis: :124-127 then tan at :38-39
-        u = tan(SD(SS(fld.ybar, y0), fld.z0));
-        v = tan(SD(-x0, fld.z0));
-    }
-}
-
 template <int ARITH, int RPT>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? 4 : 2) : 2)
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : ORT_BPS2) : 2)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
     __shared__ RawPart s_part[ORT_TILE / 32];
@@ -235,7 +238,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
-            const int kept = grid_epilogue<ARITH>(P, A, fld, h[j], amb[j], y0[j], x0[j], u[j], v[j], valid[j],
+            const int kept = grid_epilogue<ARITH>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
                                                   fbase + idx[j], cx, cy, acc);
             if (A.tile_counts) {
                 const int c = __syncthreads_count(kept);
@@ -418,6 +421,8 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.kind = (!isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC)) | (n1 != n2 ? SURF_REFR : 0) |
              (n2 < 0.0 ? SURF_N2NEG : 0);
     S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
+    S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
+    S.pad_ = 0;
 }
 
 template <int ARITH>
