@@ -6,7 +6,7 @@ libort_b200.so (include/ort_b200.h).  The Julia shim a maintainer would add is i
 julia/OpticalRayTracingB200.jl; Julia is not installed in this environment, so this Python
 mirror is what drives the same ABI in tests and benchmarks.
 """
-from . import _lib, host, prescriptions
+from . import _lib, distributed, host, prescriptions
 from ._lib import (FAST, STRICT, FLAG_CLIP, FLAG_DOMAIN, FLAG_MISS, FLAG_TIR, Context, OrtError,
                    PinnedArray, STATS_DTYPE)
 from .host import (LAMBDA, SA, TSA, Layout, Lens, RayBasis, RealRay, RealRayError, System,
@@ -15,7 +15,7 @@ from .host import (LAMBDA, SA, TSA, Layout, Lens, RayBasis, RealRay, RealRayErro
                    trace_chief_ray, trace_edge_rays, trace_marginal_ray, transfer, transfer_matrix,
                    wavegrad)
 
-__all__ = ["_lib", "host", "prescriptions", "Context", "OrtError", "PinnedArray", "STATS_DTYPE", "FAST",
+__all__ = ["_lib", "distributed", "host", "prescriptions", "Context", "OrtError", "PinnedArray", "STATS_DTYPE", "FAST",
            "STRICT", "FLAG_MISS", "FLAG_TIR", "FLAG_DOMAIN", "FLAG_CLIP", "LAMBDA", "SA", "TSA",
            "Layout", "Lens", "RayBasis", "RealRay", "RealRayError", "System", "VectorRealRay",
            "flatten", "full_trace", "full_trace_fields", "make_lens", "merge_stats", "raytrace",

@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference API (ort_b200.host) exercised WITHOUT a GPU: the same host code
+with an oracle-backed backend injected (tests/oracle_backend.py).  Checks the reference's known
+answers and that the product host logic agrees with the independent oracle prelude."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle_backend import OracleBackend
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_known_answers.json")) as f:
+    KAT = json.load(f)
+
+
+@pytest.fixture(scope="module")
+def be(orc):
+    return OracleBackend()
+
+
+@pytest.fixture(scope="module")
+def cooke(ort, be):
+    P = ort.prescriptions.COOKE
+    return ort.solve(P["surfaces"], P["a"], P["h"], backend=be)
+
+
+def test_solve_known_answers(ort, cooke):
+    C = KAT["cooke_triplet"]
+    assert abs(cooke.f - C["EFL"]) < 1e-3 and abs(cooke.EBFD - C["BFL"]) < 1e-3 and cooke.stop == 5
+    assert abs(cooke.N - 1 / (2 * C["NA"])) < 1e-3 and abs(cooke.FOV - 2 * C["HFOV"]) < 1e-3
+    yui = np.array(C["yui"])
+    assert np.max(np.abs(cooke.marginal.y - yui[:, 0])) < 1e-2 and np.max(np.abs(cooke.marginal.u - yui[:, 1])) < 1e-2
+    fl = ort.flatten(cooke)
+    assert math.isclose(fl["f"], cooke.f, rel_tol=1e-12) and math.isclose(fl["EBFD"], cooke.EBFD, rel_tol=1e-12)
+    assert math.isclose(fl["EFFD"], cooke.EFFD, rel_tol=1e-12)
+    assert math.isclose(fl["P1"], cooke.P1, rel_tol=1e-9) and math.isclose(fl["P2"], cooke.P2, rel_tol=1e-9)
+
+
+def test_host_prelude_equals_oracle_prelude(ort, pre, be, cooke):
+    P = ort.prescriptions.COOKE
+    so = pre.solve(P["surfaces"], P["a"], P["h"])
+    assert cooke.f == so.f and cooke.EBFD == so.EBFD and cooke.stop == so.stop
+    assert np.array_equal(cooke.marginal.yu, so.marginal.yu) and np.array_equal(cooke.chief.z, so.chief.z)
+    assert np.array_equal(cooke.M, so.M)
+    rm, rmo = ort.trace_marginal_ray(P["surfaces"], cooke, backend=be), pre.trace_marginal_ray_real(P["surfaces"], so)
+    assert np.array_equal(rm.y, rmo.y) and np.array_equal(rm.z, rmo.z)
+    rc, rco = ort.trace_chief_ray(P["surfaces"], cooke, backend=be), pre.trace_chief_ray_real(P["surfaces"], so)
+    assert np.array_equal(rc.y, rco.y) and np.array_equal(rc.z, rco.z)
+    for H in (0.0, 0.7, 1.0):
+        e, eo = ort.full_trace(cooke, H, backend=be), pre.full_trace(so, H)
+        assert len(e.x) == len(eo.x)
+        assert np.array_equal(e.x, eo.x) and np.array_equal(e.y, eo.y) and np.array_equal(e.t, eo.t)
+        assert np.allclose(e.r, eo.r, rtol=1e-15) and math.isclose(e.RMS, eo.RMS, rel_tol=1e-12)
+        assert e.nu == so.marginal.nu[-1] and e.H == H
+        wx, wy = ort.wavegrad(e)
+        assert np.array_equal(wx, e.x * e.nu / ort.LAMBDA)
+
+
+def test_full_trace_singlet_rms(ort, be):
+    SG = KAT["singlet"]
+    P = ort.prescriptions.SINGLET
+    s = ort.solve(P["surfaces"], P["a"], P["h"], backend=be)
+    for H, rms in zip(SG["H"], SG["RMS"]):
+        assert abs(ort.full_trace(s, H, backend=be).RMS - rms) < SG["spot_scale_atol"]
+    with pytest.raises(ValueError):
+        ort.full_trace(s, 1.5, backend=be)                   # DomainError: |H| <= 1 (PupilSampling.jl:89)
+
+
+def test_raytrace_dispatch(ort, be, cooke):
+    P = ort.prescriptions.COOKE
+    S = P["surfaces"]
+    ray = ort.raytrace(S, 1.0, 0.0, ort.RealRay, backend=be)                    # 2-D meridional
+    par = ort.raytrace(S, 1.0, 0.0, backend=be)                                 # paraxial, matrix form
+    assert len(ray.y) == len(S) and abs(ray.y[-1] - par.y[-1]) < 1e-2
+    xv, yv = ort.raytrace(S, 1.0, 0.0, 0.0, 0.0, ort.VectorRealRay, backend=be)  # 3-D skew
+    assert np.allclose(yv, ray.y[1:], rtol=1e-13)
+    ya, wa, ci = ort.raytrace(cooke.lens, np.array([1.0, 2.0]), np.array([0.0, 0.0]), backend=be)
+    assert ya.shape == (len(cooke.lens.tau) + 1, 2) and np.allclose(ya[:, 1], 2 * ya[:, 0])
+    # clip (test/runtests.jl:252-257)
+    ybar = np.abs(cooke.chief.y[1:-1])
+    with np.errstate(divide="ignore"):
+        slope = abs(cooke.chief.u[0] * np.min(P["a"] / ybar))
+    y0 = -slope * cooke.EP.t
+    r1 = ort.raytrace(cooke.lens, y0, slope, P["a"], clip=True, backend=be)
+    r2 = ort.raytrace(cooke.lens, y0 - 1e-12, slope, P["a"], clip=True, backend=be)
+    assert not np.isnan(r1.ynu).any() and np.isnan(r2.ynu).any()
+
+
+def test_raybasis_lagrange_invariant(ort, be, cooke):
+    """test/runtests.jl:94-127"""
+    s = -cooke.f + cooke.EFFD
+    rb = ort.raytrace(cooke, 10.0, s)
+    m, c = rb.marginal, rb.chief
+    assert m.y[-1] == 0.0
+    Hv = c.nu * m.y - m.nu * c.y
+    assert np.allclose(Hv, rb.H, rtol=1e-9)
+    assert math.isclose(c.y[-1], -10.0, rel_tol=1e-9)
+    e = ort.full_trace(cooke.layout, rb, 32, backend=be)      # RayBasis grid mode (PupilSampling.jl:124-127)
+    assert e.H == 1.0 and len(e.x) > 0 and math.isfinite(e.RMS)
+
+
+def test_transfer_and_reverse(ort, be, cooke):
+    v = np.array([3.0, -0.05])
+    w = ort.transfer(cooke, v, -40.0, 12.0, backend=be)
+    assert np.allclose(ort.reverse_transfer(cooke.M, w, 12.0, -40.0, backend=be), v, rtol=1e-11)
+    rv = ort.reverse_transfer(cooke.M, [1.0, 0.0], 0.0, 0.0, backend=be)
+    assert math.isclose(-rv[0] / rv[1], cooke.EFFD, rel_tol=1e-12)       # test/runtests.jl:238
+    batch = ort.transfer(cooke.M, np.tile(v, (5, 1)), 0.0, 0.0, backend=be)
+    assert batch.shape == (5, 2) and np.allclose(batch[0], cooke.M @ v)
+
+
+def test_tsa_and_sa(ort, be, cooke):
+    y, eps_ = ort.TSA(ort.prescriptions.COOKE["surfaces"], cooke, backend=be)
+    B1 = ort.SA(y, eps_, 9)[0]
+    assert abs(B1 / KAT["cooke_triplet"]["W040_book"] - 1) < 0.05        # test/runtests.jl:277-278
+    with pytest.raises(ValueError):
+        ort.SA(y, eps_, 4)
+
+
+def test_layout_rejects_polynomials(ort):
+    with pytest.raises(ValueError):
+        ort.Layout(ort.prescriptions.COOKE["surfaces"], p=[lambda y: y ** 4])
+    L = ort.Layout(ort.prescriptions.PARABOLA["surfaces"])
+    assert L.aspheric and L.K[1] == -1.0
+
+
+def test_merge_stats_matches_direct(ort):
+    rng = np.random.default_rng(3)
+    ex, ey, r = rng.normal(0.3, 0.05, 5000), rng.normal(-0.1, 0.02, 5000), rng.uniform(0, 10, 5000)
+    recs = np.zeros(4, dtype=ort.STATS_DTYPE)
+    cuts = [0, 1000, 1000, 3500, 5000]                      # includes an empty shard
+    for j in range(4):
+        sl = slice(cuts[j], cuts[j + 1])
+        n = cuts[j + 1] - cuts[j]
+        recs[j]["n_kept"] = n
+        if n:
+            recs[j]["mean_x"], recs[j]["mean_y"] = ex[sl].mean(), ey[sl].mean()
+            recs[j]["m2_x"], recs[j]["m2_y"] = ((ex[sl] - ex[sl].mean()) ** 2).sum(), ((ey[sl] - ey[sl].mean()) ** 2).sum()
+            recs[j]["r_max"] = r[sl].max()
+        recs[j]["n_clip"] = j
+    m = ort.merge_stats(recs)
+    assert m["n_kept"] == 5000 and m["n_clip"] == 6 and m["r_max"] == r.max()
+    assert math.isclose(m["mean_x"], ex.mean(), rel_tol=1e-13) and math.isclose(m["mean_y"], ey.mean(), rel_tol=1e-13)
+    assert math.isclose(m["m2_x"], ((ex - ex.mean()) ** 2).sum(), rel_tol=1e-12)
+    x2, y2 = np.concatenate([ex, -ex]), np.concatenate([ey, ey])
+    direct = math.sqrt((((x2 - x2.mean()) ** 2).sum() + ((y2 - y2.mean()) ** 2).sum()) / len(x2))
+    assert math.isclose(ort.rms_from_stats(m), direct, rel_tol=1e-12)
+
+
+def test_shard_rows(ort):
+    for ny, w in ((10, 3), (5792, 8), (7, 8), (0, 2)):
+        spans = [ort.distributed.shard_rows(ny, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == ny
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
