@@ -132,6 +132,17 @@ def cpu_baseline(ort, wl, target_s=12.0, threads=0):
 
 
 def main():
+    # the driver parses ONE JSON line from stdout: route everything else that libraries print to
+    # stdout (e.g. "NCCL version ...") to stderr at the file-descriptor level
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        return _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -150,7 +161,7 @@ def main():
     n = world
 
     if args.impl == "reference":
-        return reference_arm(args, rank, n)
+        return reference_arm(args, rank, n, real_stdout)
 
     import torch
     import ort_b200 as ort
@@ -305,13 +316,13 @@ def main():
         "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
         "clocks": sampler.result(), "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     if n > 1:
         dist.destroy_process_group()
     return 0
 
 
-def reference_arm(args, rank, n):
+def reference_arm(args, rank, n, real_stdout):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  Julia is
     absent, so this is the oracle port (oracle/ort_oracle.c), all host threads, on the same workload;
     each step is a bounded sample (a block of y-rows of every field)."""
@@ -359,7 +370,7 @@ def reference_arm(args, rank, n):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 

@@ -1,0 +1,218 @@
+# OpticalRayTracingB200.jl -- drop-in GPU methods for the data-parallel hot path of
+# OpticalRayTracing.jl, bound to libort_b200.so (include/ort_b200.h) with plain `ccall`.
+#
+#   * No CUDA.jl, no Triton, no multi-backend dispatch, no CPU fallback: if the library or a B200 is
+#     missing, `ort_init` fails and the error is thrown.
+#   * The public API is unchanged: this module only ADDS methods with the reference's own
+#     signatures / return types (and batch variants taking vectors).
+#   * NOT RUNNABLE in the build environment (Julia is not installed there); the same C ABI is driven
+#     from Python (opticalraytracing.jl_b200/_lib.py, host.py) in tests and benchmarks.
+#
+# Library path: ENV["ORT_B200_LIB"] (default "libort_b200.so" on the loader path).
+module OpticalRayTracingB200
+
+using OpticalRayTracing
+using OpticalRayTracing: Layout, Lens, System, RayBasis, SystemOrRayBasis, RealRay, RealRayError,
+                         TransferMatrix, trace_chief_ray, trace_marginal_ray, trace_edge_rays,
+                         spot_rays, λ
+import OpticalRayTracing: full_trace, raytrace, transfer, reverse_transfer
+
+const LIB = get(ENV, "ORT_B200_LIB", "libort_b200.so")
+
+const ORT_ARITH_STRICT = Cint(0)
+const ORT_ARITH_FAST = Cint(1)
+
+# --- POD mirrors of include/ort_b200.h -------------------------------------------------------
+struct OrtField            # ort_field
+    mode::Int32
+    reserved::Int32
+    u::Float64
+    v::Float64
+    ybar::Float64
+    z0::Float64
+    h_prime::Float64
+end
+
+struct OrtOpts             # ort_opts
+    arith::Int32
+    compact::Int32
+    ys_per_field::Int32
+    reserved::Int32
+    wg_nu::Float64
+    wg_lambda::Float64
+end
+
+struct OrtStats            # ort_stats
+    n_kept::Int64
+    mean_x::Float64
+    mean_y::Float64
+    m2_x::Float64
+    m2_y::Float64
+    r_max::Float64
+    n_miss::Int64
+    n_tir::Int64
+    n_domain::Int64
+    n_clip::Int64
+end
+
+struct OrtGridOut          # ort_grid_out
+    ex::Ptr{Float64}
+    ey::Ptr{Float64}
+    r::Ptr{Float64}
+    theta::Ptr{Float64}
+    wx::Ptr{Float64}
+    wy::Ptr{Float64}
+    mask::Ptr{UInt8}
+    flags::Ptr{UInt8}
+    stats::Ptr{OrtStats}
+end
+
+# --- context ---------------------------------------------------------------------------------
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:ort_last_error, LIB), Cstring, (Ptr{Cvoid},), CTX[]))
+    error("libort_b200 error $rc: $msg")
+end
+
+function ctx()
+    if CTX[] == C_NULL
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        dev = parse(Cint, get(ENV, "LOCAL_RANK", "0"))
+        rc = ccall((:ort_init, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), out, dev)
+        CTX[] = out[]
+        check(rc)
+        atexit(() -> ccall((:ort_free, LIB), Cvoid, (Ptr{Cvoid},), CTX[]))
+    end
+    return CTX[]
+end
+
+# Aspheric polynomial terms are Julia closures: they cannot cross the C ABI.
+function require_conic(surfaces::Layout)
+    all(p -> p.f === zero, surfaces.p) ||
+        throw(ArgumentError("OpticalRayTracingB200: polynomial aspheric terms (p ≢ zero) are not supported on the GPU path"))
+end
+
+function set_layout(R::Vector{Float64}, t::Vector{Float64}, n::Vector{Float64}, K::Vector{Float64})
+    check(ccall((:ort_set_layout, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx(), length(R), R, t, n, K))
+end
+
+# --- full_trace: src/PupilSampling.jl:85-147 -------------------------------------------------
+# Lines :85-114 (prelude, ray aiming, Optim) are kept verbatim; the hot loop :115-138 and the
+# reductions :139-146 become ONE ccall.
+function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
+                    k_rays::Int = spot_rays,
+                    focus = system.marginal.z[end] - system.marginal.z[end-1];
+                    arith = ORT_ARITH_FAST)
+    require_conic(surfaces)
+    H = abs(H)
+    H ≤ 1.0 || throw(DomainError(H, "Domain: |H| ≤ 1.0"))
+    stop = system.stop
+    a_stop = abs(system.a[stop])
+    real_chief = trace_chief_ray(surfaces, system)
+    real_marginal = trace_marginal_ray(surfaces, system)
+    EP_t = real_chief.z[1]
+    Ū = real_chief.u[1]
+    U = H * Ū
+    u = tan(U)
+    y_EP = abs(real_marginal.y[1])
+    y1, y2 = (±(y_EP) - u * EP_t for (±) ∈ (+, -))
+    y1, y2 = trace_edge_rays(surfaces, y1, y2, U, stop, a_stop)
+    if typeof(system) <: System
+        field = OrtField(0, 0, u, tan(0.0), 0.0, 1.0, u * system.f)
+    else
+        z0 = system.marginal.z[1]
+        ȳ = system.chief.y[2] + system.chief.u[1] * z0
+        field = OrtField(1, 0, 0.0, 0.0, ȳ, z0, system.chief.y[end])
+    end
+    # extend the surface matrix to the paraxial image plane (:111-114)
+    R = [surfaces.R; Inf]; t = [surfaces.t; 0.0]; n = [surfaces.n; 1.0]; K = [surfaces.K; 0.0]
+    t[end-1] = focus
+    set_layout(R, t, n, K)
+    ys = collect(range(y1, y2, k_rays))              # :121  (TwicePrecision range evaluated in Julia)
+    xs = collect(range(0.0, y_EP, div(k_rays, 2)))   # :122
+    N = length(ys) * length(xs)
+    εx = Vector{Float64}(undef, N); εy = similar(εx); r = similar(εx); θ = similar(εx)
+    stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+    opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0))    # compact = 1: the reference's push! order
+    GC.@preserve εx εy r θ stats begin
+        out = Ref(OrtGridOut(pointer(εx), pointer(εy), pointer(r), pointer(θ), C_NULL, C_NULL,
+                             C_NULL, C_NULL, Base.unsafe_convert(Ptr{OrtStats}, stats)))
+        check(ccall((:ort_trace3d_grid, LIB), Cint,
+                    (Ptr{Cvoid}, Ref{OrtField}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64,
+                     Ref{OrtOpts}, Ref{OrtGridOut}),
+                    ctx(), Ref(field), 1, ys, length(ys), xs, length(xs), stop, a_stop, opts, out))
+    end
+    nk = stats[].n_kept
+    resize!(εx, nk); resize!(εy, nk); resize!(r, nk); resize!(θ, nk)
+    # take advantage of symmetry (:139-146)
+    εy = [εy; εy]
+    εx = [εx; -εx]
+    ρ = r / stats[].r_max
+    ρ = [ρ; ρ]
+    θ = [θ; π .- θ]
+    nu = system.marginal.nu[end]
+    # σ(εx, εy) (:169-173) from the kernel's mergeable moments: mirrored x has mean 0
+    s = stats[]
+    RMS = sqrt((2 * (s.m2_x + nk * s.mean_x^2) + 2 * s.m2_y) / (2 * nk))
+    return RealRayError(εx, εy, nu, ρ, θ, H, RMS)
+end
+
+# --- batched 2-D meridional real rays: src/RayTracing.jl:145-173 ------------------------------
+# Returns (y, U, ts), each rows × N, for N rays in one kernel launch.
+function raytrace(surfaces::Layout{T}, ys::Vector{Float64}, Us::Vector{Float64}, ::Type{RealRay}) where T
+    require_conic(surfaces)
+    set_layout(surfaces.R, surfaces.t, surfaces.n, surfaces.K)
+    rows, N = length(surfaces.R), length(ys)
+    y = Matrix{Float64}(undef, N, rows); U = similar(y); ts = similar(y)   # [rows][N], ray index fastest
+    flags = Vector{UInt8}(undef, N)
+    aspheric = T <: OpticalRayTracing.Aspheric ? 1 : 0                     # :171-173 dispatch
+    check(ccall((:ort_trace2d_batch, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
+                ctx(), N, ys, Us, aspheric, y, U, ts, flags))
+    return permutedims(y), permutedims(U), permutedims(ts)
+end
+
+# --- batched paraxial y-nu: src/RayTracing.jl:127-143 ------------------------------------------
+# Returns the reference's rt tables (k+1) × N for y and nu, plus the clip row per ray.
+function raytrace(lens::Lens, ys::Vector{Float64}, ωs::Vector{Float64},
+                  a::AbstractVector = fill(Inf, size(lens, 1)); clip = false)
+    τ, ϕ = collect(lens[:,1]), collect(lens[:,2])
+    k, N = length(τ), length(ys)
+    yf = Vector{Float64}(undef, N); ωf = similar(yf); ci = Vector{Int32}(undef, N)
+    Y = Matrix{Float64}(undef, N, k + 1); W = similar(Y)
+    av = collect(Float64, a)
+    check(ccall((:ort_paraxial_batch, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Int64, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                ctx(), k, τ, ϕ, av, clip ? 1 : 0, ORT_ARITH_STRICT, N, ys, ωs, yf, ωf, ci, Y, W))
+    return permutedims(Y), permutedims(W), ci
+end
+
+# --- batched transfer-matrix apply: src/TransferMatrix.jl:8-17 ---------------------------------
+# V is 2 × N ([y; nu] per column), exactly Julia's column-major memory.
+function transfer(M::AbstractMatrix, V::Matrix{Float64}, τ, τ′)
+    size(V, 1) == 2 || throw(DimensionMismatch("V must be 2 × N"))
+    Mc = collect(Float64, M); out = similar(V)
+    check(ccall((:ort_transfer_batch, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Cint, Int64, Ptr{Float64}, Ptr{Float64}),
+                ctx(), Mc, τ, τ′, 0, size(V, 2), V, out))
+    return out
+end
+
+function reverse_transfer(M::AbstractMatrix, V::Matrix{Float64}, τ′, τ)
+    size(V, 1) == 2 || throw(DimensionMismatch("V must be 2 × N"))
+    Mc = collect(Float64, M); out = similar(V)
+    check(ccall((:ort_transfer_batch, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Cint, Int64, Ptr{Float64}, Ptr{Float64}),
+                ctx(), Mc, τ, τ′, 1, size(V, 2), V, out))
+    return out
+end
+
+transfer(system::System, V::Matrix{Float64}, τ, τ′) = transfer(system.M, V, τ, τ′)
+reverse_transfer(system::System, V::Matrix{Float64}, τ′, τ) = reverse_transfer(system.M, V, τ′, τ)
+
+end # module

@@ -60,50 +60,69 @@ k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
 
 // ------------------------------------------------------------------------------------------
 // K3: raytrace(lens, y, w, a; clip)  src/RayTracing.jl:127-143 with transfer/refract :55-69.
-// Lens rows live in the constant bank.  STRICT = reference order (mul, add); FAST = DFMA.
+// 4 rays per thread, row loop in convergent control flow so the Lens rows are read through the
+// uniform datapath (constant bank -> uniform registers) once per row for all 4 rays.
+// STRICT = reference order (mul, add: never contracted); FAST = DFMA.  32 B of HBM traffic per ray
+// (+4 B with clip indices): FAST is HBM-bound, STRICT sits at the FP64-issue / HBM crossover.
+// Clip test `abs(y) - a[i] > 1e-13` (:135): an integer pre-filter on the exponent/mantissa high
+// word skips the exact FP64 test for rays that are not within 2^-19 of the aperture edge.
 // ------------------------------------------------------------------------------------------
-template <int ARITH, bool TABLE>
+#define PX_RPT 4
+template <int ARITH, bool TABLE, bool CLIP>
 __global__ void __launch_bounds__(256)
 k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
 {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= A.N) return;
     const long long N = A.N;
-    double y = A.y0[i], w = A.w0[i];
-    int ci = 0;
-    if (TABLE) {
-        if (A.y_all) A.y_all[i] = y;
-        if (A.w_all) A.w_all[i] = w;
+    const long long base = (long long)blockIdx.x * (256 * PX_RPT) + threadIdx.x;
+    double y[PX_RPT], w[PX_RPT];
+    int ci[PX_RPT];
+    long long idx[PX_RPT];
+    bool valid[PX_RPT];
+#pragma unroll
+    for (int j = 0; j < PX_RPT; j++) {
+        const long long i = base + (long long)j * 256;
+        valid[j] = i < N;
+        idx[j] = valid[j] ? i : N - 1;               // padded lanes redo the last ray: warp stays convergent
+        y[j] = __ldcs(A.y0 + idx[j]); w[j] = __ldcs(A.w0 + idx[j]);
+        ci[j] = 0;
+        if (TABLE && valid[j]) {
+            if (A.y_all) A.y_all[idx[j]] = y[j];
+            if (A.w_all) A.w_all[idx[j]] = w[j];
+        }
     }
     const int k = L.k;
-    int j = 0;
-    for (; j < k; j++) {
-        const double tau = L.tau[j], phi = L.phi[j];
-        if (ARITH == ORT_ARITH_STRICT) {
-            if (isfinite(tau)) y = SA(y, SM(w, tau));            // :62
-            w = SS(w, SM(y, phi));                               // :67
-        } else {
-            if (isfinite(tau)) y = fma(w, tau, y);
-            w = fma(-y, phi, w);
+    for (int row = 0; row < k; row++) {
+        const double tau = L.tau[row], phi = L.phi[row];
+        const bool fin = isfinite(tau);                  // uniform (:62)
+        const double a = CLIP ? L.a[row] : 0.0;
+        const int a_hi = CLIP ? (__double2hiint(a) - 1) : 0;
+        if (fin) {                                       // uniform branch, not a per-ray select
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++)
+                y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);   // :62
         }
-        if (L.clip && SS(fabs(y), L.a[j]) > 1e-13) {             // :135
-            ci = j + 1; y = CUDART_NAN; w = CUDART_NAN;
-            break;
-        }
-        if (TABLE) {
-            if (A.y_all) A.y_all[(size_t)(j + 1) * N + i] = y;
-            if (A.w_all) A.w_all[(size_t)(j + 1) * N + i] = w;
+#pragma unroll
+        for (int j = 0; j < PX_RPT; j++) {
+            w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);       // :67
+            if (CLIP) {
+                // |y| >= a (1 - 2^-20) by high word, or NaN / negative a: do the exact test of :135
+                if ((__double2hiint(y[j]) & 0x7FFFFFFF) >= a_hi && ci[j] == 0) {
+                    if (SS(fabs(y[j]), a) > 1e-13) { ci[j] = row + 1; y[j] = CUDART_NAN; w[j] = CUDART_NAN; }
+                }
+            }
+            if (TABLE && valid[j]) {                                 // rt[i+1,:] (NaN after the clip row, :136)
+                if (A.y_all) A.y_all[(size_t)(row + 1) * N + idx[j]] = y[j];
+                if (A.w_all) A.w_all[(size_t)(row + 1) * N + idx[j]] = w[j];
+            }
         }
     }
-    if (TABLE && ci) {                                           // rt[i+1:end,:] .= NaN  :136
-        for (; j < k; j++) {
-            if (A.y_all) A.y_all[(size_t)(j + 1) * N + i] = CUDART_NAN;
-            if (A.w_all) A.w_all[(size_t)(j + 1) * N + i] = CUDART_NAN;
-        }
+#pragma unroll
+    for (int j = 0; j < PX_RPT; j++) {
+        if (!valid[j]) continue;
+        if (A.y) __stcs(A.y + idx[j], y[j]);
+        if (A.w) __stcs(A.w + idx[j], w[j]);
+        if (A.clip_idx) A.clip_idx[idx[j]] = ci[j];
     }
-    if (A.y) A.y[i] = y;
-    if (A.w) A.w[i] = w;
-    if (A.clip_idx) A.clip_idx[i] = ci;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -116,7 +135,7 @@ __global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
     const long long stride = (long long)gridDim.x * 256;
     const double a11 = A.E[0], a21 = A.E[1], a12 = A.E[2], a22 = A.E[3];
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < A.N; i += stride) {
-        const double2 v = A.v_in[i];
+        const double2 v = __ldcs(A.v_in + i);
         double2 o;
         if (!A.reverse) {
             o.x = SA(SM(a11, v.x), SM(a12, v.y));
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
             o.y = SD(y2, u22);
             o.x = SD(SS(b1, SM(p12, o.y)), p11);
         }
-        A.v_out[i] = o;
+        __stcs(A.v_out + i, o);
     }
 }
 
@@ -172,16 +191,20 @@ cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st
 
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st)
 {
-    const unsigned nb = (unsigned)((A.N + 255) / 256);
+    const long long per = 256 * PX_RPT;
+    const unsigned nb = (unsigned)((A.N + per - 1) / per);
     if (nb == 0) return cudaSuccess;
     const bool table = A.y_all || A.w_all;
+    const bool clip = L.clip != 0;
+#define PX_LAUNCH(AR, TB, CL) k_paraxial<AR, TB, CL><<<nb, 256, 0, st>>>(L, A)
     if (arith == ORT_ARITH_FAST) {
-        if (table) k_paraxial<ORT_ARITH_FAST, true><<<nb, 256, 0, st>>>(L, A);
-        else k_paraxial<ORT_ARITH_FAST, false><<<nb, 256, 0, st>>>(L, A);
+        if (table) { if (clip) PX_LAUNCH(ORT_ARITH_FAST, true, true); else PX_LAUNCH(ORT_ARITH_FAST, true, false); }
+        else       { if (clip) PX_LAUNCH(ORT_ARITH_FAST, false, true); else PX_LAUNCH(ORT_ARITH_FAST, false, false); }
     } else {
-        if (table) k_paraxial<ORT_ARITH_STRICT, true><<<nb, 256, 0, st>>>(L, A);
-        else k_paraxial<ORT_ARITH_STRICT, false><<<nb, 256, 0, st>>>(L, A);
+        if (table) { if (clip) PX_LAUNCH(ORT_ARITH_STRICT, true, true); else PX_LAUNCH(ORT_ARITH_STRICT, true, false); }
+        else       { if (clip) PX_LAUNCH(ORT_ARITH_STRICT, false, true); else PX_LAUNCH(ORT_ARITH_STRICT, false, false); }
     }
+#undef PX_LAUNCH
     return cudaGetLastError();
 }
 
@@ -189,7 +212,7 @@ cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st)
 {
     if (A.N == 0) return cudaSuccess;
     long long nb = (A.N + 255) / 256;
-    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb > 148 * 32) nb = 148 * 32;
     k_transfer<<<(unsigned)nb, 256, 0, st>>>(A);
     return cudaGetLastError();
 }

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Measures the secondary kernels of the hot path on one B200 (not a driver bench line):
+  K3 paraxial y-nu trace, 40-row Lens (BASELINE config 4 shape)     -- HBM / FP64 balanced
+  K4 transfer-matrix apply (forward and reverse)                    -- HBM bound
+  K5 candidate-batched 3-D trace (BASELINE config 5 shape)          -- FP64 bound
+  K1 with all outputs (r, theta) and with ordered compaction
+Prints one JSON object; device-resident inputs, CUDA-event timing via ort_profile_*."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ort_b200 as ort  # noqa: E402
+
+HBM = 6544.0
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    HBM = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timed(ctx, fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ctx.profile_enable(True)
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    t = ctx.profile_read()
+    ctx.profile_enable(False)
+    return float(np.mean(t)), float(np.min(t))
+
+
+def main():
+    N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 28          # rays for K3 / K4
+    dev = torch.device("cuda", 0)
+    ctx = ort.Context(0)
+    ort.set_default_backend(ctx)
+    st = torch.cuda.current_stream().cuda_stream
+    peak, _ = ctx.fp64_peak()
+    out = {"fp64_peak_tflops": peak, "hbm_peak_gbs": HBM, "N": N}
+
+    # ---- K3: 40-row paraxial trace, rays generated on the device (counter-based, seed 42)
+    S = ort.prescriptions.zoom20()
+    lens = ort.make_lens(S)
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    y0 = (torch.rand(N, dtype=torch.float64, device=dev, generator=g) * 20 - 10)
+    w0 = (torch.rand(N, dtype=torch.float64, device=dev, generator=g) * 0.4 - 0.2)
+    y = torch.empty_like(y0); w = torch.empty_like(w0)
+    ci = torch.empty(N, dtype=torch.int32, device=dev)
+    a = np.full(len(lens.tau), 25.0)
+    for name, arith, clip in (("fast", ort.FAST, False), ("strict", ort.STRICT, False), ("fast_clip", ort.FAST, True)):
+        ms, best = timed(ctx, lambda: ctx.paraxial_batch_dev(lens.tau, lens.phi, N, y0.data_ptr(), w0.data_ptr(), y.data_ptr(),
+                                                            w.data_ptr(), ci.data_ptr() if clip else None, a=a if clip else None,
+                                                            clip=clip, arith=arith, stream=st))
+        byts = N * (32 + (4 if clip else 0))
+        out[f"paraxial40_{name}"] = {"ms": ms, "rays_per_s": N / ms * 1e3, "GBps": byts / ms / 1e6, "hbm_frac": byts / ms / 1e6 / HBM,
+                                     "tflops_nominal": N * 160 / ms / 1e9, "fp64_frac": N * 160 / ms / 1e9 / peak}
+    # ---- K4: transfer matrix
+    sysm = ort.solve(ort.prescriptions.COOKE["surfaces"], ort.prescriptions.COOKE["a"], ort.prescriptions.COOKE["h"])
+    v = torch.stack([y0, w0], dim=1).contiguous()
+    vo = torch.empty_like(v)
+    for name, rev in (("forward", False), ("reverse", True)):
+        ms, best = timed(ctx, lambda: ctx.transfer_batch_dev(sysm.M, -50.0, 77.4, N, v.data_ptr(), vo.data_ptr(), reverse=rev, stream=st))
+        out[f"transfer_{name}"] = {"ms": ms, "rays_per_s": N / ms * 1e3, "GBps": N * 32 / ms / 1e6, "hbm_frac": N * 32 / ms / 1e6 / HBM}
+    # size-independent property at full size: reverse(forward(v)) == v
+    ctx.transfer_batch_dev(sysm.M, -50.0, 77.4, N, v.data_ptr(), vo.data_ptr(), stream=st)
+    back = torch.empty_like(v)
+    ctx.transfer_batch_dev(sysm.M, -50.0, 77.4, N, vo.data_ptr(), back.data_ptr(), reverse=True, stream=st)
+    torch.cuda.synchronize()
+    out["transfer_roundtrip_max_abs_err"] = float((back - v).abs().max())
+    del v, vo, back, y0, w0, y, w, ci
+    torch.cuda.empty_cache()
+
+    # ---- K5: candidates (config 5: C triplet variants x 4096 rays)
+    C = int(float(sys.argv[2])) if len(sys.argv) > 2 else 65536
+    p = ort.host._full_trace_setup(sysm.layout, sysm, [0.7], 64, None, ctx)
+    rows = p["ext"].shape[0]
+    base = ort.prescriptions.perturbed_triplets(C)
+    RtnK = np.zeros((C, 4, rows)); RtnK[:, :, :-1] = base
+    RtnK[:, 0, -1] = np.inf; RtnK[:, 2, -1] = 1.0; RtnK[:, 1, -2] = p["focus"]
+    d_R = torch.from_numpy(RtnK).to(dev)
+    ys = torch.from_numpy(np.linspace(p["y1"][0], p["y2"][0], 64)).to(dev)
+    xs = torch.from_numpy(np.linspace(-p["y_EP"], p["y_EP"], 64)).to(dev)
+    d_o = torch.empty((C, 4), dtype=torch.float64, device=dev)
+    fld = dict(u=float(p["u"][0]), v=0.0, h_prime=float(p["h_prime"][0]))
+    for name, arith in (("fast", ort.FAST), ("strict", ort.STRICT)):
+        ms, best = timed(ctx, lambda: ctx.trace3d_candidates_dev(rows, C, d_R.data_ptr(), fld, ys.data_ptr(), 64, xs.data_ptr(), 64,
+                                                                p["stop"], p["a_stop"], d_o.data_ptr(), arith=arith, stream=st), reps=5, warm=2)
+        rays = C * 4096
+        out[f"candidates_{name}"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "rays_per_s": rays / ms * 1e3,
+                                     "intersections_per_s_x7": rays * 7 / ms * 1e3, "tflops_nominal": rays * 513 / ms / 1e9,
+                                     "fp64_frac": rays * 513 / ms / 1e9 / peak}
+    res = d_o.cpu().numpy()
+    out["candidates_rms_range"] = [float(np.nanmin(res[:, 3])), float(np.nanmax(res[:, 3]))]
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
