@@ -237,29 +237,38 @@ def _main(real_stdout):
     kept = [int(m["n_kept"]) for m in merged]
 
     # ---- e2e: the C-ABI host-pointer call, pinned host buffers, H2D of the grid coordinates and
-    #      D2H of spot diagram + mask + statistics inside the timed region ----
+    #      D2H of spot diagram + mask + statistics inside the timed region.  Two output forms are
+    #      timed: the full grid (ex, ey over every traced ray + mask) and the reference's own form
+    #      (ex, ey compacted to the kept rays in push! order + mask), which moves ~21 % fewer bytes
+    #      over PCIe.  The headline e2e is the compacted form (what full_trace returns). ----
     e2e_steps = max(2, min(args.steps, 5))
     h_ex, h_ey = ort.PinnedArray((nf, NN)), ort.PinnedArray((nf, NN))
     h_mask = ort.PinnedArray((nf, NN), dtype=np.uint8)
     out = dict(ex=h_ex.array, ey=h_ey.array, mask=h_mask.array)
-    ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith, want=("ex", "ey", "mask"), out=out)
-    barrier()
-    l1 = ctx.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith,
+    e2e = {}
+    for form, compact in (("full_grid", False), ("compacted", True)):
+        r = ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith, compact=compact,
                              want=("ex", "ey", "mask"), out=out)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    e2e_launches = ctx.launch_count() - l1
-    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if n > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = rays_step * inter_ray * e2e_steps / float(t_e.item())
+        barrier()
+        l1 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith, compact=compact,
+                                 want=("ex", "ey", "mask"), out=out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if n > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        kept_n = int(r["stats"]["n_kept"].sum())
+        e2e[form] = {"value": rays_step * inter_ray * e2e_steps / float(t_e.item()), "ms_per_step": float(t_e.item()) / e2e_steps * 1e3,
+                     "launches": int(ctx.launch_count() - l1),
+                     "d2h": (kept_n * 16 + nf * NN + nf * 80) if compact else (nf * NN * BYTES_PER_RAY + nf * 80)}
+        assert [int(k) for k in r["stats"]["n_kept"]] == [int(s["n_kept"]) for s in stats[rank]], \
+            "host-pointer and device-pointer paths disagree"
+    best = "compacted"
+    e2e_value, e2e_ms, e2e_launches, d2h = e2e[best]["value"], e2e[best]["ms_per_step"], e2e[best]["launches"], e2e[best]["d2h"]
     h2d = (nf * NY + NX) * 8
-    d2h = nf * NN * BYTES_PER_RAY + nf * 80
-    e2e_kept = [int(k) for k in r["stats"]["n_kept"]]
-    assert e2e_kept == [int(s["n_kept"]) for s in stats[rank]], "host-pointer and device-pointer paths disagree"
 
     if rank != 0:
         if n > 1:
@@ -311,8 +320,11 @@ def _main(real_stdout):
             "spot_rms_mm": [round(x, 9) for x in rms], "kept_rays": kept,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": float(t_e.item()) / e2e_steps * 1e3,
-                "api": "ort_trace3d_grid (host pointers, pinned), per-field launches overlapped with D2H"},
+                "steps": e2e_steps, "ms_per_step": e2e_ms,
+                "api": "ort_trace3d_grid (host pointers, pinned host buffers), outputs ex, ey compacted to the kept rays "
+                       "in the reference's push! order + mask + stats; per-field launches overlapped with D2H",
+                "full_grid_form": {"value": e2e["full_grid"]["value"], "ms_per_step": e2e["full_grid"]["ms_per_step"],
+                                   "d2h_bytes_per_step": e2e["full_grid"]["d2h"]}},
         "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
         "clocks": sampler.result(), "roofline": roofline, "cpu_baseline": cpu,
     }

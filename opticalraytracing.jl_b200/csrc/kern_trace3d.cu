@@ -422,7 +422,7 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
              (n2 < 0.0 ? SURF_N2NEG : 0);
     S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
     S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
-    S.pad_ = 0;
+    S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
 }
 
 template <int ARITH>

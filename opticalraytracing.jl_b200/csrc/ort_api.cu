@@ -99,7 +99,7 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     const double thr1 = n1 * n1 * 9.313225746154785e-10;        // 2^-30 n1^2
     memcpy(&bits, &thr1, 8);
     S.gr_thr = (int32_t)(bits >> 32);
-    S.pad_ = 0;
+    S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
 }
 
 // bracket the dominant kernel with an event pair (measurement only)
