@@ -177,6 +177,7 @@ def _main(real_stdout):
     wl = workload(ort, ctx, n, rank)
     p, fields = wl["p"], wl["fields"]
     nf, NN = len(fields), NY * NX
+    SB = ort.STATS_BYTES
     ctx.set_layout(p["ext"], p["K"])
     arith = ort.FAST if args.arith == "fast" else ort.STRICT
 
@@ -186,8 +187,8 @@ def _main(real_stdout):
     d_ex = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_ey = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_mask = torch.empty((nf, NN), dtype=torch.uint8, device=dev)
-    d_stats = torch.zeros((nf, 80), dtype=torch.uint8, device=dev)
-    d_gather = torch.zeros((n, nf, 80), dtype=torch.uint8, device=dev) if n > 1 else None
+    d_stats = torch.zeros((nf, SB), dtype=torch.uint8, device=dev)
+    d_gather = torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) if n > 1 else None
     ptrs = dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats.data_ptr())
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -230,7 +231,7 @@ def _main(real_stdout):
     value = rays_step * inter_ray / (ms_step * 1e-3)
 
     # statistics of the last step, merged across ranks in rank order (Chan) -- evidence, not timed
-    stats = np.frombuffer((d_gather if n > 1 else d_stats.view(1, nf, 80)).cpu().numpy().tobytes(),
+    stats = np.frombuffer((d_gather if n > 1 else d_stats.view(1, nf, SB)).cpu().numpy().tobytes(),
                           dtype=ort.STATS_DTYPE).reshape(n, nf)
     merged = [ort.merge_stats(stats[:, f]) for f in range(nf)]
     rms = [ort.rms_from_stats(m) for m in merged]
@@ -263,7 +264,7 @@ def _main(real_stdout):
         kept_n = int(r["stats"]["n_kept"].sum())
         e2e[form] = {"value": rays_step * inter_ray * e2e_steps / float(t_e.item()), "ms_per_step": float(t_e.item()) / e2e_steps * 1e3,
                      "launches": int(ctx.launch_count() - l1),
-                     "d2h": (kept_n * 16 + nf * NN + nf * 80) if compact else (nf * NN * BYTES_PER_RAY + nf * 80)}
+                     "d2h": (kept_n * 16 + nf * NN + nf * SB) if compact else (nf * NN * BYTES_PER_RAY + nf * SB)}
         assert [int(k) for k in r["stats"]["n_kept"]] == [int(s["n_kept"]) for s in stats[rank]], \
             "host-pointer and device-pointer paths disagree"
     best = "compacted"
@@ -314,7 +315,7 @@ def _main(real_stdout):
                         f"{NY}x{NX} per field x {nf} fields per GPU, outputs ex, ey, mask + per-field spot stats",
             "arith": args.arith, "rays_per_step": rays_step, "intersections_per_ray": inter_ray,
             "loop_steps_per_ray": LOOP_STEPS, "value_x12_loop_steps": value * LOOP_STEPS / inter_ray,
-            "parallelism": f"rays sharded by y-rows over {n} GPU(s); all-gather of {nf} x 80 B stats per rank",
+            "parallelism": f"rays sharded by y-rows over {n} GPU(s); all-gather of {nf} x {SB} B stats per rank",
             "l2": "outputs 1.43 GB per step > 126 MB L2 (rewritten every step); inputs are 70 KB of grid "
                   "coordinates, cache-resident by design",
             "spot_rms_mm": [round(x, 9) for x in rms], "kept_rays": kept,

@@ -51,6 +51,7 @@ extern "C" {
 #define ORT_FLAG_TIR    2u  /* total internal reflection: 3-D tracer continues UNDEVIATED (PupilSampling.jl:27-30,58); 2-D tracer sets U = NaN (RayTracing.jl:164) */
 #define ORT_FLAG_DOMAIN 4u  /* Julia would have thrown DomainError (sqrt/asin of an out-of-range real) */
 #define ORT_FLAG_CLIP   8u  /* r_stop > a_stop (PupilSampling.jl:131-132) */
+#define ORT_FLAG_VIGN  16u  /* EXTENSION (opts.vignette): hypot(x, y) > a[i] at some surface (cf. the paraxial clip, RayTracing.jl:135) */
 
 /* arithmetic modes */
 #define ORT_ARITH_STRICT 0  /* reference operation order, no FMA, IEEE div/sqrt: bit-identical to the CPU restatement */
@@ -69,6 +70,9 @@ typedef struct ort_field {
     double  u, v;     /* mode 0 */
     double  ybar, z0; /* mode 1 */
     double  h_prime;  /* subtracted from the final y (:134) */
+    /* EXTENSION (opts.opd): reference sphere centred at (opd_xc, opd_yc) on the last plane with radius
+       opd_radius (0 = none: OPL to the last plane), and the reference (chief-ray) OPL subtracted */
+    double  opd_xc, opd_yc, opd_radius, opl_ref;
 } ort_field;
 
 typedef struct ort_opts {
@@ -79,10 +83,15 @@ typedef struct ort_opts {
                             holds stats[f].n_kept entries. */
     int32_t ys_per_field; /* 0: ys[ny] shared by all fields.  1: ys[n_fields][ny], each field has its own
                              aimed y-range (the reference aims y1, y2 per field, PupilSampling.jl:99-100,121) */
-    int32_t reserved;
+    int32_t ext;          /* EXTENSION bit field (no reference counterpart): ORT_EXT_OPD accumulates the
+                             optical path length per ray (out->opd = (OPL - field.opl_ref) * opd_scale, stats.mean_opd /
+                             m2_opd); ORT_EXT_VIGNETTE clips at every surface's clear aperture (ort_set_apertures) */
     double  wg_nu;    /* wavegrad (PupilSampling.jl:165-167): wx = ex*wg_nu/wg_lambda.  Used iff wx/wy given. */
     double  wg_lambda;
+    double  opd_scale;    /* e.g. 1/lambda for waves; used iff ORT_EXT_OPD */
 } ort_opts;
+#define ORT_EXT_OPD      1
+#define ORT_EXT_VIGNETTE 2
 
 /* Per-field spot statistics over KEPT rays of the traced half pupil (unmirrored); the host applies
  * the mirror algebra of PupilSampling.jl:139-146,169-173.  Merge-able across GPUs (Chan). */
@@ -92,6 +101,8 @@ typedef struct ort_stats {
     double  m2_x, m2_y;       /* sum of squared deviations about the centroid */
     double  r_max;            /* maximum(r) (:142) */
     int64_t n_miss, n_tir, n_domain, n_clip;   /* rays carrying each flag */
+    int64_t n_vig;            /* EXTENSION: rays clipped by a surface aperture */
+    double  mean_opd, m2_opd; /* EXTENSION: mean and sum of squared deviations of out->opd over kept rays */
 } ort_stats;
 
 /* Output arrays of a grid sweep; any pointer may be NULL (= not wanted). */
@@ -99,6 +110,7 @@ typedef struct ort_grid_out {
     double    *ex, *ey;       /* transverse ray errors: xf, yf - h'                       (:134-135) */
     double    *r, *theta;     /* hypot / atan at the stop surface                         (:131,133,136-137) */
     double    *wx, *wy;       /* wavegrad of ex, ey                                       (:165-167) */
+    double    *opd;           /* EXTENSION: optical path difference per ray (ORT_EXT_OPD) */
     uint8_t   *mask;          /* 1 = kept (always full grid, never compacted)             (:132) */
     uint8_t   *flags;         /* ORT_FLAG_* (always full grid) */
     ort_stats *stats;         /* [n_fields] */
@@ -129,6 +141,10 @@ int         ort_profile_read(ort_ctx *ctx, double *ms_out, int max_n);
 int ort_set_layout(ort_ctx *ctx, int rows, const double *R, const double *t, const double *n,
                    const double *K);
 
+/* EXTENSION: clear semi-apertures a[rows-1] of the surfaces of the current layout (row i+1 <-> a[i]); NULL or
+ * +Inf entries = unlimited.  Used iff opts.ext & ORT_EXT_VIGNETTE.  Must follow ort_set_layout. */
+int ort_set_apertures(ort_ctx *ctx, int n, const double *a);
+
 /* ---- 3-D skew real-ray trace over a pupil grid: replaces the hot loop of full_trace,
  *      src/PupilSampling.jl:115-138 (per-ray body = raytrace(...,Vector{RealRay}) :34-65) plus the
  *      statistics inputs of :139-146,169-173.  ys[ny] = collect(range(y1,y2,k)), xs[nx] =
@@ -148,6 +164,11 @@ int ort_trace3d_grid_dev(ort_ctx *ctx, const ort_field *fields /* host */, int n
 int ort_trace3d_rays(ort_ctx *ctx, int64_t N, const double *y0, const double *x0,
                      const double *u0, const double *v0, int arith,
                      double *xv, double *yv, double *kout, uint8_t *flags);
+/* EXTENSION: same, plus the optical path length to the last surface (opl[N], start term 0) and
+ * per-surface aperture flags when apertures are set. */
+int ort_trace3d_rays_opl(ort_ctx *ctx, int64_t N, const double *y0, const double *x0,
+                         const double *u0, const double *v0, int arith,
+                         double *xv, double *yv, double *kout, uint8_t *flags, double *opl);
 
 /* ---- 2-D meridional real-ray trace of N rays: replaces raytrace(surfaces, y, U, RealRay)
  *      src/RayTracing.jl:145-173.  aspheric = 1 is the Layout{Aspheric} method (:171-173: K from the

@@ -13,15 +13,16 @@ LIB_PATH = os.environ.get("ORT_B200_LIB", os.path.join(_HERE, "lib", "libort_b20
 
 ORT_OK, ORT_EINVAL, ORT_ECUDA, ORT_ENCCL, ORT_EUNSUPPORTED, ORT_ENOMEM = 0, -1, -2, -3, -4, -5
 MAX_ROWS, MAX_FIELDS, MAX_LENS = 64, 32, 128
-FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP = 1, 2, 4, 8
+FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP, FLAG_VIGN = 1, 2, 4, 8, 16
+EXT_OPD, EXT_VIGNETTE = 1, 2
 STRICT, FAST = 0, 1
 
 # every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
     "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
-    "ort_set_layout",
-    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace2d_batch",
+    "ort_set_layout", "ort_set_apertures",
+    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_fp64_peak",
 ]
@@ -39,31 +40,34 @@ class OrtError(RuntimeError):
 
 class Field(C.Structure):
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("u", C.c_double), ("v", C.c_double),
-                ("ybar", C.c_double), ("z0", C.c_double), ("h_prime", C.c_double)]
+                ("ybar", C.c_double), ("z0", C.c_double), ("h_prime", C.c_double),
+                ("opd_xc", C.c_double), ("opd_yc", C.c_double), ("opd_radius", C.c_double), ("opl_ref", C.c_double)]
 
 
 class Opts(C.Structure):
     _fields_ = [("arith", C.c_int32), ("compact", C.c_int32), ("ys_per_field", C.c_int32),
-                ("reserved", C.c_int32), ("wg_nu", C.c_double), ("wg_lambda", C.c_double)]
+                ("ext", C.c_int32), ("wg_nu", C.c_double), ("wg_lambda", C.c_double), ("opd_scale", C.c_double)]
 
 
 class Stats(C.Structure):
     _fields_ = [("n_kept", C.c_int64), ("mean_x", C.c_double), ("mean_y", C.c_double),
                 ("m2_x", C.c_double), ("m2_y", C.c_double), ("r_max", C.c_double),
                 ("n_miss", C.c_int64), ("n_tir", C.c_int64), ("n_domain", C.c_int64),
-                ("n_clip", C.c_int64)]
+                ("n_clip", C.c_int64), ("n_vig", C.c_int64), ("mean_opd", C.c_double), ("m2_opd", C.c_double)]
 
 
 STATS_DTYPE = np.dtype([("n_kept", "<i8"), ("mean_x", "<f8"), ("mean_y", "<f8"), ("m2_x", "<f8"),
                         ("m2_y", "<f8"), ("r_max", "<f8"), ("n_miss", "<i8"), ("n_tir", "<i8"),
-                        ("n_domain", "<i8"), ("n_clip", "<i8")])
-assert STATS_DTYPE.itemsize == C.sizeof(Stats) == 80
+                        ("n_domain", "<i8"), ("n_clip", "<i8"), ("n_vig", "<i8"), ("mean_opd", "<f8"),
+                        ("m2_opd", "<f8")])
+STATS_BYTES = STATS_DTYPE.itemsize
+assert STATS_BYTES == C.sizeof(Stats) == 104
 
 
 class GridOut(C.Structure):
     _fields_ = [("ex", C.c_void_p), ("ey", C.c_void_p), ("r", C.c_void_p), ("theta", C.c_void_p),
-                ("wx", C.c_void_p), ("wy", C.c_void_p), ("mask", C.c_void_p), ("flags", C.c_void_p),
-                ("stats", C.c_void_p)]
+                ("wx", C.c_void_p), ("wy", C.c_void_p), ("opd", C.c_void_p), ("mask", C.c_void_p),
+                ("flags", C.c_void_p), ("stats", C.c_void_p)]
 
 
 _lib = None
@@ -97,11 +101,13 @@ def load():
     L.ort_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.ort_profile_read.argtypes = [C.c_void_p, _dp, C.c_int]
     L.ort_set_layout.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
+    L.ort_set_apertures.argtypes = [C.c_void_p, C.c_int, _dp]
     grid_args = [C.c_void_p, C.POINTER(Field), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                  C.c_int, C.c_double, C.POINTER(Opts), C.POINTER(GridOut)]
     L.ort_trace3d_grid.argtypes = grid_args
     L.ort_trace3d_grid_dev.argtypes = grid_args + [C.c_void_p]
     L.ort_trace3d_rays.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
+    L.ort_trace3d_rays_opl.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p, _dp]
     L.ort_trace2d_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
     L.ort_paraxial_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
                                      _dp, _dp, _dp, _dp, _i32p, _dp, _dp]
@@ -169,7 +175,9 @@ def make_fields(fields):
             arr[i] = f
         else:
             arr[i] = Field(int(f.get("mode", 0)), 0, float(f.get("u", 0.0)), float(f.get("v", 0.0)),
-                           float(f.get("ybar", 0.0)), float(f.get("z0", 1.0)), float(f.get("h_prime", 0.0)))
+                           float(f.get("ybar", 0.0)), float(f.get("z0", 1.0)), float(f.get("h_prime", 0.0)),
+                           float(f.get("opd_xc", 0.0)), float(f.get("opd_yc", 0.0)), float(f.get("opd_radius", 0.0)),
+                           float(f.get("opl_ref", 0.0)))
     return arr, len(fl)
 
 
@@ -240,9 +248,17 @@ class Context:
         self._ck(self.L.ort_set_layout(self.h, len(R), _p(R), _p(t), _p(n), _p(Kc)))
         self.rows = len(R)
 
+    def set_apertures(self, a):
+        """EXTENSION: clear semi-apertures of the surfaces of the current layout (None = unlimited)."""
+        if a is None:
+            self._ck(self.L.ort_set_apertures(self.h, 0, None))
+        else:
+            a = _d(a)
+            self._ck(self.L.ort_set_apertures(self.h, len(a), _p(a)))
+
     # ---- 3-D grid ------------------------------------------------------------------------
     def trace3d_grid(self, fields, ys, xs, stop, a_stop, arith=FAST, compact=False,
-                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None):
+                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None, ext=0, opd_scale=1.0):
         """Host-pointer grid sweep.  Returns dict of numpy arrays shaped (n_fields, ny*nx)
         (+ 'stats' structured array).  `out` may supply preallocated (e.g. pinned) arrays."""
         farr, nf = make_fields(fields)
@@ -253,7 +269,9 @@ class Context:
         ny, nx = ys.shape[-1], len(xs)
         NN = ny * nx
         res = dict(out) if out else {}
-        for name in ("ex", "ey", "r", "theta", "wx", "wy"):
+        if "opd" in want:
+            ext |= EXT_OPD
+        for name in ("ex", "ey", "r", "theta", "wx", "wy", "opd"):
             if name in want and name not in res:
                 res[name] = np.empty((nf, NN), dtype=np.float64)
         for name in ("mask", "flags"):
@@ -261,35 +279,44 @@ class Context:
                 res[name] = np.zeros((nf, NN), dtype=np.uint8)
         stats = np.zeros(nf, dtype=STATS_DTYPE)
         go = GridOut(*[(res[k].ctypes.data if k in res and res[k] is not None else None)
-                       for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags")],
+                       for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags")],
                      stats.ctypes.data)
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
-        op = Opts(int(arith), int(bool(compact)), int(per_field), 0, float(nu), float(lam))
+        op = Opts(int(arith), int(bool(compact)), int(per_field), int(ext), float(nu), float(lam), float(opd_scale))
         self._ck(self.L.ort_trace3d_grid(self.h, farr, nf, _vp(ys), ny, _vp(xs), nx, int(stop),
                                          float(a_stop), C.byref(op), C.byref(go)))
         res["stats"] = stats
         return res
 
     def trace3d_grid_dev(self, fields, d_ys, ny, d_xs, nx, stop, a_stop, ptrs, stream=0,
-                         arith=FAST, compact=False, wavegrad=None, ys_per_field=False):
+                         arith=FAST, compact=False, wavegrad=None, ys_per_field=False, ext=0, opd_scale=1.0):
         """Device-pointer grid sweep (enqueue only).  ptrs: dict name -> device address (int)."""
         farr, nf = make_fields(fields)
-        go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "mask", "flags", "stats")])
+        go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags", "stats")])
+        if ptrs.get("opd"):
+            ext |= EXT_OPD
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
-        op = Opts(int(arith), int(bool(compact)), int(bool(ys_per_field)), 0, float(nu), float(lam))
+        op = Opts(int(arith), int(bool(compact)), int(bool(ys_per_field)), int(ext), float(nu), float(lam),
+                  float(opd_scale))
         self._ck(self.L.ort_trace3d_grid_dev(self.h, farr, nf, C.c_void_p(d_ys), int(ny), C.c_void_p(d_xs),
                                              int(nx), int(stop), float(a_stop), C.byref(op), C.byref(go),
                                              C.c_void_p(stream)))
 
     # ---- arbitrary rays ------------------------------------------------------------------
-    def trace3d_rays(self, y0, x0, u0, v0, arith=STRICT):
+    def trace3d_rays(self, y0, x0, u0, v0, arith=STRICT, opl=False):
+        """-> (xv, yv, k, flags[, opl]); opl=True (EXTENSION) adds the optical path length to the last surface."""
         y0, x0, u0, v0 = _d(y0), _d(x0), _d(u0), _d(v0)
         N, ns = len(y0), self.rows - 1
         xv, yv, k = np.empty((ns, N)), np.empty((ns, N)), np.empty((3, N))
         fl = np.zeros(N, dtype=np.uint8)
-        self._ck(self.L.ort_trace3d_rays(self.h, N, _p(y0), _p(x0), _p(u0), _p(v0), int(arith), _p(xv),
-                                         _p(yv), _p(k), fl.ctypes.data_as(_u8p)))
-        return xv, yv, k, fl
+        if not opl:
+            self._ck(self.L.ort_trace3d_rays(self.h, N, _p(y0), _p(x0), _p(u0), _p(v0), int(arith), _p(xv),
+                                             _p(yv), _p(k), fl.ctypes.data_as(_u8p)))
+            return xv, yv, k, fl
+        ol = np.empty(N)
+        self._ck(self.L.ort_trace3d_rays_opl(self.h, N, _p(y0), _p(x0), _p(u0), _p(v0), int(arith), _p(xv),
+                                             _p(yv), _p(k), fl.ctypes.data_as(_u8p), _p(ol)))
+        return xv, yv, k, fl, ol
 
     def trace2d_batch(self, y0, U0, aspheric=False):
         y0, U0 = _d(y0), _d(U0)

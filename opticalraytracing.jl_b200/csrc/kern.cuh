@@ -6,7 +6,8 @@
 struct RawPart {
     long long n;
     double s1x, s2x, s1y, s2y, rmax, cx, cy;
-    int nmiss, ntir, ndom, nclip;
+    double s1o, s2o, co;                    // EXTENSION: OPD moments about the shift co
+    int nmiss, ntir, ndom, nclip, nvig, pad_;
 };
 
 struct GridArgs {
@@ -18,6 +19,9 @@ struct GridArgs {
     double a_stop, a_stop2;
     double wg_nu, wg_lambda;
     double *ex, *ey, *r, *theta, *wx, *wy;  // device outputs, [n_fields][NN]; NULL = not wanted
+    double *opd;                            // EXTENSION
+    int ext;                                // ORT_EXT_* bits
+    double opd_scale;
     uint8_t *mask, *flags;
     RawPart* partials;                      // [n_fields][gridDim.x]
     int* tile_counts;                       // [n_fields][ntiles] or NULL (no compaction requested)
@@ -28,8 +32,8 @@ struct CompactArgs {
     unsigned NN;
     const uint8_t* mask;
     const int* tile_offsets;
-    const double* src[6];
-    double* dst[6];
+    const double* src[7];
+    double* dst[7];
 };
 
 struct RaysArgs {
@@ -37,6 +41,7 @@ struct RaysArgs {
     const double *y0, *x0, *u0, *v0;
     double *xv, *yv, *kout;
     uint8_t* flags;
+    double* opl;                            // EXTENSION: OPL to the last surface (NULL = not wanted)
 };
 
 struct CandArgs {
@@ -82,7 +87,7 @@ struct TransferArgs {
 #define ORT_BPS2 3                          // ... for k_grid<FAST,2>
 #endif
 int grid_rays_per_thread(int arith);
-int grid_blocks_per_sm(int arith);
+int grid_blocks_per_sm(int arith, int ext);
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st);
 cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fields, ort_stats* stats,
                                  cudaStream_t st);

@@ -19,29 +19,57 @@ struct Hit {               // what the grid epilogue needs from one traced ray
     double xs, ys;         // position at the stop surface   (xv[stop], yv[stop])
     double xf, yf;         // position at the last surface   (xv[end],  yv[end])
     unsigned flags;
+    double opl;            // EXTENSION: optical path length incl. start term and reference sphere
 };
 
-template <class SurfArray>
+// start term of the OPL (EXTENSION): collimated field -> n0 (x k1 + y k2), the lead of the start point
+// over the plane wavefront through the origin; object point at z0 -> n0 (-z0) / k3.  Same operations as
+// orc_opl_start.
+__device__ __forceinline__ double strict_opl_start(const RayS& r, int mode, double n0, double y, double x, double z0)
+{
+    if (mode == 1) return SD(SM(n0, -z0), r.k3);
+    return SM(n0, SA(SM(x, r.k1), SM(y, r.k2)));
+}
+
+// close the OPL on the reference sphere (EXTENSION): tau = -b - sign(rr) sqrt(b^2 - (|q|^2 - rr^2))
+__device__ __forceinline__ double strict_opl_close(const RayS& r, const ort_field& f, double nlast)
+{
+    if (f.opd_radius == 0.0) return r.opl;
+    const double qx = SS(r.x, f.opd_xc), qy = SS(r.y, f.opd_yc);
+    const double b = SA(SM(qx, r.k1), SM(qy, r.k2));
+    const double cq = SS(SA(SM(qx, qx), SM(qy, qy)), SM(f.opd_radius, f.opd_radius));
+    const double sg = (f.opd_radius < 0.0) ? -1.0 : 1.0;
+    const double tau = SS(-b, SM(sg, SQ(SS(SM(b, b), cq))));
+    return SA(r.opl, SM(nlast, tau));
+}
+
+template <bool EXT, class SurfArray>
 __device__ __forceinline__ Hit trace_strict(const SurfArray& S, int nsurf, int stop,
-                                            double y, double x, double u, double v)
+                                            double y, double x, double u, double v,
+                                            const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
+                                            bool vignette = false)
 {
     RayS r;
     strict_init(r, y, x, u, v);
-    Hit h; h.xs = h.ys = CUDART_NAN;
+    if (EXT) r.opl = strict_opl_start(r, fld->mode, n0, y, x, fld->z0);
+    Hit h; h.xs = h.ys = CUDART_NAN; h.opl = 0.0;
     for (int i = 0; i < nsurf; i++) {
-        strict_step(S[i], r);
+        strict_step<EXT>(S[i], r, vignette);
         if (i == stop - 1) { h.xs = r.x; h.ys = r.y; }
     }
     h.xf = r.x; h.yf = r.y; h.flags = r.flags;
+    if (EXT) h.opl = strict_opl_close(r, *fld, nlast);
     return h;
 }
 
 // the strict re-trace of guard-band rays lives out of line so it does not bloat the hot loop
-template <class SurfArray>
+template <bool EXT, class SurfArray>
 __device__ __noinline__ Hit trace_strict_cold(const SurfArray& S, int nsurf, int stop,
-                                              double y, double x, double u, double v)
+                                              double y, double x, double u, double v,
+                                              const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
+                                              bool vignette = false)
 {
-    return trace_strict(S, nsurf, stop, y, x, u, v);
+    return trace_strict<EXT>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette);
 }
 
 // sign bit set iff a is NaN or +-Inf (exponent field all ones)
@@ -56,23 +84,45 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
 // (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
 // (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
-template <int RPT, class SurfArray>
+template <int RPT, bool EXT, class SurfArray>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
-                                           const double* v, Hit* h, int* amb)
+                                           const double* v, Hit* h, int* amb,
+                                           const ort_field* fld = nullptr, double nlast = 1.0, bool vignette = false)
 {
     RaysF<RPT> r;
 #pragma unroll
-    for (int j = 0; j < RPT; j++) fast_init(r, j, n0, y[j], x[j], u[j], v[j]);
+    for (int j = 0; j < RPT; j++) {
+        fast_init(r, j, n0, y[j], x[j], u[j], v[j]);
+        if (EXT) {          // start term: K = n0 k, so n0 (x k1 + y k2) = x Kx + y Ky;  n0 (-z0) / k3 = -n0^2 z0 / Kz
+            r.opl[j] = (fld->mode == 1) ? fast_div(-(n0 * n0) * fld->z0, r.Kz[j]) : fma(x[j], r.Kx[j], y[j] * r.Ky[j]);
+        }
+    }
     int i = 0;
-    for (; i < stop; i++) fast_step<RPT>(S[i], r);
+    for (; i < stop; i++) fast_step<RPT, EXT>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
-    for (; i < nsurf; i++) fast_step<RPT>(S[i], r);
+    for (; i < nsurf; i++) fast_step<RPT, EXT>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
-        h[j].xf = r.x[j]; h[j].yf = r.y[j]; h[j].flags = 0;
+        h[j].xf = r.x[j]; h[j].yf = r.y[j];
+        h[j].flags = (EXT && r.vig[j]) ? ORT_FLAG_VIGN : 0u;
         amb[j] = r.amb[j] | nonfinite_bit(r.x[j]) | nonfinite_bit(r.y[j]) | nonfinite_bit(r.Kz[j]);
+        h[j].opl = 0.0;
+        if (EXT) {          // reference sphere in optical cosines: n tau = -q.K - sgn(rr) sgn(n) sqrt((q.K)^2 - n^2 (|q|^2 - rr^2))
+            double opl = r.opl[j];
+            if (fld->opd_radius != 0.0) {
+                const double qx = r.x[j] - fld->opd_xc, qy = r.y[j] - fld->opd_yc;
+                const double bK = fma(qx, r.Kx[j], qy * r.Ky[j]);
+                const double cq = fma(qx, qx, fma(qy, qy, -fld->opd_radius * fld->opd_radius));
+                const double d = fma(bK, bK, -(nlast * nlast) * cq);
+                double sq = fast_sqrt(d);
+                if ((fld->opd_radius < 0.0) != (nlast < 0.0)) sq = -sq;
+                opl = opl - bK - sq;
+                amb[j] |= nonfinite_bit(opl);
+            }
+            h[j].opl = opl;
+        }
     }
 }
 
@@ -86,6 +136,7 @@ __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int st
 struct RawAcc {
     int n, nflag_lo, nflag_hi;                  // counts; nflag_* pack (miss, tir) and (domain, clip) as 16+16 bits
     double s1x, s2x, s1y, s2y, rmax;            // rmax holds r (strict) or r^2 (fast)
+    double s1o, s2o; int nvig;                  // EXTENSION: OPD moments, vignetted count
 };
 
 __device__ __forceinline__ void raw_add(RawPart& p, const RawPart& q)
@@ -93,6 +144,7 @@ __device__ __forceinline__ void raw_add(RawPart& p, const RawPart& q)
     p.n += q.n; p.s1x += q.s1x; p.s2x += q.s2x; p.s1y += q.s1y; p.s2y += q.s2y;
     p.rmax = fmax(p.rmax, q.rmax);
     p.nmiss += q.nmiss; p.ntir += q.ntir; p.ndom += q.ndom; p.nclip += q.nclip;
+    p.s1o += q.s1o; p.s2o += q.s2o; p.nvig += q.nvig;
 }
 
 __device__ __forceinline__ void raw_warp_reduce(RawPart& p)
@@ -109,6 +161,9 @@ __device__ __forceinline__ void raw_warp_reduce(RawPart& p)
         p.ntir += __shfl_down_sync(0xffffffffu, p.ntir, d);
         p.ndom += __shfl_down_sync(0xffffffffu, p.ndom, d);
         p.nclip += __shfl_down_sync(0xffffffffu, p.nclip, d);
+        p.s1o += __shfl_down_sync(0xffffffffu, p.s1o, d);
+        p.s2o += __shfl_down_sync(0xffffffffu, p.s2o, d);
+        p.nvig += __shfl_down_sync(0xffffffffu, p.nvig, d);
     }
 }
 
@@ -135,11 +190,12 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
     }
 }
 
-template <int ARITH>
+template <int ARITH, bool EXT>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
-                                             bool valid, size_t o, double cx, double cy, RawAcc& acc)
+                                             bool valid, size_t o, double cx, double cy, double co, RawAcc& acc)
 {
+    const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
     double ri = 0.0, r2 = 0.0;
     bool clip = false;
     if (ARITH == ORT_ARITH_FAST) {
@@ -152,19 +208,23 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         const unsigned iy = idx / (unsigned)A.nx, ix = idx - iy * (unsigned)A.nx;
         const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
         double u, v; field_slopes(fld, y0, x0, u, v);
-        h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(P.s, P.nsurf, A.stop, y0, x0, u, v)
-                                        : trace_strict_cold(P.s, P.nsurf, A.stop, y0, x0, u, v);
+        h = (ARITH == ORT_ARITH_STRICT)
+                ? trace_strict<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette)
+                : trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
         r2 = ri * ri;
     } else if (A.r) {
         ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
     }
-    const bool drop = clip || is_nan_bits(h.xf) || is_nan_bits(h.yf);   // :132
+    const bool vig = EXT && (h.flags & ORT_FLAG_VIGN);
+    const bool drop = clip || vig || is_nan_bits(h.xf) || is_nan_bits(h.yf);   // :132 (+ surface apertures)
     const unsigned flags = h.flags | (clip ? ORT_FLAG_CLIP : 0u);
     const int kept = valid && !drop;
     const double ex = h.xf;                                             // :135
     const double ey = sv ? SS(h.yf, fld.h_prime) : h.yf - fld.h_prime;  // :134
+    double opd = 0.0;
+    if (EXT && (A.ext & ORT_EXT_OPD)) opd = sv ? SM(SS(h.opl, fld.opl_ref), A.opd_scale) : (h.opl - fld.opl_ref) * A.opd_scale;
     if (valid) {
         if (A.ex) A.ex[o] = ex;
         if (A.ey) A.ey[o] = ey;
@@ -172,27 +232,30 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         if (A.theta) A.theta[o] = atan2(h.ys, h.xs);                    // :133
         if (A.wx) A.wx[o] = SD(SM(ex, A.wg_nu), A.wg_lambda);           // :166
         if (A.wy) A.wy[o] = SD(SM(ey, A.wg_nu), A.wg_lambda);
+        if (EXT && A.opd) A.opd[o] = opd;
         if (A.mask) A.mask[o] = (uint8_t)kept;
         if (A.flags) A.flags[o] = (uint8_t)flags;
         acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
         acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0) + (flags & ORT_FLAG_CLIP ? 0x10000 : 0);
+        if (EXT) acc.nvig += vig ? 1 : 0;
     }
     if (kept) {
         const double dx = ex - cx, dy = ey - cy;
         acc.s1x += dx; acc.s2x = fma(dx, dx, acc.s2x);
         acc.s1y += dy; acc.s2y = fma(dy, dy, acc.s2y);
         acc.rmax = fmax(acc.rmax, (ARITH == ORT_ARITH_STRICT) ? ri : r2);
+        if (EXT) { const double dd = opd - co; acc.s1o += dd; acc.s2o = fma(dd, dd, acc.s2o); }
         acc.n++;
     }
     return kept;
 }
 
-template <int ARITH, int RPT>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : ORT_BPS2) : 2)
+template <int ARITH, int RPT, bool EXT>
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? 2 : ORT_BPS2)) : 2)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
     __shared__ RawPart s_part[ORT_TILE / 32];
-    __shared__ double s_shift[2];
+    __shared__ double s_shift[3];
     const int f = blockIdx.y;
     const ort_field& fld = A.fields[f];
     const unsigned NN = A.NN;
@@ -200,24 +263,28 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     const unsigned ntiles = (nsub + RPT - 1) / RPT;
     const size_t fbase = (size_t)f * NN;
     const double* ysf = A.ys + (size_t)f * A.ys_stride;
+    const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
 
     RawAcc acc;
-    acc.n = acc.nflag_lo = acc.nflag_hi = 0;
-    acc.s1x = acc.s2x = acc.s1y = acc.s2y = 0.0; acc.rmax = -CUDART_INF;
+    acc.n = acc.nflag_lo = acc.nflag_hi = acc.nvig = 0;
+    acc.s1x = acc.s2x = acc.s1y = acc.s2y = acc.s1o = acc.s2o = 0.0; acc.rmax = -CUDART_INF;
 
     if (threadIdx.x == 0) {                      // common shift of this field: its centre ray
         const double y0 = __ldg(ysf + A.ny / 2), x0 = __ldg(A.xs);
         double u, v; field_slopes(fld, y0, x0, u, v);
         Hit h; int amb = 0;
-        if (ARITH == ORT_ARITH_FAST) trace_fast<1>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb);
-        if (ARITH == ORT_ARITH_STRICT || amb < 0) h = trace_strict_cold(P.s, P.nsurf, A.stop, y0, x0, u, v);
+        if (ARITH == ORT_ARITH_FAST) trace_fast<1, EXT>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
+        if (ARITH == ORT_ARITH_STRICT || amb < 0)
+            h = trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
         const double ey = h.yf - fld.h_prime;
         const bool bad = nonfinite_bit(h.xf) < 0 || nonfinite_bit(ey) < 0;
         s_shift[0] = bad ? 0.0 : h.xf;
         s_shift[1] = bad ? 0.0 : ey;
+        const double od = (h.opl - fld.opl_ref) * A.opd_scale;
+        s_shift[2] = (!EXT || bad || nonfinite_bit(od) < 0) ? 0.0 : od;
     }
     __syncthreads();
-    const double cx = s_shift[0], cy = s_shift[1];
+    const double cx = s_shift[0], cy = s_shift[1], co = s_shift[2];
 
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         double y0[RPT], x0[RPT], u[RPT], v[RPT];
@@ -234,12 +301,13 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         }
         Hit h[RPT];
         int amb[RPT];
-        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb);
+        if (ARITH == ORT_ARITH_FAST)
+            trace_fast<RPT, EXT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette);
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
-            const int kept = grid_epilogue<ARITH>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
-                                                  fbase + idx[j], cx, cy, acc);
+            const int kept = grid_epilogue<ARITH, EXT>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
+                                                       fbase + idx[j], cx, cy, co, acc);
             if (A.tile_counts) {
                 const int c = __syncthreads_count(kept);
                 const unsigned sub = tile * RPT + j;
@@ -249,7 +317,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     }
     RawPart p;
     p.n = acc.n; p.s1x = acc.s1x; p.s2x = acc.s2x; p.s1y = acc.s1y; p.s2y = acc.s2y; p.rmax = acc.rmax;
-    p.cx = cx; p.cy = cy;
+    p.cx = cx; p.cy = cy; p.co = co; p.s1o = acc.s1o; p.s2o = acc.s2o; p.nvig = acc.nvig; p.pad_ = 0;
     p.nmiss = acc.nflag_lo & 0xFFFF; p.ntir = acc.nflag_lo >> 16; p.ndom = acc.nflag_hi & 0xFFFF; p.nclip = acc.nflag_hi >> 16;
     raw_block_reduce<ORT_TILE / 32>(p, s_part);
     if (threadIdx.x == 0) {
@@ -265,22 +333,24 @@ __global__ void __launch_bounds__(256) k_grid_finalize(const RawPart* partials, 
     __shared__ RawPart s_part[8];
     const int f = blockIdx.x;
     RawPart p;
-    p.n = 0; p.s1x = p.s2x = p.s1y = p.s2y = 0.0; p.rmax = -CUDART_INF; p.cx = p.cy = 0.0;
-    p.nmiss = p.ntir = p.ndom = p.nclip = 0;
+    p.n = 0; p.s1x = p.s2x = p.s1y = p.s2y = p.s1o = p.s2o = 0.0; p.rmax = -CUDART_INF; p.cx = p.cy = p.co = 0.0;
+    p.nmiss = p.ntir = p.ndom = p.nclip = p.nvig = p.pad_ = 0;
     for (int j = threadIdx.x; j < nparts; j += 256) raw_add(p, partials[(size_t)f * nparts + j]);
     raw_block_reduce<8>(p, s_part);
     if (threadIdx.x == 0) {
-        const double cx = partials[(size_t)f * nparts].cx, cy = partials[(size_t)f * nparts].cy;
+        const RawPart& p0 = partials[(size_t)f * nparts];
         ort_stats s;
         s.n_kept = p.n;
         if (p.n > 0) {
             const double n = (double)p.n;
-            s.mean_x = cx + p.s1x / n; s.mean_y = cy + p.s1y / n;
+            s.mean_x = p0.cx + p.s1x / n; s.mean_y = p0.cy + p.s1y / n;
             s.m2_x = fmax(p.s2x - p.s1x * p.s1x / n, 0.0);
             s.m2_y = fmax(p.s2y - p.s1y * p.s1y / n, 0.0);
             s.r_max = p.rmax;
-        } else { s.mean_x = s.mean_y = s.m2_x = s.m2_y = 0.0; s.r_max = -CUDART_INF; }
-        s.n_miss = p.nmiss; s.n_tir = p.ntir; s.n_domain = p.ndom; s.n_clip = p.nclip;
+            s.mean_opd = p0.co + p.s1o / n;
+            s.m2_opd = fmax(p.s2o - p.s1o * p.s1o / n, 0.0);
+        } else { s.mean_x = s.mean_y = s.m2_x = s.m2_y = s.mean_opd = s.m2_opd = 0.0; s.r_max = -CUDART_INF; }
+        s.n_miss = p.nmiss; s.n_tir = p.ntir; s.n_domain = p.ndom; s.n_clip = p.nclip; s.n_vig = p.nvig;
         stats[f] = s;
     }
 }
@@ -306,7 +376,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(int* counts, unsigned ntiles
     for (unsigned j = lo; j < hi; j++) { unsigned v = (unsigned)c[j]; c[j] = (int)run; run += v; }
 }
 
-// order-preserving scatter of up to 6 arrays: one CTA per (tile, field)
+// order-preserving scatter of up to 7 arrays: one CTA per (tile, field)
 __global__ void __launch_bounds__(ORT_TILE) k_compact(CompactArgs C)
 {
     __shared__ int s_warp[ORT_TILE / 32];
@@ -324,7 +394,7 @@ __global__ void __launch_bounds__(ORT_TILE) k_compact(CompactArgs C)
     off += __popc(ball & ((1u << lane) - 1u));
     if (m) {
 #pragma unroll
-        for (int a = 0; a < 6; a++)
+        for (int a = 0; a < 7; a++)
             if (C.src[a]) C.dst[a][fbase + off] = C.src[a][fbase + i];
     }
 }
@@ -332,7 +402,7 @@ __global__ void __launch_bounds__(ORT_TILE) k_compact(CompactArgs C)
 // ------------------------------------------------------------------------------------------
 // arbitrary rays, all surfaces recorded
 // ------------------------------------------------------------------------------------------
-template <int ARITH>
+template <int ARITH, bool EXT>
 __global__ void __launch_bounds__(256)
 k_rays(const __grid_constant__ Presc P, RaysArgs A)
 {
@@ -340,12 +410,13 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
     if (i >= A.N) return;
     const double y0 = A.y0[i], x0 = A.x0[i], u0 = A.u0[i], v0 = A.v0[i];
     const int nsurf = P.nsurf;
+    const bool vignette = EXT && P.has_apertures;
     bool strict = (ARITH == ORT_ARITH_STRICT);
     if (!strict) {
         RaysF<1> r;
         fast_init(r, 0, P.n0, y0, x0, u0, v0);
         for (int s = 0; s < nsurf; s++) {
-            fast_step<1>(P.s[s], r);
+            fast_step<1, EXT>(P.s[s], r, vignette);
             if (A.xv) A.xv[(size_t)s * A.N + i] = r.x[0];
             if (A.yv) A.yv[(size_t)s * A.N + i] = r.y[0];
         }
@@ -356,19 +427,21 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
                 const double sg = (r.Kz[0] < 0.0) ? -inv : inv;
                 A.kout[i] = r.Kx[0] * sg; A.kout[A.N + i] = r.Ky[0] * sg; A.kout[2 * A.N + i] = r.Kz[0] * sg;
             }
-            if (A.flags) A.flags[i] = 0;
+            if (A.flags) A.flags[i] = (EXT && r.vig[0]) ? (uint8_t)ORT_FLAG_VIGN : (uint8_t)0;
+            if (EXT && A.opl) A.opl[i] = r.opl[0];
         } else strict = true;
     }
     if (strict) {
         RayS r;
         strict_init(r, y0, x0, u0, v0);
         for (int s = 0; s < nsurf; s++) {
-            strict_step(P.s[s], r);
+            strict_step<EXT>(P.s[s], r, vignette);
             if (A.xv) A.xv[(size_t)s * A.N + i] = r.x;
             if (A.yv) A.yv[(size_t)s * A.N + i] = r.y;
         }
         if (A.kout) { A.kout[i] = r.k1; A.kout[A.N + i] = r.k2; A.kout[2 * A.N + i] = r.k3; }
         if (A.flags) A.flags[i] = (uint8_t)r.flags;
+        if (EXT && A.opl) A.opl[i] = r.opl;
     }
 }
 
@@ -423,6 +496,7 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
     S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
     S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
+    S.a = CUDART_INF; S.a2 = CUDART_INF;
 }
 
 template <int ARITH>
@@ -447,14 +521,14 @@ k_candidates(CandArgs A)
         const double y0 = __ldg(A.ys + iy), x0 = __ldg(A.xs + ix);
         Hit h; int amb = 0; double ri = 0.0, r2 = 0.0; bool clip;
         if (ARITH == ORT_ARITH_FAST) {
-            { const double uu = A.u, vv = A.v; trace_fast<1>(s_surf, nsurf, A.stop, Rc[2 * rows], &y0, &x0, &uu, &vv, &h, &amb); }
+            { const double uu = A.u, vv = A.v; trace_fast<1, false>(s_surf, nsurf, A.stop, Rc[2 * rows], &y0, &x0, &uu, &vv, &h, &amb); }
             r2 = fma(h.xs, h.xs, h.ys * h.ys);
             amb |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);
             clip = r2 > A.a_stop2;
         }
         if (ARITH == ORT_ARITH_STRICT || amb < 0) {
-            h = (ARITH == ORT_ARITH_STRICT) ? trace_strict(s_surf, nsurf, A.stop, y0, x0, A.u, A.v)
-                                            : trace_strict_cold(s_surf, nsurf, A.stop, y0, x0, A.u, A.v);
+            h = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, A.stop, y0, x0, A.u, A.v)
+                                            : trace_strict_cold<false>(s_surf, nsurf, A.stop, y0, x0, A.u, A.v);
             ri = jl_hypot(h.xs, h.ys);
             clip = ri > A.a_stop;
             r2 = ri * ri;
@@ -477,20 +551,30 @@ k_candidates(CandArgs A)
 // ------------------------------------------------------------------------------------------
 int grid_rays_per_thread(int arith) { return arith == ORT_ARITH_FAST ? ORT_FAST_RPT : 1; }
 
-int grid_blocks_per_sm(int arith)
+int grid_blocks_per_sm(int arith, int ext)
 {
     int nb = 0;
-    cudaError_t e = (arith == ORT_ARITH_FAST)
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT>, ORT_TILE, 0)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1>, ORT_TILE, 0);
+    cudaError_t e;
+    if (arith == ORT_ARITH_FAST)
+        e = ext ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true>, ORT_TILE, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false>, ORT_TILE, 0);
+    else
+        e = ext ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, true>, ORT_TILE, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, false>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st)
 {
-    if (arith == ORT_ARITH_FAST) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT><<<grid, ORT_TILE, 0, st>>>(P, A);
-    else k_grid<ORT_ARITH_STRICT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+    const bool ext = A.ext != 0;
+    if (arith == ORT_ARITH_FAST) {
+        if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+    } else {
+        if (ext) k_grid<ORT_ARITH_STRICT, 1, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else k_grid<ORT_ARITH_STRICT, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+    }
     return cudaGetLastError();
 }
 
@@ -515,8 +599,14 @@ cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream
 {
     const unsigned nb = (unsigned)((A.N + 255) / 256);
     if (nb == 0) return cudaSuccess;
-    if (arith == ORT_ARITH_FAST) k_rays<ORT_ARITH_FAST><<<nb, 256, 0, st>>>(P, A);
-    else k_rays<ORT_ARITH_STRICT><<<nb, 256, 0, st>>>(P, A);
+    const bool ext = A.opl != nullptr || P.has_apertures;
+    if (arith == ORT_ARITH_FAST) {
+        if (ext) k_rays<ORT_ARITH_FAST, true><<<nb, 256, 0, st>>>(P, A);
+        else k_rays<ORT_ARITH_FAST, false><<<nb, 256, 0, st>>>(P, A);
+    } else {
+        if (ext) k_rays<ORT_ARITH_STRICT, true><<<nb, 256, 0, st>>>(P, A);
+        else k_rays<ORT_ARITH_STRICT, false><<<nb, 256, 0, st>>>(P, A);
+    }
     return cudaGetLastError();
 }
 

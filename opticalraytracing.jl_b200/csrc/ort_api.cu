@@ -14,8 +14,8 @@ namespace {
 
 enum Slot {
     SL_YS, SL_XS, SL_PARTIALS, SL_TILES, SL_STATS,
-    SL_EX, SL_EY, SL_R, SL_TH, SL_WX, SL_WY, SL_MASK, SL_FLAGS,     // trace outputs (full grid)
-    SL_CEX, SL_CEY, SL_CR, SL_CTH, SL_CWX, SL_CWY,                  // compacted outputs
+    SL_EX, SL_EY, SL_R, SL_TH, SL_WX, SL_WY, SL_OPD, SL_MASK, SL_FLAGS,     // trace outputs (full grid)
+    SL_CEX, SL_CEY, SL_CR, SL_CTH, SL_CWX, SL_CWY, SL_COPD,                 // compacted outputs
     SL_IN0, SL_IN1, SL_IN2, SL_IN3, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3, SL_OUT4, SL_SINK,
     SL_COUNT
 };
@@ -35,7 +35,7 @@ struct ort_ctx {
     Presc presc;
     int rows;
     bool have_layout;
-    int bps[2];                 // resident CTAs/SM of k_grid<STRICT>, <FAST>
+    int bps[2][2];              // resident CTAs/SM of k_grid<STRICT|FAST, EXT off|on>
     void* slot[SL_COUNT];
     size_t slot_bytes[SL_COUNT];
     long long launches;
@@ -100,6 +100,7 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     memcpy(&bits, &thr1, 8);
     S.gr_thr = (int32_t)(bits >> 32);
     S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
+    S.a = INFINITY; S.a2 = INFINITY;
 }
 
 // bracket the dominant kernel with an event pair (measurement only)
@@ -163,8 +164,10 @@ int ort_init(ort_ctx** out, int device)
     for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) { CKI(cudaEventCreate(&ctx->prof_ev[i][0])); CKI(cudaEventCreate(&ctx->prof_ev[i][1])); }
 #undef CKI
-    ctx->bps[ORT_ARITH_STRICT] = grid_blocks_per_sm(ORT_ARITH_STRICT);
-    ctx->bps[ORT_ARITH_FAST] = grid_blocks_per_sm(ORT_ARITH_FAST);
+    for (int e = 0; e < 2; e++) {
+        ctx->bps[ORT_ARITH_STRICT][e] = grid_blocks_per_sm(ORT_ARITH_STRICT, e);
+        ctx->bps[ORT_ARITH_FAST][e] = grid_blocks_per_sm(ORT_ARITH_FAST, e);
+    }
     *out = ctx;
     return ORT_OK;
 }
@@ -262,6 +265,21 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
     return ORT_OK;
 }
 
+int ort_set_apertures(ort_ctx* ctx, int n, const double* a)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "ort_set_apertures: call ort_set_layout first");
+    Presc& P = ctx->presc;
+    if (a && (n < 0 || n > P.nsurf)) return fail(ctx, ORT_EINVAL, "ort_set_apertures: n = %d not in [0, %d]", n, P.nsurf);
+    P.has_apertures = 0;
+    for (int i = 0; i < P.nsurf; i++) {
+        const double ai = (a && i < n && !isnan(a[i])) ? fabs(a[i]) : INFINITY;
+        P.s[i].a = ai; P.s[i].a2 = ai * ai;
+        if (isfinite(ai)) P.has_apertures = 1;
+    }
+    return ORT_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // pupil-grid sweep
 // ------------------------------------------------------------------------------------------
@@ -296,6 +314,8 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
     A.ys_stride = opts->ys_per_field ? ny : 0;
     A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
     A.wg_nu = opts->wg_nu; A.wg_lambda = opts->wg_lambda;
+    A.ext = opts->ext & (ORT_EXT_OPD | ORT_EXT_VIGNETTE);
+    A.opd_scale = opts->opd_scale; A.opd = (A.ext & ORT_EXT_OPD) ? full.opd : nullptr;
     A.ex = full.ex; A.ey = full.ey; A.r = full.r; A.theta = full.theta; A.wx = full.wx; A.wy = full.wy;
     A.mask = full.mask; A.flags = full.flags;
     A.partials = d_partials;
@@ -315,21 +335,21 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
         CompactArgs C;
         memset(&C, 0, sizeof C);
         C.NN = NN; C.mask = full.mask; C.tile_offsets = d_tiles;
-        const double* src[6] = {full.ex, full.ey, full.r, full.theta, full.wx, full.wy};
-        double* dd[6] = {dst->ex, dst->ey, dst->r, dst->theta, dst->wx, dst->wy};
-        for (int a = 0; a < 6; a++) { C.src[a] = dd[a] ? src[a] : nullptr; C.dst[a] = dd[a]; }
+        const double* src[7] = {full.ex, full.ey, full.r, full.theta, full.wx, full.wy, A.opd};
+        double* dd[7] = {dst->ex, dst->ey, dst->r, dst->theta, dst->wx, dst->wy, A.opd ? dst->opd : nullptr};
+        for (int a = 0; a < 7; a++) { C.src[a] = dd[a] ? src[a] : nullptr; C.dst[a] = dd[a]; }
         CK(launch_compact(d_tiles, C, n_fields, st));
         ctx->launches += 2;
     }
     return ORT_OK;
 }
 
-static int grid_dims(const ort_ctx* ctx, int arith, int n_fields, unsigned NN)
+static int grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsigned NN)
 {
     const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;
     const unsigned rpt = (unsigned)grid_rays_per_thread(arith);
     const unsigned ntiles = (nsub + rpt - 1) / rpt;
-    long long gx = (long long)ctx->sm_count * ctx->bps[arith] / n_fields;
+    long long gx = (long long)ctx->sm_count * ctx->bps[arith][ext ? 1 : 0] / n_fields;
     if (gx < 1) gx = 1;
     if (gx > (long long)ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
@@ -346,7 +366,7 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned NN = (unsigned)((long long)ny * nx);
     const int arith = resolve_arith(ctx, opts->arith);
-    const int gx = grid_dims(ctx, arith, n_fields, NN);
+    const int gx = grid_dims(ctx, arith, opts->ext & 3, n_fields, NN);
     RawPart* d_partials; ENSURE(SL_PARTIALS, sizeof(RawPart) * (size_t)gx * n_fields, d_partials);
     ort_stats* d_stats = d_out->stats;
     if (!d_stats) ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
@@ -362,6 +382,7 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     if (d_out->theta) ENSURE(SL_TH, tot * 8, full.theta);
     if (d_out->wx) ENSURE(SL_WX, tot * 8, full.wx);
     if (d_out->wy) ENSURE(SL_WY, tot * 8, full.wy);
+    if (d_out->opd) ENSURE(SL_OPD, tot * 8, full.opd);
     if (!d_out->mask) ENSURE(SL_MASK, tot, full.mask);
     int* d_tiles; ENSURE(SL_TILES, sizeof(int) * (size_t)((NN + ORT_TILE - 1) / ORT_TILE + 1) * n_fields, d_tiles);
     return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full, d_out, d_stats,
@@ -379,7 +400,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     const size_t tot = (size_t)NN * n_fields;
     const int arith = resolve_arith(ctx, opts->arith);
     // one launch per field so the D2H of field f overlaps the trace of field f+1
-    const int gx = grid_dims(ctx, arith, 1, NN);
+    const int gx = grid_dims(ctx, arith, opts->ext & 3, 1, NN);
     double *d_ys, *d_xs;
     const size_t nys = (size_t)ny * (opts->ys_per_field ? n_fields : 1);
     ENSURE(SL_YS, sizeof(double) * nys, d_ys);
@@ -396,6 +417,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     if (out->theta) ENSURE(SL_TH, tot * 8, full.theta);
     if (out->wx) ENSURE(SL_WX, tot * 8, full.wx);
     if (out->wy) ENSURE(SL_WY, tot * 8, full.wy);
+    if (out->opd) ENSURE(SL_OPD, tot * 8, full.opd);
     if (out->mask || opts->compact) ENSURE(SL_MASK, tot, full.mask);
     if (out->flags) ENSURE(SL_FLAGS, tot, full.flags);
     if (opts->compact) {
@@ -406,6 +428,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         if (out->theta) ENSURE(SL_CTH, tot * 8, comp.theta);
         if (out->wx) ENSURE(SL_CWX, tot * 8, comp.wx);
         if (out->wy) ENSURE(SL_CWY, tot * 8, comp.wy);
+        if (out->opd) ENSURE(SL_COPD, tot * 8, comp.opd);
     }
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * nys, cudaMemcpyHostToDevice, st));
@@ -415,8 +438,8 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         const size_t o = (size_t)f * NN;
         ort_grid_out ff = full, cc = comp;
 #define OFF(p) if (p) p += o
-        OFF(ff.ex); OFF(ff.ey); OFF(ff.r); OFF(ff.theta); OFF(ff.wx); OFF(ff.wy); OFF(ff.mask); OFF(ff.flags);
-        OFF(cc.ex); OFF(cc.ey); OFF(cc.r); OFF(cc.theta); OFF(cc.wx); OFF(cc.wy);
+        OFF(ff.ex); OFF(ff.ey); OFF(ff.r); OFF(ff.theta); OFF(ff.wx); OFF(ff.wy); OFF(ff.opd); OFF(ff.mask); OFF(ff.flags);
+        OFF(cc.ex); OFF(cc.ey); OFF(cc.r); OFF(cc.theta); OFF(cc.wx); OFF(cc.wy); OFF(cc.opd);
 #undef OFF
         rc = grid_enqueue(ctx, fields + f, 1, d_ys + (opts->ys_per_field ? (size_t)f * ny : 0), ny, d_xs, nx, stop, a_stop, opts, ff,
                           opts->compact ? &cc : nullptr, d_stats + f, d_partials + (size_t)f * gx,
@@ -439,6 +462,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         if (out->theta) CK(cudaMemcpyAsync(out->theta + o, src.theta, cnt * 8, cudaMemcpyDeviceToHost, cs));
         if (out->wx) CK(cudaMemcpyAsync(out->wx + o, src.wx, cnt * 8, cudaMemcpyDeviceToHost, cs));
         if (out->wy) CK(cudaMemcpyAsync(out->wy + o, src.wy, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        if (out->opd && (opts->ext & ORT_EXT_OPD)) CK(cudaMemcpyAsync(out->opd + o, src.opd, cnt * 8, cudaMemcpyDeviceToHost, cs));
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(cs));
@@ -449,8 +473,9 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
 // ------------------------------------------------------------------------------------------
 // arbitrary rays / 2-D / paraxial / transfer / candidates: host wrappers stage through scratch
 // ------------------------------------------------------------------------------------------
-int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0, const double* u0,
-                     const double* v0, int arith, double* xv, double* yv, double* kout, uint8_t* flags)
+int ort_trace3d_rays_opl(ort_ctx* ctx, int64_t N, const double* y0, const double* x0, const double* u0,
+                         const double* v0, int arith, double* xv, double* yv, double* kout, uint8_t* flags,
+                         double* opl)
 {
     if (!ctx) return ORT_EINVAL;
     if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "trace3d_rays: call ort_set_layout first");
@@ -467,6 +492,7 @@ int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0
     if (yv) ENSURE(SL_OUT1, ns * n * 8, A.yv);
     if (kout) ENSURE(SL_OUT2, 3 * n * 8, A.kout);
     if (flags) ENSURE(SL_OUT3, n, A.flags);
+    if (opl) ENSURE(SL_OUT4, n * 8, A.opl);
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d1, x0, n * 8, cudaMemcpyHostToDevice, st));
@@ -479,8 +505,15 @@ int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0
     if (yv) CK(cudaMemcpyAsync(yv, A.yv, ns * n * 8, cudaMemcpyDeviceToHost, st));
     if (kout) CK(cudaMemcpyAsync(kout, A.kout, 3 * n * 8, cudaMemcpyDeviceToHost, st));
     if (flags) CK(cudaMemcpyAsync(flags, A.flags, n, cudaMemcpyDeviceToHost, st));
+    if (opl) CK(cudaMemcpyAsync(opl, A.opl, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORT_OK;
+}
+
+int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0, const double* u0,
+                     const double* v0, int arith, double* xv, double* yv, double* kout, uint8_t* flags)
+{
+    return ort_trace3d_rays_opl(ctx, N, y0, x0, u0, v0, arith, xv, yv, kout, flags, nullptr);
 }
 
 int ort_trace2d_batch(ort_ctx* ctx, int64_t N, const double* y0, const double* U0, int aspheric,

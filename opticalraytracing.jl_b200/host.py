@@ -442,32 +442,41 @@ def trace_chief_ray(surfaces, system, atol=EPS, backend=None):
     return RealRayData(yb, ub, np.column_stack([yb, ub]), L.n.copy(), z)
 
 
-def trace_edge_rays(surfaces, y1, y2, U, stop, a_stop, backend=None):
-    """src/PupilSampling.jl:67-83.  The reference minimises |y_stop -/+ a_stop| with Optim.BFGS; the
-    same two roots are found here by a secant iteration (2-ray batches).  U may be an array of
-    field angles: all fields are aimed together."""
+def aim_rays(surfaces, y_start, U, target, stop, scale, backend=None):
+    """Entrance heights y (array) such that the meridional ray (y, U) crosses surface `stop` at height
+    `target`: secant iteration, every step is one batch of the 2-D kernel over all rays being aimed."""
     layout = _as_layout(surfaces)
-    U = np.atleast_1d(np.asarray(U, dtype=np.float64))
-    nf = len(U)
-    y = np.concatenate([np.broadcast_to(y1, nf), np.broadcast_to(y2, nf)]).astype(np.float64)
-    tgt = np.concatenate([np.full(nf, a_stop), np.full(nf, -a_stop)])
-    UU = np.concatenate([U, U])
+    y = np.array(y_start, dtype=np.float64)
+    UU = np.broadcast_to(np.asarray(U, dtype=np.float64), y.shape).copy()
+    tgt = np.broadcast_to(np.asarray(target, dtype=np.float64), y.shape)
+    m = len(y)
     fx_prev = None
     for _ in range(60):
         h = EPS * np.maximum(1.0, np.abs(y))
         yo, _, _, _ = _trace2d(layout, np.concatenate([y, y + h]), np.concatenate([UU, UU]), layout.aspheric, backend)
-        fx = yo[stop, :2 * nf] - tgt
-        fh = yo[stop, 2 * nf:] - tgt
+        fx = yo[stop, :m] - tgt
+        fh = yo[stop, m:] - tgt
         if not np.all(np.isfinite(fx)):
-            raise RuntimeError("trace_edge_rays left the domain")
-        done = np.abs(fx) <= 4e-16 * a_stop
+            raise RuntimeError("ray aiming left the domain")
+        done = np.abs(fx) <= 4e-16 * scale
         if fx_prev is not None:
-            done |= (np.abs(fx) >= np.abs(fx_prev)) & (np.abs(fx_prev) <= 1e-13 * a_stop)
+            done |= (np.abs(fx) >= np.abs(fx_prev)) & (np.abs(fx_prev) <= 1e-13 * scale)
         if np.all(done):
             break
-        step = fx * h / (fh - fx)
-        y = np.where(done, y, y - step)
+        y = np.where(done, y, y - fx * h / (fh - fx))
         fx_prev = fx
+    return y
+
+
+def trace_edge_rays(surfaces, y1, y2, U, stop, a_stop, backend=None):
+    """src/PupilSampling.jl:67-83.  The reference minimises |y_stop -/+ a_stop| with Optim.BFGS; the
+    same two roots are found here by a secant iteration (2-ray batches).  U may be an array of
+    field angles: all fields are aimed together."""
+    U = np.atleast_1d(np.asarray(U, dtype=np.float64))
+    nf = len(U)
+    y0 = np.concatenate([np.broadcast_to(y1, nf), np.broadcast_to(y2, nf)]).astype(np.float64)
+    tgt = np.concatenate([np.full(nf, a_stop), np.full(nf, -a_stop)])
+    y = aim_rays(surfaces, y0, np.concatenate([U, U]), tgt, stop, a_stop, backend=backend)
     return y[:nf], y[nf:]
 
 
@@ -582,24 +591,86 @@ def merge_stats(records):
     out = np.zeros(1, dtype=_lib.STATS_DTYPE)[0]
     out["r_max"] = -np.inf
     for rec in records:
-        for k in ("n_miss", "n_tir", "n_domain", "n_clip"):
+        for k in ("n_miss", "n_tir", "n_domain", "n_clip", "n_vig"):
             out[k] += rec[k]
         nb = float(rec["n_kept"])
         if nb == 0:
             continue
         na = float(out["n_kept"])
         if na == 0:
-            for k in ("n_kept", "mean_x", "mean_y", "m2_x", "m2_y", "r_max"):
+            for k in ("n_kept", "mean_x", "mean_y", "m2_x", "m2_y", "r_max", "mean_opd", "m2_opd"):
                 out[k] = rec[k]
             continue
         n = na + nb
         w = nb / n
-        for mk, vk in (("mean_x", "m2_x"), ("mean_y", "m2_y")):
+        for mk, vk in (("mean_x", "m2_x"), ("mean_y", "m2_y"), ("mean_opd", "m2_opd")):
             d = float(rec[mk]) - float(out[mk])
             out[mk] = float(out[mk]) + d * w
             out[vk] = float(out[vk]) + float(rec[vk]) + d * d * (na * w)
         out["n_kept"] += rec["n_kept"]
         out["r_max"] = max(float(out["r_max"]), float(rec["r_max"]))
+    return out
+
+
+@dataclass
+class Wavefront:
+    """EXTENSION (no reference counterpart): ray-traced optical path difference over the
+    pupil grid of full_trace, referred to the chief ray on a reference sphere centred at the chief ray's image
+    point with its centre of curvature distance = image plane - paraxial exit pupil."""
+    opd: np.ndarray          # waves, kept rays in push! order, mirrored like RealRayError ([opd; opd])
+    x: np.ndarray            # transverse errors of the same rays (mirrored)
+    y: np.ndarray
+    H: float
+    rms: float               # RMS OPD about its mean, waves
+    mean: float
+    pv: float
+    stats: np.ndarray = field(default=None, repr=False)
+
+
+def wavefront(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, lam=LAMBDA, vignette=False, backend=None,
+              arith=_lib.FAST):
+    """OPD map per field point (list of Wavefront).  W = (OPL_chief - OPL_ray) / lam -- the sign convention of
+    the reference's Seidel wavefront W(rho, theta, H) (src/SeidelAberrations.jl:61-76), so that the rho^4 term
+    of the on-axis map reproduces its W040 -- with the OPL accumulated surface by surface inside the grid
+    kernel and closed on the reference sphere."""
+    be = _be(backend)
+    layout = _as_layout(surfaces)
+    p = _full_trace_setup(layout, system, Hs, k_rays, focus, backend)
+    if p["z0"] is not None:
+        raise NotImplementedError("wavefront: RayBasis (finite object) reference wavefront not implemented")
+    ext = p["ext"].copy()
+    ext[-1, 2] = layout.n[-1]                     # the image plane sits in the last medium (no fake refraction)
+    nf = len(p["Hs"])
+    # chief ray of every field: through the centre of the stop (aiming uses the 2-D kernel on the bare layout)
+    y_c = aim_rays(layout, -p["u"] * p["EP_t"], p["U"], np.zeros(nf), p["stop"], p["a_stop"], backend=backend)
+    be.set_layout(ext, p["K"])
+    be.set_apertures(system.a if vignette else None)
+    xv, yv, k, fl, opl = be.trace3d_rays(y_c, np.zeros(nf), p["u"], np.zeros(nf), arith=_lib.STRICT, opl=True)
+    n0, nl = layout.n[0], layout.n[-1]
+    knorm = 1.0 / np.sqrt(p["u"] ** 2 + 1.0)                 # k = normalize([0, u, 1])
+    opl0 = n0 * (y_c * (p["u"] * knorm))                     # start term of the chief ray
+    Rr = p["focus"] - system.XP.t                            # image plane - paraxial exit pupil
+    yc = yv[-1]
+    opl_ref = opl + opl0 + nl * (-Rr)
+    xs = np.linspace(0.0, p["y_EP"], k_rays // 2)
+    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], k_rays) for j in range(nf)])
+    flds = [dict(mode=0, u=float(p["u"][j]), v=0.0, h_prime=float(p["h_prime"][j]), opd_xc=0.0, opd_yc=float(yc[j]),
+                 opd_radius=float(Rr), opl_ref=float(opl_ref[j])) for j in range(nf)]
+    out = []
+    for j0 in range(0, nf, _lib.MAX_FIELDS):
+        sl = slice(j0, j0 + _lib.MAX_FIELDS)
+        r = be.trace3d_grid(flds[sl], ys[sl], xs, p["stop"], p["a_stop"], arith=arith, compact=True,
+                            want=("ex", "ey", "opd", "mask", "stats"), ext=_lib.EXT_OPD | (_lib.EXT_VIGNETTE if vignette else 0),
+                            opd_scale=-1.0 / lam)
+        for j, H in enumerate(p["Hs"][sl]):
+            st = r["stats"][j]
+            n = int(st["n_kept"])
+            o = r["opd"][j][:n]
+            ex, ey = r["ex"][j][:n], r["ey"][j][:n]
+            out.append(Wavefront(np.concatenate([o, o]), np.concatenate([ex, -ex]), np.concatenate([ey, ey]), float(H),
+                                 math.sqrt(st["m2_opd"] / n) if n else float("nan"), float(st["mean_opd"]),
+                                 float(o.max() - o.min()) if n else float("nan"), stats=r["stats"][j:j + 1].copy()))
+    be.set_apertures(None)
     return out
 
 

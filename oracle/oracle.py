@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libort_oracle.so")
 
-F_MISS, F_TIR, F_DOMAIN, F_CLIP = 1, 2, 4, 8
+F_MISS, F_TIR, F_DOMAIN, F_CLIP, F_VIGN = 1, 2, 4, 8, 16
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
@@ -47,6 +47,9 @@ def lib():
         L.orc_sigma.restype = C.c_double
         L.orc_mirror_stats.restype = C.c_double
         L.orc_max_threads.restype = C.c_int
+        L.orc_trace3d_ext.restype = C.c_uint
+        L.orc_opl_start.restype = C.c_double
+        L.orc_grid_trace_ext.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -235,6 +238,50 @@ def grid_trace(ext_surfaces, ys, xs, stop, a_stop, h_prime, u=0.0, v=0.0, mode=0
         C.c_double(ybar), C.c_double(z0), C.c_double(h_prime), C.c_int(ny), _p(ys), C.c_int(nx),
         _p(xs), C.c_int(stop), C.c_double(a_stop), _p(out["ex"]), _p(out["ey"]), _p(out["r"]),
         _p(out["theta"]), _pu8(out["mask"]), _pu8(out["flags"]), C.c_int(threads))
+    out["n_kept"] = int(kept)
+    return out
+
+
+def opl_start(mode, n0, y, x, u, v, z0=1.0):
+    return lib().orc_opl_start(C.c_int(mode), C.c_double(n0), C.c_double(y), C.c_double(x), C.c_double(u),
+                               C.c_double(v), C.c_double(z0))
+
+
+def trace3d_ext(surfaces, y, x, u, v, K=None, a=None, opl0=0.0, xc=0.0, yc=0.0, rr=0.0, truth=False):
+    """EXTENSION (no reference counterpart): 3-D trace with OPL accumulation, per-surface apertures and an
+    optional reference sphere.  -> (xv, yv, k, opl, flags); truth=True -> 80-bit OPL only."""
+    R, t, n, Kc = _cols(surfaces, K)
+    rows = len(R)
+    a_ = None if a is None else _d(a)
+    opl = C.c_double()
+    if truth:
+        lib().orc_trace3d_ext_ld(C.c_int(rows), _p(R), _p(t), _p(n), _p(Kc), C.c_double(y), C.c_double(x),
+                                 C.c_double(u), C.c_double(v), C.c_double(opl0), C.c_double(xc), C.c_double(yc),
+                                 C.c_double(rr), C.byref(opl))
+        return opl.value
+    xv, yv, k = np.empty(rows - 1), np.empty(rows - 1), np.empty(3)
+    f = lib().orc_trace3d_ext(C.c_int(rows), _p(R), _p(t), _p(n), _p(Kc), _p(a_), C.c_double(y), C.c_double(x),
+                              C.c_double(u), C.c_double(v), C.c_double(opl0), C.c_double(xc), C.c_double(yc),
+                              C.c_double(rr), _p(xv), _p(yv), _p(k), C.byref(opl))
+    return xv, yv, k, opl.value, int(f)
+
+
+def grid_trace_ext(ext_surfaces, ys, xs, stop, a_stop, h_prime, u=0.0, v=0.0, mode=0, ybar=0.0, z0=1.0, K=None,
+                   a=None, xc=0.0, yc=0.0, rr=0.0, opl_ref=0.0, opd_scale=1.0, threads=0):
+    """EXTENSION: grid sweep with OPD output and per-surface aperture clipping."""
+    R, t, n, Kc = _cols(ext_surfaces, K)
+    rows = len(R)
+    ys, xs = _d(ys), _d(xs)
+    a_ = None if a is None else _d(a)
+    NN = len(ys) * len(xs)
+    out = {"ex": np.empty(NN), "ey": np.empty(NN), "opd": np.empty(NN), "mask": np.zeros(NN, dtype=np.uint8),
+           "flags": np.zeros(NN, dtype=np.uint8)}
+    kept = lib().orc_grid_trace_ext(
+        C.c_int(rows), _p(R), _p(t), _p(n), _p(Kc), _p(a_), C.c_int(mode), C.c_double(u), C.c_double(v),
+        C.c_double(ybar), C.c_double(z0), C.c_double(h_prime), C.c_double(xc), C.c_double(yc), C.c_double(rr),
+        C.c_double(opl_ref), C.c_double(opd_scale), C.c_int(len(ys)), _p(ys), C.c_int(len(xs)), _p(xs),
+        C.c_int(stop), C.c_double(a_stop), _p(out["ex"]), _p(out["ey"]), _p(out["opd"]), _pu8(out["mask"]),
+        _pu8(out["flags"]), C.c_int(threads))
     out["n_kept"] = int(kept)
     return out
 

@@ -547,6 +547,185 @@ ORC_API int64_t orc_grid_trace(int rows, const double *R, const double *t, const
     return kept;
 }
 
+
+/* ------------------------------------------------------------------------------------
+ * EXTENSION (no reference counterpart -- SURVEY.md section 8 rows f3/f4, "parity unpinned"):
+ * the same 3-D trace (src/PupilSampling.jl:34-65, identical operations for x, y, k) that also
+ *   - accumulates the optical path length  OPL = sum_i n[i] * dz_i / k3_i, where dz_i = ts[i] is
+ *     the sag-corrected z-advance of leg i (:54-55) and k3 the z direction cosine on that leg;
+ *   - tests every surface's clear aperture: hypot(x, y) > a[i] sets F_VIGN (the reference's real-ray
+ *     tracer only tests the stop radius, :131-132; its paraxial tracer clips at every surface, :135).
+ * opl0 is the start term (distance from the reference wavefront / object point to the start point).
+ * If rr != 0 the OPL is closed on a reference sphere of radius rr centred at (xc, yc) on the last
+ * plane: tau = -b - sign(rr) sqrt(b^2 - (|q|^2 - rr^2)), q = P - C, b = q.k;  OPL += n_last * tau.
+ * Returns flags; *opl_out = OPL (NaN if the ray is NaN).
+ * ---------------------------------------------------------------------------------- */
+#define F_VIGN 16u
+ORC_API unsigned orc_trace3d_ext(int rows, const double *R, const double *t, const double *n,
+                                 const double *K, const double *a, double y, double x, double u, double v,
+                                 double opl0, double xc, double yc, double rr,
+                                 double *xv, double *yv, double *kout, double *opl_out)
+{
+    unsigned flags = 0;
+    double k1 = v, k2 = u, k3 = 1.0;
+    {
+        double nrm = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+        double inv = 1.0 / nrm;
+        k1 *= inv; k2 *= inv; k3 *= inv;
+    }
+    double opl = opl0;
+    double s_prev = 0.0; int have_prev = 0;
+    for (int i = 0; i + 1 < rows; i++) {
+        double ti = have_prev ? t[i] - s_prev : t[i];
+        y += u * ti;
+        x += v * ti;
+        double Rs = R[i + 1], Ks = K ? K[i + 1] : 0.0;
+        double s = sag3d(y, x, u, v, Rs, Ks, &flags);
+        y += s * u;
+        x += s * v;
+        s_prev = s; have_prev = 1;
+        opl += n[i] * (ti + s) / k3;                             /* extension: OPL of leg i */
+        if (a && orc_hypot(x, y) > a[i]) flags |= F_VIGN;        /* extension: clear aperture of surface i+1 */
+        double D = Rs * Rs - (x * x + y * y) * (1.0 + Ks);
+        if (D < 0.0) flags |= F_DOMAIN;
+        double sq = sqrt(D);
+        double m1 = jl_sign(Rs) * x / sq + 0.0;
+        double m2 = jl_sign(Rs) * y / sq + 0.0;
+        double m3 = -1.0;
+        {
+            double nrm = sqrt(m1 * m1 + m2 * m2 + m3 * m3);
+            double inv = 1.0 / nrm;
+            m1 *= inv; m2 *= inv; m3 *= inv;
+        }
+        double eta = n[i] / n[i + 1];
+        double dot = 0.0 + k1 * m1; dot += k2 * m2; dot += k3 * m3;
+        double gam = -dot;
+        double Dr = 1.0 - eta * eta * (1.0 - gam * gam);
+        if (Dr >= 0.0) {
+            double c = eta * gam - sqrt(Dr);
+            k1 = eta * k1 + c * m1;
+            k2 = eta * k2 + c * m2;
+            k3 = eta * k3 + c * m3;
+        } else if (Dr < 0.0) flags |= F_TIR;
+        u = k2 / k3;
+        v = k1 / k3;
+        if (xv) xv[i] = x;
+        if (yv) yv[i] = y;
+    }
+    if (rr != 0.0) {                                             /* close on the reference sphere */
+        double qx = x - xc, qy = y - yc;
+        double b = qx * k1 + qy * k2;
+        double cq = qx * qx + qy * qy - rr * rr;
+        double tau = -b - jl_sign(rr) * sqrt(b * b - cq);
+        opl += n[rows - 1] * tau;
+    }
+    if (kout) { kout[0] = k1; kout[1] = k2; kout[2] = k3; }
+    if (opl_out) *opl_out = opl;
+    return flags;
+}
+
+/* 80-bit evaluation of the same extension: "truth" for the OPL/OPD tolerance checks */
+ORC_API void orc_trace3d_ext_ld(int rows, const double *R, const double *t, const double *n,
+                                const double *K, double y0, double x0, double u0, double v0,
+                                double opl0, double xc, double yc, double rr, double *opl_out)
+{
+    long double y = y0, x = x0, u = u0, v = v0, k1 = v, k2 = u, k3 = 1.0L, opl = opl0, s_prev = 0.0L;
+    { long double inv = 1.0L / sqrtl(k1 * k1 + k2 * k2 + k3 * k3); k1 *= inv; k2 *= inv; k3 *= inv; }
+    for (int i = 0; i + 1 < rows; i++) {
+        long double ti = (long double)t[i] - s_prev;
+        y += u * ti; x += v * ti;
+        long double Rs = R[i + 1], Ks = K ? K[i + 1] : 0.0, s;
+        if (isfinite(R[i + 1])) {
+            long double beta = Rs - y * u - x * v, r2 = x * x + y * y;
+            long double D = beta * beta - r2 * (1.0L + Ks + u * u + v * v);
+            s = (D >= 0.0L) ? r2 / (beta + (long double)jl_sign(R[i + 1]) * sqrtl(D)) : (long double)NAN;
+        } else s = 0.0L;
+        y += s * u; x += s * v; s_prev = s;
+        opl += (long double)n[i] * (ti + s) / k3;
+        long double m1, m2, m3 = -1.0L;
+        if (isfinite(R[i + 1])) {
+            long double sq = sqrtl(Rs * Rs - (x * x + y * y) * (1.0L + Ks));
+            m1 = (long double)jl_sign(R[i + 1]) * x / sq; m2 = (long double)jl_sign(R[i + 1]) * y / sq;
+        } else { m1 = (x != x) ? x : 0.0L; m2 = (y != y) ? y : 0.0L; }
+        { long double inv = 1.0L / sqrtl(m1 * m1 + m2 * m2 + m3 * m3); m1 *= inv; m2 *= inv; m3 *= inv; }
+        long double eta = (long double)n[i] / (long double)n[i + 1];
+        long double gam = -(k1 * m1 + k2 * m2 + k3 * m3);
+        long double Dr = 1.0L - eta * eta * (1.0L - gam * gam);
+        if (Dr >= 0.0L) {
+            long double c = eta * gam - sqrtl(Dr);
+            k1 = eta * k1 + c * m1; k2 = eta * k2 + c * m2; k3 = eta * k3 + c * m3;
+        }
+        u = k2 / k3; v = k1 / k3;
+    }
+    if (rr != 0.0) {
+        long double qx = x - xc, qy = y - yc, b = qx * k1 + qy * k2, cq = qx * qx + qy * qy - (long double)rr * rr;
+        opl += (long double)n[rows - 1] * (-b - (long double)jl_sign(rr) * sqrtl(b * b - cq));
+    }
+    *opl_out = (double)opl;
+}
+
+/* start term of the OPL: mode 0 (collimated): n0 (x k1 + y k2) -- the distance by which the start
+ * point (x, y, 0) is ahead of the plane wavefront through the origin; mode 1 (object point at z0):
+ * n0 (-z0) / k3.  k = normalize([v, u, 1]) exactly as :40-41. */
+ORC_API double orc_opl_start(int mode, double n0, double y, double x, double u, double v, double z0)
+{
+    double k1 = v, k2 = u, k3 = 1.0;
+    double nrm = sqrt(k1 * k1 + k2 * k2 + k3 * k3);
+    double inv = 1.0 / nrm;
+    k1 *= inv; k2 *= inv; k3 *= inv;
+    if (mode == 1) return n0 * (-z0) / k3;
+    return n0 * (x * k1 + y * k2);
+}
+
+/* Grid form of the extension: like orc_grid_trace plus per-surface apertures (a may be NULL), OPD
+ * output  opd = (OPL - opl_ref) * opd_scale  and its mask semantics: kept = !(stop clip || vignetted
+ * || NaN).  opd may be NULL. */
+ORC_API int64_t orc_grid_trace_ext(int rows, const double *R, const double *t, const double *n,
+                                   const double *K, const double *a, int mode, double u_in, double v_in,
+                                   double ybar, double z0, double h_prime,
+                                   double xc, double yc, double rr, double opl_ref, double opd_scale,
+                                   int ny, const double *ys, int nx, const double *xs,
+                                   int stop, double a_stop,
+                                   double *ex, double *ey, double *opd, uint8_t *mask, uint8_t *flags_out,
+                                   int threads)
+{
+    int64_t kept = 0;
+    int nsurf = rows - 1;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel reduction(+ : kept)
+#endif
+    {
+        double *bx = (double *)malloc(sizeof(double) * 2 * rows);
+        double *by = bx + rows;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int iy = 0; iy < ny; iy++) {
+            for (int ix = 0; ix < nx; ix++) {
+                int64_t idx = (int64_t)iy * nx + ix;
+                double yi = ys[iy], xi = xs[ix];
+                double u = u_in, v = v_in;
+                if (mode == 1) { u = tan((ybar - yi) / z0); v = tan(-xi / z0); }
+                double opl0 = orc_opl_start(mode, n[0], yi, xi, u, v, z0), opl;
+                unsigned f = orc_trace3d_ext(rows, R, t, n, K, a, yi, xi, u, v, opl0, xc, yc, rr, bx, by, NULL, &opl);
+                double xf = bx[nsurf - 1], yf = by[nsurf - 1];
+                double ri = orc_hypot(bx[stop - 1], by[stop - 1]);
+                if (ri > a_stop) f |= F_CLIP;
+                int drop = (ri > a_stop) || (f & F_VIGN) || isnan(xf) || isnan(yf);
+                if (ex) ex[idx] = xf;
+                if (ey) ey[idx] = yf - h_prime;
+                if (opd) opd[idx] = (opl - opl_ref) * opd_scale;
+                if (mask) mask[idx] = (uint8_t)!drop;
+                if (flags_out) flags_out[idx] = (uint8_t)f;
+                kept += !drop;
+            }
+        }
+        free(bx);
+    }
+    return kept;
+}
+
 /* Ordered compaction: the reference's push! order (:134-137).  Returns count. */
 ORC_API int64_t orc_compact(int64_t N, const uint8_t *mask, const double *in, double *out)
 {

@@ -11,6 +11,7 @@ class OracleBackend:
         self.S = None
         self.K = None
         self.rows = 0
+        self.a = None
 
     def set_layout(self, surfaces, K=None):
         S = np.asarray(surfaces, dtype=np.float64)
@@ -18,11 +19,18 @@ class OracleBackend:
         self.K = None if K is None else np.asarray(K, dtype=np.float64).copy()
         self.rows = S.shape[0]
 
+    def set_apertures(self, a):
+        self.a = None if a is None else np.asarray(a, dtype=np.float64).copy()
+
     def trace2d_batch(self, y0, U0, aspheric=False):
         return orc.trace2d_batch(self.S, y0, U0, K=self.K, aspheric=aspheric)
 
-    def trace3d_rays(self, y0, x0, u0, v0, arith=0):
-        return orc.trace3d_batch(self.S, y0, x0, u0, v0, K=self.K)
+    def trace3d_rays(self, y0, x0, u0, v0, arith=0, opl=False):
+        xv, yv, k, fl = orc.trace3d_batch(self.S, y0, x0, u0, v0, K=self.K)
+        if not opl:
+            return xv, yv, k, fl
+        ol = np.array([orc.trace3d_ext(self.S, y0[i], x0[i], u0[i], v0[i], K=self.K)[3] for i in range(len(y0))])
+        return xv, yv, k, fl, ol
 
     def paraxial_batch(self, tau, phi, y0, w0, a=None, clip=False, arith=0, table=False):
         y, w, ci = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=clip)
@@ -39,11 +47,11 @@ class OracleBackend:
         return orc.transfer_batch(M, tau, taup, v_in, reverse=reverse)
 
     def trace3d_grid(self, fields, ys, xs, stop, a_stop, arith=1, compact=False,
-                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None):
+                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None, ext=0, opd_scale=1.0):
         from ort_b200 import STATS_DTYPE
         ys = np.asarray(ys, dtype=np.float64)
         nf, NN = len(fields), ys.shape[-1] * len(xs)
-        res = {k: np.full((nf, NN), np.nan) for k in ("ex", "ey", "r", "theta")}
+        res = {k: np.full((nf, NN), np.nan) for k in ("ex", "ey", "r", "theta", "opd")}
         res["mask"] = np.zeros((nf, NN), dtype=np.uint8)
         res["flags"] = np.zeros((nf, NN), dtype=np.uint8)
         stats = np.zeros(nf, dtype=STATS_DTYPE)
@@ -51,9 +59,21 @@ class OracleBackend:
             g = orc.grid_trace(self.S, ys[f] if ys.ndim == 2 else ys, xs, stop, a_stop, fld.get("h_prime", 0.0), u=fld.get("u", 0.0),
                                v=fld.get("v", 0.0), mode=fld.get("mode", 0), ybar=fld.get("ybar", 0.0),
                                z0=fld.get("z0", 1.0), K=self.K)
+            if ext or "opd" in want:
+                a = None
+                if ext & 2 and self.a is not None:
+                    a = np.full(self.rows - 1, np.inf); a[:len(self.a)] = self.a
+                ge = orc.grid_trace_ext(self.S, ys[f] if ys.ndim == 2 else ys, xs, stop, a_stop, fld.get("h_prime", 0.0),
+                                        u=fld.get("u", 0.0), v=fld.get("v", 0.0), mode=fld.get("mode", 0),
+                                        ybar=fld.get("ybar", 0.0), z0=fld.get("z0", 1.0), K=self.K, a=a,
+                                        xc=fld.get("opd_xc", 0.0), yc=fld.get("opd_yc", 0.0), rr=fld.get("opd_radius", 0.0),
+                                        opl_ref=fld.get("opl_ref", 0.0), opd_scale=opd_scale)
+                g["mask"], g["flags"], g["opd"] = ge["mask"], ge["flags"], ge["opd"]
+            else:
+                g["opd"] = np.zeros(NN)
             m = g["mask"].astype(bool)
             n = int(m.sum())
-            for k in ("ex", "ey", "r", "theta"):
+            for k in ("ex", "ey", "r", "theta", "opd"):
                 if compact:
                     res[k][f, :n] = g[k][m]
                 else:
@@ -66,7 +86,9 @@ class OracleBackend:
                 st["mean_x"], st["mean_y"] = ex.mean(), ey.mean()
                 st["m2_x"], st["m2_y"] = ((ex - ex.mean()) ** 2).sum(), ((ey - ey.mean()) ** 2).sum()
                 st["r_max"] = g["r"][m].max()
-            for k, bit in (("n_miss", 1), ("n_tir", 2), ("n_domain", 4), ("n_clip", 8)):
+                st["mean_opd"] = g["opd"][m].mean()
+                st["m2_opd"] = ((g["opd"][m] - g["opd"][m].mean()) ** 2).sum()
+            for k, bit in (("n_miss", 1), ("n_tir", 2), ("n_domain", 4), ("n_clip", 8), ("n_vig", 16)):
                 st[k] = int(((g["flags"] & bit) != 0).sum())
         res["stats"] = stats
         return res

@@ -29,10 +29,10 @@ def test_header_symbols_exported(ort):
 
 
 def test_struct_layouts(ort):
-    assert C.sizeof(ort._lib.Field) == 48
-    assert C.sizeof(ort._lib.Opts) == 32
-    assert C.sizeof(ort._lib.Stats) == 80 == ort.STATS_DTYPE.itemsize
-    assert C.sizeof(ort._lib.GridOut) == 9 * C.sizeof(C.c_void_p)
+    assert C.sizeof(ort._lib.Field) == 80
+    assert C.sizeof(ort._lib.Opts) == 40
+    assert C.sizeof(ort._lib.Stats) == 104 == ort.STATS_DTYPE.itemsize == ort.STATS_BYTES
+    assert C.sizeof(ort._lib.GridOut) == 10 * C.sizeof(C.c_void_p)
     assert ort._lib.load().ort_version() == 100
 
 

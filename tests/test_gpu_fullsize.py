@@ -30,7 +30,7 @@ def _sweep(ctx, ort, p, j, ys, xs, arith, compact=False, want=("ex", "ey", "mask
     for k in ("mask", "flags"):
         if k in want:
             bufs[k] = torch.empty(NN, dtype=torch.uint8, device=dev)
-    stats = torch.zeros(80, dtype=torch.uint8, device=dev)
+    stats = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
     ptrs = {k: v.data_ptr() for k, v in bufs.items()}
     ptrs["stats"] = stats.data_ptr()
     fld = dict(u=float(p["u"][j]), v=0.0, h_prime=float(p["h_prime"][j]))

@@ -222,3 +222,80 @@ def test_candidates(ctx, orc, pre, ort):
         assert np.array_equal(out[:, 0], ref[:, 0])                 # kept counts exact
         assert np.max(np.abs(out[:, 1:3] - ref[:, 1:3])) / 25.0 < TOL
         assert np.max(np.abs(out[:, 3] / ref[:, 3] - 1)) < 1e-11     # RMS about the centroid
+
+
+# ------------------------------------------------------------------------------------------------
+# EXTENSION: OPL / OPD accumulation and per-surface aperture clipping
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,H,vig", [("COOKE", 0.0, False), ("COOKE", 1.0, True), ("DOUBLE_GAUSS", 0.7, True),
+                                        ("TESSAR", 1.0, True), ("SINGLET", 0.7, False)])
+def test_grid_opd_and_vignetting(ctx, orc, pre, ort, name, H, vig):
+    P = getattr(ort.prescriptions, name)
+    sysm = pre.solve(P["surfaces"], P["a"], P["h"])
+    p = pre.full_trace_inputs(sysm, H, 64)
+    a = np.append(P["a"], np.inf) if vig else None               # image plane: unlimited
+    rr, yc = p.focus - sysm.XP.t, p.h_prime
+    opl_ref, scale = 100.0, -1.0 / 587.5618e-6
+    g = orc.grid_trace_ext(p.ext, p.ys, p.xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K, a=a, xc=0.0, yc=yc,
+                           rr=rr, opl_ref=opl_ref, opd_scale=scale)
+    ctx.set_layout(p.ext, p.K)
+    ctx.set_apertures(a)
+    fld = dict(u=p.u, v=p.v, h_prime=p.h_prime, opd_xc=0.0, opd_yc=yc, opd_radius=rr, opl_ref=opl_ref)
+    ext = ort.EXT_OPD | (ort.EXT_VIGNETTE if vig else 0)
+    m = g["mask"].astype(bool)
+    for arith in (ort.STRICT, ort.FAST):
+        r = ctx.trace3d_grid([fld], p.ys, p.xs, p.stop, p.a_stop, arith=arith, ext=ext, opd_scale=scale,
+                             want=("ex", "ey", "opd", "mask", "flags", "stats"))
+        assert np.array_equal(r["mask"][0], g["mask"]) and np.array_equal(r["flags"][0], g["flags"])
+        st = r["stats"][0]
+        assert int(st["n_kept"]) == g["n_kept"] and int(st["n_vig"]) == int(((g["flags"] & 16) != 0).sum())
+        if arith == ort.STRICT:
+            assert bits_equal(r["opd"][0], g["opd"]) and bits_equal(r["ex"][0], g["ex"])
+        else:
+            # OPD is a difference of ~100 mm optical paths: 1e-12 relative to the path length
+            err_mm = np.nanmax(np.abs(r["opd"][0] - g["opd"])) / abs(scale)
+            assert np.array_equal(np.isnan(r["opd"][0]), np.isnan(g["opd"])) and err_mm / 100.0 < TOL
+        if m.any():
+            assert abs(st["mean_opd"] - g["opd"][m].mean()) / abs(scale) / 100.0 < TOL
+            ref_m2 = ((g["opd"][m] - g["opd"][m].mean()) ** 2).sum()
+            assert abs(st["m2_opd"] - ref_m2) <= 1e-9 * max(ref_m2, 1.0)
+        # compacted OPD follows the same order
+        rc = ctx.trace3d_grid([fld], p.ys, p.xs, p.stop, p.a_stop, arith=arith, ext=ext, opd_scale=scale, compact=True,
+                              want=("opd", "mask", "stats"))
+        assert np.array_equal(rc["opd"][0][:int(st["n_kept"])], r["opd"][0][m])
+    ctx.set_apertures(None)
+
+
+def test_rays_opl(ctx, orc, ort):
+    S = ort.prescriptions.DOUBLE_GAUSS["surfaces"]
+    rng = np.random.default_rng(12)
+    N = 3000
+    y0, x0 = rng.uniform(-20, 20, N), rng.uniform(-20, 20, N)
+    u0, v0 = rng.uniform(-0.15, 0.15, N), rng.uniform(-0.15, 0.15, N)
+    ref = np.array([orc.trace3d_ext(S, y0[i], x0[i], u0[i], v0[i])[3] for i in range(N)])
+    truth = np.array([orc.trace3d_ext(S, y0[i], x0[i], u0[i], v0[i], truth=True) for i in range(N)])
+    ctx.set_layout(S)
+    xs, ys, ks, fs, ols = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT, opl=True)
+    assert n_bits_differ(ols, ref) == 0
+    xf, yf, kf, ff, olf = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST, opl=True)
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(olf), np.isnan(ref))
+    cond = np.abs(ref[ok] / truth[ok] - 1)
+    assert np.all(np.abs(olf[ok] / truth[ok] - 1) <= TOL / 2 + 2 * cond)
+
+
+def test_wavefront_api(ctx, ort):
+    """the public wavefront() on the GPU: parabola = perfect imaging, Cooke W040 = Seidel (book) value"""
+    ort.set_default_backend(ctx)
+    P = ort.prescriptions.PARABOLA
+    s = ort.solve(ort.Layout(P["surfaces"]), P["a"], P["h"])
+    w = ort.wavefront(s.layout, s, [0.0], 64)[0]
+    assert w.rms < 1e-9
+    P = ort.prescriptions.COOKE
+    s = ort.solve(P["surfaces"], P["a"], P["h"])
+    w = ort.wavefront(s.layout, s, [0.0], 64)[0]
+    e = ort.full_trace(s, 0.0)
+    n = len(w.opd) // 2
+    rho = e.r[:n]
+    c = np.linalg.lstsq(np.column_stack([rho ** 2, rho ** 4, rho ** 6, rho ** 8]), w.opd[:n], rcond=None)[0]
+    assert abs(c[1] / (2 * s.marginal.u[-1] / 587.5618e-6 * (-0.186575) / 8) - 1) < 0.03
