@@ -62,6 +62,7 @@ def test_vignetting_by_surface_apertures(ort, be):
     v0, v1 = ort.wavefront(s.layout, s, [0.0, 1.0], 64, backend=be, vignette=True)
     assert len(v0.opd) == len(w0.opd)      # on axis the stop limits: only rays already outside the stop are vignetted
     assert int(v1.stats["n_vig"][0]) > 0 and len(v1.opd) < len(w1.opd)       # at full field the rims vignette
-    # the surviving rays carry identical values
-    keep = np.isin(w1.x[:len(w1.x) // 2], v1.x[:len(v1.x) // 2])
-    assert np.array_equal(w1.opd[:len(w1.opd) // 2][keep], v1.opd[:len(v1.opd) // 2])
+    # the surviving rays carry identical values: every (ex, ey, opd) triple of the vignetted run occurs unvignetted
+    n1, nv = len(w1.opd) // 2, len(v1.opd) // 2
+    full = {(a, b): c for a, b, c in zip(w1.x[:n1], w1.y[:n1], w1.opd[:n1])}
+    assert all(full.get((a, b)) == c for a, b, c in zip(v1.x[:nv], v1.y[:nv], v1.opd[:nv]))
