@@ -31,15 +31,20 @@ struct OrtField            # ort_field
     ybar::Float64
     z0::Float64
     h_prime::Float64
+    opd_xc::Float64        # extension (ORT_EXT_OPD): reference sphere centre / radius, reference OPL
+    opd_yc::Float64
+    opd_radius::Float64
+    opl_ref::Float64
 end
 
 struct OrtOpts             # ort_opts
     arith::Int32
     compact::Int32
     ys_per_field::Int32
-    reserved::Int32
+    ext::Int32             # ORT_EXT_OPD = 1, ORT_EXT_VIGNETTE = 2 (extensions; 0 = the reference's behaviour)
     wg_nu::Float64
     wg_lambda::Float64
+    opd_scale::Float64
 end
 
 struct OrtStats            # ort_stats
@@ -53,6 +58,9 @@ struct OrtStats            # ort_stats
     n_tir::Int64
     n_domain::Int64
     n_clip::Int64
+    n_vig::Int64
+    mean_opd::Float64
+    m2_opd::Float64
 end
 
 struct OrtGridOut          # ort_grid_out
@@ -62,6 +70,7 @@ struct OrtGridOut          # ort_grid_out
     theta::Ptr{Float64}
     wx::Ptr{Float64}
     wy::Ptr{Float64}
+    opd::Ptr{Float64}
     mask::Ptr{UInt8}
     flags::Ptr{UInt8}
     stats::Ptr{OrtStats}
@@ -122,11 +131,11 @@ function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
     y1, y2 = (±(y_EP) - u * EP_t for (±) ∈ (+, -))
     y1, y2 = trace_edge_rays(surfaces, y1, y2, U, stop, a_stop)
     if typeof(system) <: System
-        field = OrtField(0, 0, u, tan(0.0), 0.0, 1.0, u * system.f)
+        field = OrtField(0, 0, u, tan(0.0), 0.0, 1.0, u * system.f, 0.0, 0.0, 0.0, 0.0)
     else
         z0 = system.marginal.z[1]
         ȳ = system.chief.y[2] + system.chief.u[1] * z0
-        field = OrtField(1, 0, 0.0, 0.0, ȳ, z0, system.chief.y[end])
+        field = OrtField(1, 0, 0.0, 0.0, ȳ, z0, system.chief.y[end], 0.0, 0.0, 0.0, 0.0)
     end
     # extend the surface matrix to the paraxial image plane (:111-114)
     R = [surfaces.R; Inf]; t = [surfaces.t; 0.0]; n = [surfaces.n; 1.0]; K = [surfaces.K; 0.0]
@@ -136,10 +145,10 @@ function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
     xs = collect(range(0.0, y_EP, div(k_rays, 2)))   # :122
     N = length(ys) * length(xs)
     εx = Vector{Float64}(undef, N); εy = similar(εx); r = similar(εx); θ = similar(εx)
-    stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
-    opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0))    # compact = 1: the reference's push! order
+    stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+    opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0, 1.0))   # compact = 1: the reference's push! order
     GC.@preserve εx εy r θ stats begin
-        out = Ref(OrtGridOut(pointer(εx), pointer(εy), pointer(r), pointer(θ), C_NULL, C_NULL,
+        out = Ref(OrtGridOut(pointer(εx), pointer(εy), pointer(r), pointer(θ), C_NULL, C_NULL, C_NULL,
                              C_NULL, C_NULL, Base.unsafe_convert(Ptr{OrtStats}, stats)))
         check(ccall((:ort_trace3d_grid, LIB), Cint,
                     (Ptr{Cvoid}, Ref{OrtField}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64,
