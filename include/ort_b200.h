@@ -208,6 +208,20 @@ int ort_trace3d_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *
                                const double *d_xs, int nx, int stop, double a_stop, int arith,
                                double *d_out, void *stream);
 
+/* ---- candidate-batched first-order solve + Seidel sums: what the reference's optimize()
+ *      evaluates per candidate (src/Optimization.jl:32-45): Lens(surfaces) src/RayTracing.jl:38-53, paraxial marginal
+ *      and chief rays :208-221, :246-263, aberrations() src/SeidelAberrations.jl:6-53.  RtnK[C][4][rows] (K unused),
+ *      shared apertures a[rows-1], image height h_prime, wavelength lambda, dispersion dn[rows] (NULL = zeros).
+ *      out[C][16] = f, EBFD, stop, H, W040, W131, W222, W220P, W311, W020, W111, W220, W220M, W220T, marginal nu[end],
+ *      chief nu[1]; per_surface (optional, [C][7][rows-1]) = spherical, coma, astigmatism, petzval, distortion, axial,
+ *      lateral.  One thread per candidate, reference operation order (bit-identical to the CPU restatement). */
+#define ORT_SEIDEL_NOUT 16
+int ort_seidel_candidates(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *a, double h_prime,
+                          double lambda, const double *dn, double *out, double *per_surface);
+int ort_seidel_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a /* host */,
+                              double h_prime, double lambda, const double *dn /* host */, double *d_out,
+                              double *d_per_surface, void *stream);
+
 /* ---- measurement helper: register-resident DFMA-chain microbenchmark; the FP64 roofline
  *      denominator (MEASURED_PEAKS.json holds no FP64 figure).  Returns TFLOP/s (2 flop per DFMA). */
 int ort_fp64_peak(ort_ctx *ctx, double *tflops, double *ms);

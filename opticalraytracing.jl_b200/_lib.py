@@ -24,7 +24,8 @@ SYMBOLS = [
     "ort_set_layout", "ort_set_apertures",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
-    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_fp64_peak",
+    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_seidel_candidates",
+    "ort_seidel_candidates_dev", "ort_fp64_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -122,6 +123,9 @@ def load():
     L.ort_trace3d_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.POINTER(Field),
                                              C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.ort_seidel_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.ort_seidel_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, _dp,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
     L.ort_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
     _lib = L
     return L
@@ -376,6 +380,25 @@ class Context:
         self._ck(self.L.ort_trace3d_candidates(self.h, rows, Cn, _p(RtnK), farr, _p(ys), len(ys), _p(xs),
                                                len(xs), int(stop), float(a_stop), int(arith), _p(out)))
         return out
+
+    def seidel_candidates(self, RtnK, a, h_prime, lam=587.5618e-6, dn=None, per_surface=False):
+        """first-order solve + Seidel sums per candidate -> (C, 16) [, (C, 7, rows-1)]"""
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        assert four == 4
+        a = _d(a)
+        dn_ = None if dn is None else _d(dn)
+        out = np.empty((Cn, 16))
+        per = np.empty((Cn, 7, rows - 1)) if per_surface else None
+        self._ck(self.L.ort_seidel_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(lam), _p(dn_),
+                                              _p(out), _p(per)))
+        return (out, per) if per_surface else out
+
+    def seidel_candidates_dev(self, rows, Cn, d_RtnK, a, h_prime, d_out, lam=587.5618e-6, dn=None, stream=0):
+        a = _d(a)
+        dn_ = None if dn is None else _d(dn)
+        self._ck(self.L.ort_seidel_candidates_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), _p(a), float(h_prime),
+                                                  float(lam), _p(dn_), C.c_void_p(d_out), None, C.c_void_p(stream)))
 
     def trace3d_candidates_dev(self, rows, Cn, d_RtnK, field, d_ys, ny, d_xs, nx, stop, a_stop, d_out,
                                arith=FAST, stream=0):

@@ -52,6 +52,14 @@ struct CandArgs {
     double* out;
 };
 
+struct SeidelArgs {
+    int rows; long long C;
+    const double* RtnK;
+    double h_prime, lambda;
+    double a[ORT_MAX_ROWS], dn[ORT_MAX_ROWS];
+    double* out; double* per;
+};
+
 struct LensK {                              // paraxial Lens rows in the constant bank
     int k; int clip;
     double tau[ORT_MAX_LENS], phi[ORT_MAX_LENS], a[ORT_MAX_LENS];
@@ -97,5 +105,6 @@ cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st);
 cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st);
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st);
 cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
+cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
                              long long* dfma_per_launch);

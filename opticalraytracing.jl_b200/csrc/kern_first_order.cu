@@ -158,6 +158,96 @@ __global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
+// K7: first-order solve + Seidel sums, one thread per candidate prescription.
+// Lens(surfaces) src/RayTracing.jl:38-53; trace_marginal_ray(lens, a) :208-221; trace_chief_ray(lens, ...)
+// :246-263; aberrations() src/SeidelAberrations.jl:6-53.  Two passes over the surfaces (the stop --
+// argmin a./y, :215-216 -- must be known before the chief ray can be combined), no per-thread arrays:
+// pass 2 recomputes the two basis rays with the same operations, hence the same bits.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelArgs A)
+{
+    const long long c = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (c >= A.C) return;
+    const int rows = A.rows, k = rows - 1;
+    const double* R = A.RtnK + (size_t)c * 4 * rows;
+    const double* t = R + rows;
+    const double* n = t + rows;
+    double* out = A.out + (size_t)c * ORT_SEIDEL_NOUT;
+    const double tl = t[rows - 1];
+    if (!(tl == 0.0 || !isfinite(tl))) {             // Lens() keeps the last row: solve() cannot use it
+        for (int j = 0; j < ORT_SEIDEL_NOUT; j++) out[j] = CUDART_NAN;
+        return;
+    }
+    // ---- pass 1
+    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
+    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0;
+    int stop = 1;
+    for (int i = 0; i < k; i++) {
+        double ti = t[i];
+        if (i == 0 && !isfinite(ti)) ti = 0.0;                       // :42
+        const double tau = SD(ti, n[i]);                             // :43
+        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);         // :45
+        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }     // :62
+        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));          // :67
+        const double v = SD(A.a[i], y1);
+        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }              // findmin :215-216
+    }
+    const double f = -SD(1.0, w1);                                   // :213
+    const double EBFD = SM(y1, f);
+    const double numk = SM(w1, s);                                   // marginal.nu[end]
+    const double y_stop = SM(ys1, s), y2_stop = ys2;
+    const double ym1 = SM(1.0, s);                                   // marginal.y[1] = y at the first surface?  see below
+    // ---- pass 2
+    y1 = 1.0; w1 = 0.0; y2 = 0.0; w2 = 1.0;
+    double W[7] = {0, 0, 0, 0, 0, 0, 0};
+    double nub = 0.0, H = 0.0;
+    for (int i = 0; i < k; i++) {
+        double ti = t[i];
+        if (i == 0 && !isfinite(ti)) ti = 0.0;
+        const double tau = SD(ti, n[i]);
+        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
+        const double w1_prev = w1;
+        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
+        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        const double ym = SM(y1, s);                                 // marginal y at surface i+1
+        if (i == 0) {
+            nub = SD(SM(-numk, A.h_prime), ym);                      // :256  -marginal.nu[end] * h' / y[1]
+            H = SM(nub, ym1);                                        // _solve :316  nu_bar * marginal.y[begin]
+        }
+        const double Ri = R[i + 1];
+        const double ni = n[i], ni1 = (i + 1 < rows) ? n[i + 1] : n[rows - 1];
+        const double yb = SM(nub, SS(y2, SD(SM(ym, y2_stop), y_stop)));               // :258
+        const double nu = SM(w1_prev, s), nu1 = SM(w1, s);
+        const double u0 = SD(nu, ni), u1 = SD(nu1, ni1);
+        const double Aa = SA(nu, SD(SM(ni, ym), Ri));                                  // SeidelAberrations.jl:17
+        const double Ab = SD(SA(H, SM(Aa, yb)), ym);                                   // :18
+        const double yD = SM(ym, SS(SD(u1, ni1), SD(u0, ni)));                         // :19
+        const double yd = SM(ym, SS(SD(A.dn[i + 1], ni1), SD(A.dn[i], ni)));           // :20
+        const double in1 = SD(1.0, ni1), in0 = SD(1.0, ni);
+        const double Dn2 = SS(SM(in1, in1), SM(in0, in0));                             // :21
+        const double P = SD(SS(in1, in0), Ri);                                         // :22
+        const double l8 = SM(8.0, A.lambda), l2 = SM(2.0, A.lambda), l4 = SM(4.0, A.lambda);
+        double v[7];
+        v[0] = SD(SM(-SM(Aa, Aa), yD), l8);                                            // :24
+        v[1] = SD(SM(SM(-Aa, Ab), yD), l2);                                            // :25
+        v[2] = SD(SM(-SM(Ab, Ab), yD), l2);                                            // :26
+        v[3] = SD(SM(-SM(H, H), P), l4);                                               // :27
+        v[4] = SD(SM(-Ab, SS(SM(SM(SM(Ab, Ab), ym), Dn2), SM(SM(SA(H, SM(Ab, ym)), yb), P))), l2);   // :29
+        v[5] = SD(SM(Aa, yd), l2);                                                     // :30
+        v[6] = SD(SM(Ab, yd), A.lambda);                                               // :31
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            W[j] = SA(W[j], v[j]);
+            if (A.per) A.per[((size_t)c * 7 + j) * k + i] = v[j];
+        }
+    }
+    out[0] = f; out[1] = EBFD; out[2] = (double)stop; out[3] = H;
+    out[4] = W[0]; out[5] = W[1]; out[6] = W[2]; out[7] = W[3]; out[8] = W[4]; out[9] = W[5]; out[10] = W[6];
+    out[11] = SA(W[3], SM(0.5, W[2])); out[12] = SA(W[3], W[2]); out[13] = SA(W[3], SM(1.5, W[2]));
+    out[14] = numk; out[15] = nub;
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 roofline denominator: 8 independent DFMA chains per thread, register resident.
 // ------------------------------------------------------------------------------------------
 #define PEAK_CHAINS 8
@@ -214,6 +304,13 @@ cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st)
     long long nb = (A.N + 255) / 256;
     if (nb > 148 * 32) nb = 148 * 32;
     k_transfer<<<(unsigned)nb, 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st)
+{
+    if (A.C == 0) return cudaSuccess;
+    k_seidel<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A);
     return cudaGetLastError();
 }
 

@@ -712,6 +712,48 @@ int ort_trace3d_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK
     return ORT_OK;
 }
 
+int ort_seidel_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* a, double h_prime,
+                              double lambda, const double* dn, double* d_out, double* d_per_surface, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS) return fail(ctx, ORT_EINVAL, "seidel: rows = %d", rows);
+    if (C < 0 || C >= (1LL << 31) || !d_RtnK || !a || !d_out) return fail(ctx, ORT_EINVAL, "seidel: bad input");
+    if (!(lambda > 0.0)) return fail(ctx, ORT_EINVAL, "seidel: lambda must be positive");
+    CK(cudaSetDevice(ctx->device));
+    SeidelArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.h_prime = h_prime; A.lambda = lambda; A.out = d_out; A.per = d_per_surface;
+    for (int i = 0; i + 1 < rows; i++) A.a[i] = a[i];
+    for (int i = 0; i < rows; i++) A.dn[i] = dn ? dn[i] : 0.0;
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_seidel(A, (cudaStream_t)stream));
+    }
+    if (C > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_seidel_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, const double* a, double h_prime,
+                          double lambda, const double* dn, double* out, double* per_surface)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (C < 0 || !RtnK || !a || !out || rows < 2) return fail(ctx, ORT_EINVAL, "seidel: bad input");
+    if (C == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)C * 4 * (size_t)rows * 8, no = (size_t)C * ORT_SEIDEL_NOUT * 8;
+    const size_t np_ = (size_t)C * 7 * (size_t)(rows - 1) * 8;
+    double *d_p, *d_o, *d_per = nullptr;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT0, no, d_o);
+    if (per_surface) ENSURE(SL_OUT1, np_, d_per);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
+    int rc = ort_seidel_candidates_dev(ctx, rows, C, d_p, a, h_prime, lambda, dn, d_o, d_per, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, no, cudaMemcpyDeviceToHost, st));
+    if (per_surface) CK(cudaMemcpyAsync(per_surface, d_per, np_, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
 int ort_fp64_peak(ort_ctx* ctx, double* tflops, double* ms)
 {
     if (!ctx || !tflops) return ORT_EINVAL;

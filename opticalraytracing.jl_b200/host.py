@@ -674,6 +674,91 @@ def wavefront(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, lam=LAMBDA, vi
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# Seidel aberrations: the per-candidate objective of the reference's optimize()
+# ------------------------------------------------------------------------------------------------
+SEIDEL_FIELDS = ("f", "EBFD", "stop", "H", "W040", "W131", "W222", "W220P", "W311", "W020", "W111", "W220", "W220M",
+                 "W220T", "nu_marginal", "nu_chief")
+SEIDEL_SURFACE_FIELDS = ("spherical", "coma", "astigmatism", "petzval", "distortion", "axial", "lateral")
+
+
+@dataclass
+class Aberration:
+    """Aberration (src/Types.jl:143-167): wave coefficients + per-surface contributions"""
+    W040: float
+    W131: float
+    W222: float
+    W220: float
+    W311: float
+    W020: float
+    W111: float
+    W220P: float
+    W220M: float
+    W220T: float
+    spherical: np.ndarray
+    coma: np.ndarray
+    astigmatism: np.ndarray
+    sagittal: np.ndarray
+    distortion: np.ndarray
+    axial: np.ndarray
+    lateral: np.ndarray
+    petzval: np.ndarray
+    medial: np.ndarray
+    tangential: np.ndarray
+    lam: float
+    field_sign: int
+    nu: float
+
+    def __call__(self, rho, theta, H):
+        """W(rho, theta, H) -- the Seidel wavefront polynomial, src/SeidelAberrations.jl:61-76"""
+        H = np.abs(H)
+        if np.any(H > 1.0):
+            raise ValueError("DomainError: Domain: |H| <= 1.0")
+        if np.any((np.asarray(rho) < 0.0) | (np.asarray(rho) > 1.0)):
+            raise ValueError("DomainError: Domain: 0.0 <= rho <= 1.0")
+        H = H * self.field_sign
+        c = np.cos(theta)
+        return (self.W040 * rho ** 4 + self.W131 * H * rho ** 3 * c + self.W222 * H ** 2 * rho ** 2 * c ** 2 +
+                self.W220 * H ** 2 * rho ** 2 + self.W311 * H ** 3 * rho * c + self.W020 * rho ** 2 + self.W111 * H * rho * c)
+
+    def ray_error(self, x, y, H):
+        """transverse ray error polynomials (eps_x, eps_y), src/SeidelAberrations.jl:78-102"""
+        if np.any(np.hypot(x, y) > 1.0):
+            raise ValueError("DomainError: Domain: hypot(x, y) <= 1.0")
+        H = np.abs(H)
+        if np.any(H > 1.0):
+            raise ValueError("DomainError: Domain: |H| <= 1.0")
+        H = H * self.field_sign
+        ey = (4 * self.W040 * (x ** 2 * y + y ** 3) + self.W131 * H * (x ** 2 + 3 * y ** 2) + 2 * self.W222 * H ** 2 * y +
+              2 * self.W220 * H ** 2 * y + self.W311 * H ** 3 + 2 * self.W020 * y + self.W111 * H) * self.lam / self.nu
+        ex = (4 * self.W040 * (y ** 2 * x + x ** 3) + self.W131 * H * (2 * x * y) + 0 + 2 * self.W220 * H ** 2 * x + 0 +
+              2 * self.W020 * x + 0) * self.lam / self.nu
+        return ex, ey
+
+
+def aberrations(surfaces, system, lam=LAMBDA, dn=None, backend=None):
+    """aberrations(surfaces, system, lambda, dn) -- src/SeidelAberrations.jl:6-53, evaluated by the candidate
+    kernel (K7) on a batch of one.  `system` must be solve(surfaces, system.a, system.chief.y[-1])."""
+    layout = _as_layout(surfaces)
+    RtnK = np.stack([layout.R, layout.t, layout.n, layout.K])[None]
+    out, per = _be(backend).seidel_candidates(RtnK, system.a, system.chief.y[-1], lam=lam, dn=dn, per_surface=True)
+    o = dict(zip(SEIDEL_FIELDS, out[0]))
+    sp, co, ast, ptz, dist, ax, lat = per[0]
+    return Aberration(o["W040"], o["W131"], o["W222"], o["W220"], o["W311"], o["W020"], o["W111"], o["W220P"], o["W220M"],
+                      o["W220T"], sp, co, ast, ptz + ast / 2, dist, ax, lat, ptz, ptz + ast, ptz + 1.5 * ast, lam,
+                      int(np.sign(system.chief.y[-1])), float(system.marginal.nu[-1]))
+
+
+def seidel_merit(backend, RtnK, a, h_prime, aberr=("W040", "W131", "W222", "W220", "W311"), weights=None, lam=LAMBDA,
+                 dn=None):
+    """Population evaluation of the reference's optimisation objective, sum_i w_i |W_i| (src/Optimization.jl:40-45,
+    without its constraint penalty), for C candidate prescriptions in one launch.  Returns (merit (C,), table (C, 16))."""
+    out = _be(backend).seidel_candidates(RtnK, a, h_prime, lam=lam, dn=dn)
+    w = np.ones(len(aberr)) if weights is None else np.asarray(weights, dtype=np.float64)
+    cols = [SEIDEL_FIELDS.index(k) for k in aberr]
+    return np.abs(out[:, cols]) @ w, out
+
+
 def wavegrad(eps, lam=LAMBDA):
     """wavegrad(eps::RealRayError, lambda) -- src/PupilSampling.jl:165-167"""
     return eps.x * eps.nu / lam, eps.y * eps.nu / lam

@@ -286,6 +286,36 @@ def grid_trace_ext(ext_surfaces, ys, xs, stop, a_stop, h_prime, u=0.0, v=0.0, mo
     return out
 
 
+SEIDEL_FIELDS = ("f", "EBFD", "stop", "H", "W040", "W131", "W222", "W220P", "W311", "W020", "W111", "W220", "W220M",
+                 "W220T", "nu_marginal", "nu_chief")
+
+
+def seidel(surfaces, a, h_prime, lam=587.5618e-6, dn=None):
+    """solve + aberrations of one prescription -> (dict of the 16 scalars, per-surface (7, k) table)
+    [src/RayTracing.jl:38-53,208-221,246-263; src/SeidelAberrations.jl:6-53]"""
+    R, t, n, _ = _cols(surfaces)
+    rows = len(R)
+    a = _d(a)
+    dn_ = None if dn is None else _d(dn)
+    out, per = np.empty(16), np.empty((7, rows - 1))
+    rc = lib().orc_seidel(C.c_int(rows), _p(R), _p(t), _p(n), _p(a), C.c_double(h_prime), C.c_double(lam), _p(dn_),
+                          _p(out), _p(per))
+    if rc != 0:
+        raise ValueError(f"orc_seidel failed ({rc})")
+    return dict(zip(SEIDEL_FIELDS, out)), per
+
+
+def seidel_candidates(RtnK, a, h_prime, lam=587.5618e-6, dn=None, threads=0):
+    RtnK = _d(RtnK)
+    Cn, four, rows = RtnK.shape
+    a = _d(a)
+    dn_ = None if dn is None else _d(dn)
+    out = np.empty((Cn, 16))
+    lib().orc_seidel_candidates(C.c_int(rows), C.c_int64(Cn), _p(RtnK), _p(a), C.c_double(h_prime), C.c_double(lam),
+                                _p(dn_), _p(out), C.c_int(threads))
+    return out
+
+
 def compact(mask, arr):
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     arr = _d(arr)

@@ -726,6 +726,91 @@ ORC_API int64_t orc_grid_trace_ext(int rows, const double *R, const double *t, c
     return kept;
 }
 
+
+/* ------------------------------------------------------------------------------------
+ * First-order solve + Seidel aberration sums of ONE prescription: what the
+ * reference's optimize() evaluates per candidate (src/Optimization.jl:32-45).  Restates
+ *   Lens(surfaces)                 src/RayTracing.jl:38-53
+ *   trace_marginal_ray(lens, a)    src/RayTracing.jl:208-221   (y = 1, w = 0; stop = argmin a./y)
+ *   trace_chief_ray(lens, ...)     src/RayTracing.jl:246-263   (y = 0, w = 1 basis ray)
+ *   aberrations(surfaces, system, lambda, dn)   src/SeidelAberrations.jl:6-53
+ * out[16] = f, EBFD, stop, H, W040, W131, W222, W220P, W311, W020, W111, W220, W220M, W220T,
+ *           marginal nu[end], chief nu[1].   per[7][k] (optional): spherical, coma, astigmatism,
+ * petzval, distortion, axial, lateral per surface.  dn may be NULL (zeros).  k = rows - 1 surfaces
+ * (the prescription's last thickness must be 0 or Inf, as solve() requires).
+ * ---------------------------------------------------------------------------------- */
+ORC_API int orc_seidel(int rows, const double *R, const double *t, const double *n, const double *a,
+                       double h_prime, double lambda, const double *dn, double *out, double *per)
+{
+    int k = rows - 1;
+    if (k < 1 || k > 126) return -1;
+    double tau[128], phi[128];
+    if (orc_lens(rows, R, t, n, tau, phi) != k) return -2;
+    /* pass 1: basis rays (1, 0) and (0, 1); stop = argmin a[i] / y[i] */
+    double y1[129], w1[129], y2[129], w2[129];
+    y1[0] = 1.0; w1[0] = 0.0; y2[0] = 0.0; w2[0] = 1.0;
+    for (int i = 0; i < k; i++) {
+        y1[i + 1] = px_transfer(y1[i], w1[i], tau[i]); w1[i + 1] = px_refract(y1[i + 1], w1[i], phi[i]);
+        y2[i + 1] = px_transfer(y2[i], w2[i], tau[i]); w2[i + 1] = px_refract(y2[i + 1], w2[i], phi[i]);
+    }
+    double f = -(1.0 / w1[k]);                                   /* f = -inv(w[end])   :213 */
+    double EBFD = y1[k] * f;
+    int stop = 1; double s = a[0] / y1[1];
+    for (int i = 1; i < k; i++) { double v = a[i] / y1[i + 1]; if (v < s) { s = v; stop = i + 1; } }   /* findmin :215-216 */
+    /* marginal_ray *= s (:217); n extended by n[end] (Types.jl:39) */
+    double ym[130], num[130], nx[130];
+    for (int i = 0; i <= k; i++) { ym[i] = y1[i] * s; num[i] = w1[i] * s; }
+    for (int i = 0; i < rows; i++) nx[i] = n[i];
+    nx[rows] = n[rows - 1];
+    double y_stop = ym[stop], y2_stop = y2[stop];
+    double nub = -num[k] * h_prime / ym[1];                      /* :256  (marginal.nu[end] = extended row = num[k]) */
+    double H = nub * ym[0];                                      /* _solve :316 */
+    double W[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 1; i <= k; i++) {                               /* surface i: row i+1 of the layout */
+        double Ri = R[i];
+        double y = ym[i];
+        double yb = nub * (y2[i] - ym[i] * y2_stop / y_stop);    /* chief.y at surface i  :258 */
+        double nu = num[i - 1], ni = nx[i - 1], ni1 = nx[i];
+        double u0 = num[i - 1] / nx[i - 1], u1 = num[i] / nx[i];
+        double A = nu + ni * y / Ri;                             /* SeidelAberrations.jl:17 */
+        double Ab = (H + A * yb) / y;                            /* :18 */
+        double yD = y * (u1 / ni1 - u0 / ni);                    /* :19, Delta :4 */
+        double d0 = dn ? dn[i - 1] : 0.0, d1 = dn ? dn[i] : 0.0;
+        double yd = y * (d1 / ni1 - d0 / ni);                    /* :20 */
+        double in1 = 1.0 / ni1, in0 = 1.0 / ni;
+        double Dn2 = in1 * in1 - in0 * in0;                      /* :21 */
+        double P = (in1 - in0) / Ri;                             /* :22 */
+        double sph = -(A * A) * yD / (8 * lambda);               /* :24 */
+        double coma = -A * Ab * yD / (2 * lambda);               /* :25 */
+        double ast = -(Ab * Ab) * yD / (2 * lambda);             /* :26 */
+        double ptz = -(H * H) * P / (4 * lambda);                /* :27 */
+        double dist = -Ab * (Ab * Ab * y * Dn2 - (H + Ab * y) * yb * P) / (2 * lambda);   /* :29 */
+        double ax = A * yd / (2 * lambda);                       /* :30 */
+        double lat = Ab * yd / lambda;                           /* :31 */
+        double v[7] = {sph, coma, ast, ptz, dist, ax, lat};
+        for (int j = 0; j < 7; j++) { W[j] += v[j]; if (per) per[j * k + (i - 1)] = v[j]; }
+    }
+    out[0] = f; out[1] = EBFD; out[2] = (double)stop; out[3] = H;
+    out[4] = W[0]; out[5] = W[1]; out[6] = W[2]; out[7] = W[3]; out[8] = W[4]; out[9] = W[5]; out[10] = W[6];
+    out[11] = W[3] + 0.5 * W[2]; out[12] = W[3] + W[2]; out[13] = W[3] + 1.5 * W[2];     /* :41-43 */
+    out[14] = num[k]; out[15] = nub;
+    return 0;
+}
+
+ORC_API void orc_seidel_candidates(int rows, int64_t C, const double *RtnK, const double *a, double h_prime,
+                                   double lambda, const double *dn, double *out, int threads)
+{
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t c = 0; c < C; c++) {
+        const double *Rc = RtnK + c * 4 * rows;
+        if (orc_seidel(rows, Rc, Rc + rows, Rc + 2 * rows, a, h_prime, lambda, dn, out + 16 * c, NULL) != 0)
+            for (int j = 0; j < 16; j++) out[16 * c + j] = NAN;
+    }
+}
+
 /* Ordered compaction: the reference's push! order (:134-137).  Returns count. */
 ORC_API int64_t orc_compact(int64_t N, const uint8_t *mask, const double *in, double *out)
 {

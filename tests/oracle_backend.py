@@ -43,6 +43,13 @@ class OracleBackend:
             ya[:, j], wa[:, j] = rt[:, 0], rt[:, 1]
         return y, w, ci, ya, wa
 
+    def seidel_candidates(self, RtnK, a, h_prime, lam=587.5618e-6, dn=None, per_surface=False):
+        out = orc.seidel_candidates(RtnK, a, h_prime, lam=lam, dn=dn)
+        if not per_surface:
+            return out
+        per = np.stack([orc.seidel(np.asarray(c)[:3].T, a, h_prime, lam=lam, dn=dn)[1] for c in RtnK])
+        return out, per
+
     def transfer_batch(self, M, tau, taup, v_in, reverse=False):
         return orc.transfer_batch(M, tau, taup, v_in, reverse=reverse)
 

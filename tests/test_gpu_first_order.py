@@ -124,3 +124,22 @@ def test_error_paths(ctx, ort):
 def test_fp64_peak(ctx):
     tf, ms = ctx.fp64_peak()
     assert 10.0 < tf < 60.0, tf
+
+
+def test_seidel_candidates(ctx, orc, ort):
+    """K7: first-order solve + Seidel sums per candidate == the CPU restatement, bit for bit"""
+    P = ort.prescriptions.COOKE
+    dn = [0.0, 0.010450, 0.0, 0.019151, 0.0, 0.0, 0.010450, 0.0]
+    C = 4099
+    RtnK = ort.prescriptions.perturbed_triplets(C)
+    RtnK[0] = np.vstack([P["surfaces"].T, np.zeros(8)])            # candidate 0 = the nominal triplet
+    ref = orc.seidel_candidates(RtnK, P["a"], P["h"], dn=dn)
+    out, per = ctx.seidel_candidates(RtnK, P["a"], P["h"], dn=dn, per_surface=True)
+    assert n_bits_differ(out, ref) == 0
+    d, per0 = orc.seidel(P["surfaces"], P["a"], P["h"], dn=dn)
+    assert n_bits_differ(per[0], per0) == 0
+    assert abs(out[0, 0] - 101.181) < 1e-3 and out[0, 2] == 5 and abs(out[0, 4] - 11.46) < 0.25
+    # a prescription solve() cannot use (last thickness nonzero) -> NaN row, not a crash
+    bad = RtnK[:2].copy(); bad[1, 1, -1] = 3.0
+    o2 = ctx.seidel_candidates(bad, P["a"], P["h"])
+    assert np.isnan(o2[1]).all() and not np.isnan(o2[0]).any()

@@ -156,3 +156,33 @@ def test_shard_rows(ort):
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_aberrations_and_ray_error_functors(ort, be, cooke):
+    """test/runtests.jl:205-229 (coefficients) and :290-310 (transverse ray error functors)"""
+    SE = KAT["cooke_triplet"]["seidel"]
+    P = ort.prescriptions.COOKE
+    ab = ort.aberrations(P["surfaces"], cooke, dn=SE["dn"], backend=be)
+    alpha = 2 * cooke.marginal.u[-1] / ort.LAMBDA
+    for name, div in SE["total_divisors"].items():
+        assert abs(getattr(ab, name) - alpha * SE[name] / div) < 0.25, name
+    assert np.allclose(ab.sagittal, ab.petzval + ab.astigmatism / 2) and np.allclose(ab.tangential, ab.petzval + 1.5 * ab.astigmatism)
+    ab0 = ort.aberrations(P["surfaces"], cooke, backend=be)                     # no dispersion
+    W040, W131, W222, W220P, W311 = (SE[k] for k in ("W040", "W131", "W222", "W220P", "W311"))
+    ex, ey = ab0.ray_error(0.0, 1.0, 1.0)
+    assert abs(ey - (W040 + 3 * W131 + 3 * W222 + W220P + W311)) < 1e-3          # :294
+    ex, ey = ab0.ray_error(1.0, 0.0, 1.0)
+    assert abs(ex - (W040 + W222 + W220P)) < 1e-3                                # :295
+    rng = np.random.default_rng(5)
+    rho, th, H = rng.uniform(), 2 * math.pi * rng.uniform(), rng.uniform()
+    x, y = rho * math.sin(th), rho * math.cos(th)
+    ex, ey = ab0.ray_error(x, y, H)
+    assert abs(ey - (W040 * rho ** 3 * math.cos(th) + W131 * rho ** 2 * H * (2 + math.cos(2 * th)) +
+                     (3 * W222 + W220P) * rho * H ** 2 * math.cos(th) + W311 * H ** 3)) < 1e-3       # :303-306
+    assert abs(ex - (W040 * rho ** 3 * math.sin(th) + W131 * rho ** 2 * H * math.sin(2 * th) +
+                     (W222 + W220P) * rho * H ** 2 * math.sin(th))) < 1e-3                           # :307-309
+    assert abs(ab0(1.0, 0.0, 0.0) - ab0.W040) < 1e-12 and ab0(0.0, 0.3, 0.5) == 0.0
+    with pytest.raises(ValueError):
+        ab0(1.5, 0.0, 0.0)
+    merit, table = ort.seidel_merit(be, ort.prescriptions.perturbed_triplets(16), P["a"], P["h"])
+    assert merit.shape == (16,) and np.all(merit > 0) and table.shape == (16, 16)

@@ -217,3 +217,25 @@ def test_oracle_edge_cases(orc):
     # empty grid
     g = orc.grid_trace(np.vstack([S, [np.inf, 0, 1]]), np.zeros(0), np.zeros(3), 5, 10.3, 0.0)
     assert g["n_kept"] == 0 and g["ex"].size == 0
+
+
+def test_seidel_aberrations(system, orc):
+    """test/runtests.jl:160-229: per-surface Seidel contributions and totals vs the book table (0.25 wave)"""
+    SE = COOKE["seidel"]
+    d, per = orc.seidel(S, A, COOKE["h_prime"], dn=SE["dn"])
+    assert d["f"] == system.f and d["EBFD"] == system.EBFD and d["stop"] == 5 and d["H"] == system.H
+    alpha = 2 * system.marginal.u[-1] / KAT["constants"]["lambda_mm"]
+    tol = SE["wave_scale_atol"]
+    third = np.array(SE["third_order"])
+    for j, div in enumerate(SE["third_order_divisors"]):            # spherical, coma, astigmatism, petzval, distortion
+        assert np.max(np.abs(per[j] - alpha * third[:, j] / div)) < tol
+    assert np.max(np.abs(per[5] - alpha * np.array(SE["PAC"]) / SE["PAC_divisor"])) < tol
+    assert np.max(np.abs(per[6] - alpha * np.array(SE["PLC"]) / SE["PLC_divisor"])) < tol
+    for name, div in SE["total_divisors"].items():
+        assert abs(d[name] - alpha * SE[name] / div) < tol, name
+    # Petzval curvature identity (test/runtests.jl:223-228)
+    N = system.N
+    rho = COOKE["h_prime"] ** 2 / (2 * (-8 * N ** 2 * d["W220P"] * KAT["constants"]["lambda_mm"]))
+    n = S[:, 2]
+    ptzc = -np.sum(system.phi / (n[1:] * n[:-1]))
+    assert math.isclose(1 / rho, ptzc, rel_tol=1e-9)
