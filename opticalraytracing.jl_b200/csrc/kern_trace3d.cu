@@ -88,12 +88,17 @@ template <int RPT, bool EXT, class SurfArray>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
-                                           const ort_field* fld = nullptr, double nlast = 1.0, bool vignette = false)
+                                           const ort_field* fld = nullptr, double nlast = 1.0, bool vignette = false,
+                                           const double* K0 = nullptr)
 {
     RaysF<RPT> r;
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
-        fast_init(r, j, n0, y[j], x[j], u[j], v[j]);
+        if (K0) {           // collimated field: the optical direction is the same for every ray of the field
+            r.x[j] = x[j]; r.y[j] = y[j]; r.z[j] = 0.0;
+            r.Kx[j] = K0[0]; r.Ky[j] = K0[1]; r.Kz[j] = K0[2];
+            r.amb[j] = 0; r.opl[j] = 0.0; r.vig[j] = 0;
+        } else fast_init(r, j, n0, y[j], x[j], u[j], v[j]);
         if (EXT) {          // start term: K = n0 k, so n0 (x k1 + y k2) = x Kx + y Ky;  n0 (-z0) / k3 = -n0^2 z0 / Kz
             r.opl[j] = (fld->mode == 1) ? fast_div(-(n0 * n0) * fld->z0, r.Kz[j]) : fma(x[j], r.Kx[j], y[j] * r.Ky[j]);
         }
@@ -218,7 +223,9 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
     }
     const bool vig = EXT && (h.flags & ORT_FLAG_VIGN);
-    const bool drop = clip || vig || is_nan_bits(h.xf) || is_nan_bits(h.yf);   // :132 (+ surface apertures)
+    // :132 (+ surface apertures).  A ray that stayed on the fast path is finite by construction (non-finite
+    // values set amb), so the NaN tests are only needed after a strict trace.
+    const bool drop = clip || vig || (sv && (is_nan_bits(h.xf) || is_nan_bits(h.yf)));
     const unsigned flags = h.flags | (clip ? ORT_FLAG_CLIP : 0u);
     const int kept = valid && !drop;
     const double ex = h.xf;                                             // :135
@@ -235,8 +242,11 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         if (EXT && A.opd) A.opd[o] = opd;
         if (A.mask) A.mask[o] = (uint8_t)kept;
         if (A.flags) A.flags[o] = (uint8_t)flags;
-        acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
-        acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0) + (flags & ORT_FLAG_CLIP ? 0x10000 : 0);
+        if (sv) {           // miss / TIR / domain flags can only come out of a strict trace
+            acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
+            acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0);
+        }
+        acc.nflag_hi += clip ? 0x10000 : 0;
         if (EXT) acc.nvig += vig ? 1 : 0;
     }
     if (kept) {
@@ -286,6 +296,24 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     __syncthreads();
     const double cx = s_shift[0], cy = s_shift[1], co = s_shift[2];
 
+    // collimated field (mode 0): K = n0 normalize([v, u, 1]) once per thread, not once per ray
+    const bool collimated = (fld.mode == 0);
+    double K0[3] = {0.0, 0.0, 0.0};
+    if (ARITH == ORT_ARITH_FAST && collimated) {
+        const double inv = P.n0 * fast_rsqrt(fma(fld.v, fld.v, fma(fld.u, fld.u, 1.0)));
+        K0[0] = fld.v * inv; K0[1] = fld.u * inv; K0[2] = inv;
+    }
+    // (iy, ix) of this thread's rays advance by a constant (dq, dr) per tile: no division in the loop
+    const unsigned nxu = (unsigned)A.nx;
+    const unsigned step = gridDim.x * (RPT * ORT_TILE);
+    const unsigned dq = step / nxu, dr = step - dq * nxu;
+    unsigned iyj[RPT], ixj[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const unsigned i0 = (blockIdx.x * RPT + j) * ORT_TILE + threadIdx.x;
+        iyj[j] = i0 / nxu; ixj[j] = i0 - iyj[j] * nxu;
+    }
+
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         double y0[RPT], x0[RPT], u[RPT], v[RPT];
         unsigned idx[RPT];
@@ -295,14 +323,18 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
             const unsigned i0 = (tile * RPT + j) * ORT_TILE + threadIdx.x;
             valid[j] = i0 < NN;
             idx[j] = valid[j] ? i0 : NN - 1;     // padded lanes re-trace the last ray: the warp stays convergent
-            const unsigned iy = idx[j] / (unsigned)A.nx, ix = idx[j] - iy * (unsigned)A.nx;   // y outer, x inner (:123)
+            const unsigned iy = valid[j] ? iyj[j] : (unsigned)A.ny - 1, ix = valid[j] ? ixj[j] : nxu - 1;   // y outer, x inner (:123)
             y0[j] = __ldg(ysf + iy); x0[j] = __ldg(A.xs + ix);
-            field_slopes(fld, y0[j], x0[j], u[j], v[j]);
+            if (collimated) { u[j] = fld.u; v[j] = fld.v; }
+            else field_slopes(fld, y0[j], x0[j], u[j], v[j]);
+            ixj[j] += dr; iyj[j] += dq;
+            if (ixj[j] >= nxu) { ixj[j] -= nxu; iyj[j]++; }
         }
         Hit h[RPT];
         int amb[RPT];
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<RPT, EXT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette);
+            trace_fast<RPT, EXT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
+                                 collimated ? K0 : nullptr);
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
