@@ -1,0 +1,98 @@
+"""Parity over the input space: seeded random sequential systems (spheres, planes, conics, mirrors with
+negative indices, cemented groups) -- STRICT bit-exact, FAST within 1e-12 of the reference arithmetic (or
+as accurate as it against the 80-bit truth on ill-conditioned rays), flags and clip masks identical."""
+import numpy as np
+import pytest
+
+from util import n_bits_differ
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def random_system(rng, mirrors=False, conics=False):
+    nel = int(rng.integers(1, 6))
+    rows = [[np.inf, 0.0, 1.0, 0.0]]
+    n_air = 1.0
+    for e in range(nel):
+        ng = rng.uniform(1.45, 1.9) * np.sign(n_air)
+        for face in range(2):
+            R = np.inf if rng.uniform() < 0.15 else rng.choice([-1, 1]) * rng.uniform(25.0, 300.0)
+            K = rng.uniform(-2.0, 0.8) if (conics and np.isfinite(R) and rng.uniform() < 0.5) else 0.0
+            if face == 0:
+                rows.append([R, rng.uniform(2.0, 8.0) * np.sign(n_air), ng, K])
+            else:
+                rows.append([R, rng.uniform(0.5, 15.0) * np.sign(n_air), n_air, K])
+        if rng.uniform() < 0.3:                        # cemented extra element
+            rows.insert(-1, [rng.choice([-1, 1]) * rng.uniform(25.0, 300.0), rng.uniform(1.0, 5.0) * np.sign(n_air),
+                             rng.uniform(1.45, 1.9) * np.sign(n_air), 0.0])
+        if mirrors and rng.uniform() < 0.4:            # fold: index and thickness signs flip
+            n_air = -n_air
+            rows.append([rng.choice([-1, 1]) * rng.uniform(80.0, 400.0), rng.uniform(5.0, 20.0) * np.sign(n_air), n_air,
+                         rng.uniform(-1.5, 0.0) if conics else 0.0])
+    S = np.array(rows)
+    S[-1, 1] = 0.0
+    return S
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_system_rays(ctx, orc, ort, seed):
+    rng = np.random.default_rng(1000 + seed)
+    S = random_system(rng, mirrors=seed % 3 == 1, conics=seed % 2 == 1)
+    K = S[:, 3].copy()
+    N = 2048
+    y0, x0 = rng.uniform(-9, 9, N), rng.uniform(-9, 9, N)
+    u0, v0 = rng.uniform(-0.12, 0.12, N), rng.uniform(-0.12, 0.12, N)
+    y0[:2] = 0.0; x0[:2] = 0.0; u0[0] = v0[0] = 0.0
+    xo, yo, ko, fo = orc.trace3d_batch(S[:, :3], y0, x0, u0, v0, K=K)
+    ctx.set_layout(S[:, :3], K)
+    xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+    assert np.array_equal(fs, fo)
+    assert n_bits_differ(xs, xo) == 0 and n_bits_differ(ys, yo) == 0 and n_bits_differ(ks, ko) == 0
+    xf, yf, kf, ff = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
+    assert np.array_equal(ff, fo)
+    assert np.array_equal(np.isnan(xf), np.isnan(xo)) and np.array_equal(np.isnan(yf), np.isnan(yo))
+    xl, yl, kl = orc.trace3d_ld_batch(S[:, :3], y0, x0, u0, v0, K=K)
+    with np.errstate(all="ignore"):
+        scale = np.maximum(np.nan_to_num(np.nanmax(np.abs(np.stack([xo, yo])), axis=(0, 1)), nan=1.0), 1.0)
+
+        def err(a, b):
+            return np.nan_to_num(np.nanmax(np.abs(a - b), axis=0), nan=0.0) / scale
+        cond = np.maximum(err(xo, xl), err(yo, yl))
+        e_true = np.maximum(err(xf, xl), err(yf, yl))
+        e_fast = np.maximum(err(xf, xo), err(yf, yo))
+    well = cond < 1e-13
+    assert e_fast[well].max(initial=0.0) < TOL
+    assert np.all(e_true <= TOL / 2 + 2 * cond)
+    ok = ((fo & ort.FLAG_MISS) == 0) & well & ~np.isnan(ko[2])
+    if ok.any():
+        # the reference's k is a line direction (sign not meaningful after mirrors): compare up to sign
+        s = np.sign(np.sum(kf[:, ok] * ko[:, ok], axis=0))
+        assert np.max(np.abs(kf[:, ok] * s - ko[:, ok])) < 1e-11
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_system_grid_mask(ctx, orc, ort, seed):
+    rng = np.random.default_rng(2000 + seed)
+    S = random_system(rng, mirrors=seed % 2 == 1, conics=True)
+    K = np.append(S[:, 3], 0.0)
+    ext = np.vstack([S[:, :3], [np.inf, 0.0, S[-1, 2]]])
+    ext[-2, 1] = rng.uniform(20.0, 80.0) * np.sign(S[-1, 2])
+    stop = int(rng.integers(1, ext.shape[0] - 1))
+    a_stop = rng.uniform(3.0, 8.0)
+    ys, xs = np.linspace(-10, 10, 61), np.linspace(0, 10, 37)
+    u = rng.uniform(-0.1, 0.1)
+    g = orc.grid_trace(ext, ys, xs, stop, a_stop, 0.25, u=u, v=0.0, K=K)
+    ctx.set_layout(ext, K)
+    for arith in (ort.STRICT, ort.FAST):
+        r = ctx.trace3d_grid([dict(u=u, v=0.0, h_prime=0.25)], ys, xs, stop, a_stop, arith=arith,
+                             want=("ex", "ey", "mask", "flags", "stats"))
+        assert np.array_equal(r["mask"][0], g["mask"]) and np.array_equal(r["flags"][0], g["flags"])
+        assert int(r["stats"]["n_kept"][0]) == g["n_kept"]
+        m = g["mask"].astype(bool)
+        if arith == ort.STRICT:
+            assert n_bits_differ(r["ex"][0], g["ex"]) == 0 and n_bits_differ(r["ey"][0], g["ey"]) == 0
+        elif m.any():
+            sc = max(np.abs(g["ex"][m]).max(), np.abs(g["ey"][m]).max(), 10.0)
+            assert np.abs(r["ex"][0][m] - g["ex"][m]).max() / sc < 1e-11
+            assert np.abs(r["ey"][0][m] - g["ey"][m]).max() / sc < 1e-11
