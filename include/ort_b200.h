@@ -177,6 +177,18 @@ int ort_trace3d_rays_opl(ort_ctx *ctx, int64_t N, const double *y0, const double
 int ort_trace2d_batch(ort_ctx *ctx, int64_t N, const double *y0, const double *U0, int aspheric,
                       double *y_out, double *U_out, double *ts_out, uint8_t *flags);
 
+/* ---- ray aiming on the device: N independent secant solves, one thread each, over the
+ *      2-D meridional tracer of the current layout.  Finds x (the entrance height y if vary_u = 0, the entrance
+ *      angle U if vary_u = 1) such that the ray's height at surface `stop` equals target[j].
+ *      mode 0 = the reference's iteration (src/RayTracing.jl:229-233, 282-286): fixed step eps = sqrt(eps()),
+ *               x -= f eps / (f(x + eps) - f) while |f| > atol;
+ *      mode 1 = root polish used for the edge rays (src/PupilSampling.jl:67-83 minimises |f| with Optim.BFGS; the
+ *               same root is found by a secant iteration with relative step until |f| <= 4e-16 scale or stagnation).
+ *      other[j] is the fixed coordinate (U if vary_u = 0, y if vary_u = 1).  iters (optional) returns the iteration
+ *      count, negative if the solve left the domain or did not converge. */
+int ort_aim2d(ort_ctx *ctx, int64_t N, const double *x_start, const double *other, const double *target,
+              int stop, int vary_u, int mode, double atol_or_scale, int aspheric, double *x_out, int32_t *iters);
+
 /* ---- paraxial y-nu trace of N rays through a k-row Lens [tau phi]: replaces
  *      raytrace(lens, y, w, a; clip) src/RayTracing.jl:127-143 (+ :55-69).  a may be NULL (no clip).
  *      y, w: final (y, nu) per ray (NaN if clipped); clip_idx: 1-based row where clipped, 0 if not;

@@ -22,7 +22,7 @@ SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
     "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
     "ort_set_layout", "ort_set_apertures",
-    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch",
+    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_seidel_candidates",
     "ort_seidel_candidates_dev", "ort_fp64_peak",
@@ -110,6 +110,7 @@ def load():
     L.ort_trace3d_rays.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
     L.ort_trace3d_rays_opl.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p, _dp]
     L.ort_trace2d_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
+    L.ort_aim2d.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp, _i32p]
     L.ort_paraxial_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
                                      _dp, _dp, _dp, _dp, _i32p, _dp, _dp]
     L.ort_paraxial_batch_dev.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
@@ -330,6 +331,19 @@ class Context:
         self._ck(self.L.ort_trace2d_batch(self.h, N, _p(y0), _p(U0), int(bool(aspheric)), _p(yo), _p(Uo),
                                           _p(ts), fl.ctypes.data_as(_u8p)))
         return yo, Uo, ts, fl
+
+    def aim2d(self, x_start, other, target, stop, vary_u=False, mode=1, tol=1.0, aspheric=False):
+        """N secant solves on the device (one thread each): x such that y_stop(x) == target.
+        mode 0: the reference's fixed-step iteration with |f| <= tol; mode 1: root polish, tol = scale."""
+        x_start, other, target = np.broadcast_arrays(_d(np.atleast_1d(x_start)), _d(np.atleast_1d(other)),
+                                                     _d(np.atleast_1d(target)))
+        x_start, other, target = _d(x_start), _d(other), _d(target)
+        N = len(x_start)
+        out = np.empty(N)
+        it = np.zeros(N, dtype=np.int32)
+        self._ck(self.L.ort_aim2d(self.h, N, _p(x_start), _p(other), _p(target), int(stop), int(bool(vary_u)), int(mode),
+                                  float(tol), int(bool(aspheric)), _p(out), it.ctypes.data_as(_i32p)))
+        return out, it
 
     # ---- paraxial / transfer matrix ------------------------------------------------------
     def paraxial_batch(self, tau, phi, y0, w0, a=None, clip=False, arith=STRICT, table=False):

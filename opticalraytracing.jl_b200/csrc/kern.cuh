@@ -79,6 +79,13 @@ struct Trace2dArgs {
     uint8_t* flags;
 };
 
+struct AimArgs {
+    long long N; int stop, vary_u, mode, aspheric;
+    double tol;
+    const double *x0, *other, *target;
+    double* x_out; int32_t* iters;
+};
+
 struct TransferArgs {
     long long N; int reverse;
     double E[4];                            // extend(M, tau, taup), column-major
@@ -106,5 +113,6 @@ cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st);
 cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
 cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st);
+cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
                              long long* dfma_per_launch);

@@ -8,6 +8,41 @@
 // asin / sin / atan are CUDA's double-precision libm (<= 2 ulp; Julia's own libm differs in the
 // last ulp too), so parity here is 1e-12 relative, not bit-exact.
 // ------------------------------------------------------------------------------------------
+// one iteration of the surface loop of src/RayTracing.jl:151-167; returns ts[i] (:160)
+__device__ __forceinline__ double trace2d_step(const SurfK& S, int aspheric, double& y, double& U, double& sprev,
+                                               unsigned& flags)
+{
+    const double tU = tan(U);
+    const double ti = SS(S.t, sprev);                        // ts[i] (:148, :161)
+    y = SA(y, SM(tU, ti));                                   // :152
+    const double Ks = aspheric ? S.K : 0.0;
+    double sg;
+    if (isfinite(S.R)) {                                     // sag :75-88
+        double beta = SS(S.R, SM(y, tU));
+        double y2 = SM(y, y);
+        double sec = SD(1.0, cos(U));
+        double D = SS(SM(beta, beta), SM(y2, SA(SM(sec, sec), Ks)));
+        if (D >= 0.0) sg = SA(SD(y2, SA(beta, SM(S.sgnR, SQ(D)))), 0.0);
+        else { if (D < 0.0) flags |= ORT_FLAG_MISS; sg = CUDART_NAN; }
+    } else sg = 0.0;
+    y = SA(y, SM(sg, tU));                                   // :158
+    sprev = sg;                                              // ts[i+1] -= s :161
+    double theta;
+    if (!aspheric) {                                         // asin(tilt(y, R))  :162, :101
+        double q = SD(y, S.R);
+        if (fabs(q) > 1.0) flags |= ORT_FLAG_DOMAIN;
+        theta = asin(q);
+    } else {                                                 // atan(tilt(y, R, K, p))  :98
+        double D2 = SS(SM(S.R, S.R), SM(SM(y, y), SA(1.0, Ks)));
+        if (D2 < 0.0) flags |= ORT_FLAG_DOMAIN;
+        theta = atan(SA(SD(SM(S.sgnR, y), SQ(D2)), 0.0));
+    }
+    const double sin_ip = SD(SM(S.n1, sin(SA(U, theta))), S.n2);   // :163
+    if (fabs(sin_ip) <= 1.0) U = SS(asin(sin_ip), theta);          // :164
+    else { if (fabs(sin_ip) > 1.0) flags |= ORT_FLAG_TIR; U = CUDART_NAN; }
+    return SA(ti, sg);                                       // ts[i] += s  :160
+}
+
 __global__ void __launch_bounds__(256)
 k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
 {
@@ -21,41 +56,62 @@ k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
     if (A.U_out) A.U_out[i] = U;
     const int nsurf = P.nsurf;
     for (int s = 0; s < nsurf; s++) {
-        const SurfK& S = P.s[s];
-        const double tU = tan(U);
-        const double ti = SS(S.t, sprev);                        // ts[i] (:148, :161)
-        y = SA(y, SM(tU, ti));                                   // :152
-        const double Ks = A.aspheric ? S.K : 0.0;
-        double sg;
-        if (isfinite(S.R)) {                                     // sag :75-88
-            double beta = SS(S.R, SM(y, tU));
-            double y2 = SM(y, y);
-            double sec = SD(1.0, cos(U));
-            double D = SS(SM(beta, beta), SM(y2, SA(SM(sec, sec), Ks)));
-            if (D >= 0.0) sg = SA(SD(y2, SA(beta, SM(S.sgnR, SQ(D)))), 0.0);
-            else { if (D < 0.0) flags |= ORT_FLAG_MISS; sg = CUDART_NAN; }
-        } else sg = 0.0;
-        y = SA(y, SM(sg, tU));                                   // :158
-        if (A.ts_out) A.ts_out[(size_t)s * N + i] = SA(ti, sg);  // ts[i] += s  :160
-        sprev = sg;                                              // ts[i+1] -= s :161
-        double theta;
-        if (!A.aspheric) {                                       // asin(tilt(y, R))  :162, :101
-            double q = SD(y, S.R);
-            if (fabs(q) > 1.0) flags |= ORT_FLAG_DOMAIN;
-            theta = asin(q);
-        } else {                                                 // atan(tilt(y, R, K, p))  :98
-            double D2 = SS(SM(S.R, S.R), SM(SM(y, y), SA(1.0, Ks)));
-            if (D2 < 0.0) flags |= ORT_FLAG_DOMAIN;
-            theta = atan(SA(SD(SM(S.sgnR, y), SQ(D2)), 0.0));
-        }
-        const double sin_ip = SD(SM(S.n1, sin(SA(U, theta))), S.n2);   // :163
-        if (fabs(sin_ip) <= 1.0) U = SS(asin(sin_ip), theta);          // :164
-        else { if (fabs(sin_ip) > 1.0) flags |= ORT_FLAG_TIR; U = CUDART_NAN; }
+        const double ts = trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags);
+        if (A.ts_out) A.ts_out[(size_t)s * N + i] = ts;
         if (A.y_out) A.y_out[(size_t)(s + 1) * N + i] = y;
         if (A.U_out) A.U_out[(size_t)(s + 1) * N + i] = U;
     }
     if (A.ts_out) A.ts_out[(size_t)nsurf * N + i] = SS(P.t_last, sprev);
     if (A.flags) A.flags[i] = (uint8_t)flags;
+}
+
+// ------------------------------------------------------------------------------------------
+// Ray aiming on the device: the secant loops of trace_marginal_ray / trace_chief_ray
+// (src/RayTracing.jl:223-240, 265-296; stop_loss :117-125) and of the edge-ray search
+// (src/PupilSampling.jl:67-83), one thread per solve, every function evaluation = a 2-D trace to the stop.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double aim_eval(const Presc& P, const AimArgs& A, double x, double other)
+{
+    double y = A.vary_u ? other : x, U = A.vary_u ? x : other, sprev = 0.0;
+    unsigned flags = 0;
+    for (int s = 0; s < A.stop; s++) trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags);
+    return y;
+}
+
+__global__ void __launch_bounds__(64)
+k_aim2d(const __grid_constant__ Presc P, AimArgs A)
+{
+    const long long j = (long long)blockIdx.x * 64 + threadIdx.x;
+    if (j >= A.N) return;
+    double x = A.x0[j];
+    const double other = A.other[j], tgt = A.target[j];
+    const double eps = 1.4901161193847656e-08;                 // sqrt(eps())  src/RayTracing.jl:1
+    int it = 0, status = 0;
+    if (A.mode == 0) {
+        double f = SS(aim_eval(P, A, x, other), tgt);
+        while (fabs(f) > A.tol) {                               // :229, :282
+            if (++it > 100 || !isfinite(f)) { status = -1; break; }
+            const double fe = SS(aim_eval(P, A, SA(x, eps), other), tgt);
+            x = SS(x, SD(SM(f, eps), SS(fe, f)));               // :231, :284
+            f = SS(aim_eval(P, A, x, other), tgt);
+        }
+    } else {
+        double f_prev = 0.0;
+        for (;; it++) {
+            if (it >= 60) break;
+            const double h = SM(eps, fmax(1.0, fabs(x)));
+            const double f = SS(aim_eval(P, A, x, other), tgt);
+            const double fh = SS(aim_eval(P, A, SA(x, h), other), tgt);
+            if (!isfinite(f)) { status = -1; break; }
+            bool done = fabs(f) <= SM(4e-16, A.tol);
+            if (it > 0) done = done || (fabs(f) >= fabs(f_prev) && fabs(f_prev) <= SM(1e-13, A.tol));
+            if (done) break;
+            x = SS(x, SD(SM(f, h), SS(fh, f)));
+            f_prev = f;
+        }
+    }
+    A.x_out[j] = x;
+    if (A.iters) A.iters[j] = status < 0 ? -(it + 1) : it;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,6 +360,13 @@ cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st)
     long long nb = (A.N + 255) / 256;
     if (nb > 148 * 32) nb = 148 * 32;
     k_transfer<<<(unsigned)nb, 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st)
+{
+    if (A.N == 0) return cudaSuccess;
+    k_aim2d<<<(unsigned)((A.N + 63) / 64), 64, 0, st>>>(P, A);
     return cudaGetLastError();
 }
 

@@ -547,6 +547,35 @@ int ort_trace2d_batch(ort_ctx* ctx, int64_t N, const double* y0, const double* U
     return ORT_OK;
 }
 
+int ort_aim2d(ort_ctx* ctx, int64_t N, const double* x_start, const double* other, const double* target, int stop,
+              int vary_u, int mode, double atol_or_scale, int aspheric, double* x_out, int32_t* iters)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "aim2d: call ort_set_layout first");
+    if (N < 0 || !x_start || !other || !target || !x_out) return fail(ctx, ORT_EINVAL, "aim2d: bad input");
+    if (stop < 1 || stop > ctx->presc.nsurf) return fail(ctx, ORT_EINVAL, "aim2d: stop = %d not in [1, %d]", stop, ctx->presc.nsurf);
+    if (mode != 0 && mode != 1) return fail(ctx, ORT_EINVAL, "aim2d: mode = %d", mode);
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N;
+    double *d0, *d1, *d2, *d3; int32_t* di = nullptr;
+    ENSURE(SL_IN0, n * 8, d0); ENSURE(SL_IN1, n * 8, d1); ENSURE(SL_IN2, n * 8, d2); ENSURE(SL_OUT0, n * 8, d3);
+    if (iters) ENSURE(SL_OUT1, n * 4, di);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d0, x_start, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d1, other, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, target, n * 8, cudaMemcpyHostToDevice, st));
+    AimArgs A; memset(&A, 0, sizeof A);
+    A.N = N; A.stop = stop; A.vary_u = vary_u ? 1 : 0; A.mode = mode; A.aspheric = aspheric ? 1 : 0; A.tol = atol_or_scale;
+    A.x0 = d0; A.other = d1; A.target = d2; A.x_out = d3; A.iters = di;
+    CK(launch_aim2d(ctx->presc, A, st));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(x_out, d3, n * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters, di, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
 static int lens_fill(ort_ctx* ctx, LensK& L, int k, const double* tau, const double* phi, const double* a, int clip)
 {
     if (k < 0 || k > ORT_MAX_LENS) return fail(ctx, ORT_EINVAL, "paraxial_batch: k = %d not in [0, %d]", k, ORT_MAX_LENS);

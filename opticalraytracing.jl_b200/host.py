@@ -390,6 +390,13 @@ def trace_marginal_ray(surfaces, system, atol=EPS, backend=None):
     stop = system.stop
     y = system.marginal.y[0]
     a_stop = system.a[stop - 1]
+    be = _be(backend)
+    if hasattr(be, "aim2d"):                       # the reference's secant loop (:229-233) in one launch
+        be.set_layout(layout.M3, layout.K)
+        out, it = be.aim2d([y], [0.0], [a_stop], stop, vary_u=False, mode=0, tol=atol, aspheric=layout.aspheric)
+        if it[0] < 0:
+            raise RuntimeError("trace_marginal_ray did not converge")
+        y = float(out[0])
     for _ in range(100):
         yo, Uo, ts, fl = _trace2d(layout, np.array([y, y + EPS]), np.zeros(2), layout.aspheric, backend)
         d = yo[stop, 0] - a_stop
@@ -424,6 +431,13 @@ def trace_chief_ray(surfaces, system, atol=EPS, backend=None):
     stop = rows - system.stop
     ybp = system.chief.y[-1]
     ubp = -system.chief.u[-1]
+    be = _be(backend)
+    if hasattr(be, "aim2d"):                       # the reference's secant loop on U (:282-286) in one launch
+        be.set_layout(rev.M3, rev.K)
+        out, it = be.aim2d([ubp], [ybp], [0.0], stop, vary_u=True, mode=0, tol=atol, aspheric=rev.aspheric)
+        if it[0] < 0:
+            raise RuntimeError("trace_chief_ray did not converge")
+        ubp = float(out[0])
     for _ in range(100):
         yo, Uo, ts, fl = _trace2d(rev, np.array([ybp, ybp]), np.array([ubp, ubp + EPS]), rev.aspheric, backend)
         ys = yo[stop, 0]
@@ -450,7 +464,14 @@ def aim_rays(surfaces, y_start, U, target, stop, scale, backend=None):
     UU = np.broadcast_to(np.asarray(U, dtype=np.float64), y.shape).copy()
     tgt = np.broadcast_to(np.asarray(target, dtype=np.float64), y.shape)
     m = len(y)
-    fx_prev = None
+    be = _be(backend)
+    if hasattr(be, "aim2d"):                       # the whole secant loop runs on the device: one launch
+        be.set_layout(layout.M3, layout.K)
+        out, it = be.aim2d(y, UU, tgt, stop, vary_u=False, mode=1, tol=scale, aspheric=layout.aspheric)
+        if np.any(it < 0):
+            raise RuntimeError("ray aiming left the domain")
+        return out
+    fx_prev = None                                 # injected test backends: same iteration, one batch per step
     for _ in range(60):
         h = EPS * np.maximum(1.0, np.abs(y))
         yo, _, _, _ = _trace2d(layout, np.concatenate([y, y + h]), np.concatenate([UU, UU]), layout.aspheric, backend)

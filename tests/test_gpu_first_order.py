@@ -143,3 +143,43 @@ def test_seidel_candidates(ctx, orc, ort):
     bad = RtnK[:2].copy(); bad[1, 1, -1] = 3.0
     o2 = ctx.seidel_candidates(bad, P["a"], P["h"])
     assert np.isnan(o2[1]).all() and not np.isnan(o2[0]).any()
+
+
+class _NoAim:
+    """proxy that hides aim2d so the host runs its own secant loop (one 2-ray batch per step)"""
+
+    def __init__(self, ctx):
+        self._c = ctx
+
+    def __getattr__(self, name):
+        if name == "aim2d":
+            raise AttributeError(name)
+        return getattr(self._c, name)
+
+
+@pytest.mark.parametrize("name", ["COOKE", "DOUBLE_GAUSS", "TESSAR", "SINGLET"])
+def test_device_aiming_equals_host_loop(ctx, orc, ort, name):
+    """f1: the secant loops of trace_marginal_ray / trace_chief_ray / trace_edge_rays run in one kernel launch and
+    reproduce the launch-per-step host iteration bit for bit; the aimed rays hit their targets (checked with the oracle)."""
+    P = getattr(ort.prescriptions, name)
+    S = P["surfaces"]
+    s = ort.solve(S, P["a"], P["h"], backend=ctx)
+    host = _NoAim(ctx)
+    rm_d, rm_h = ort.trace_marginal_ray(S, s, backend=ctx), ort.trace_marginal_ray(S, s, backend=host)
+    assert np.array_equal(rm_d.y, rm_h.y) and np.array_equal(rm_d.z, rm_h.z)
+    L = ort.Layout(S)
+    rc_d, rc_h = ort.trace_chief_ray(L, s, backend=ctx), ort.trace_chief_ray(L, s, backend=host)
+    assert np.array_equal(rc_d.y, rc_h.y) and np.array_equal(rc_d.u, rc_h.u)
+    a_stop = abs(s.a[s.stop - 1])
+    assert abs(rm_d.y[s.stop] - a_stop) < 1.5e-8 and abs(rc_d.y[s.stop]) < 1.5e-8          # test/runtests.jl:271-280
+    U = np.array([0.0, 0.5, 1.0]) * rc_d.u[0]
+    y_EP = abs(rm_d.y[0])
+    y1, y2 = y_EP - np.tan(U) * rc_d.z[0], -y_EP - np.tan(U) * rc_d.z[0]
+    e_d, e_h = ort.trace_edge_rays(S, y1, y2, U, s.stop, a_stop, backend=ctx), ort.trace_edge_rays(S, y1, y2, U, s.stop, a_stop, backend=host)
+    assert np.array_equal(e_d[0], e_h[0]) and np.array_equal(e_d[1], e_h[1])
+    for yy, uu, tgt in [(e_d[0][j], U[j], a_stop) for j in range(3)] + [(e_d[1][j], U[j], -a_stop) for j in range(3)]:
+        rt, _, _ = orc.trace2d(S, float(yy), float(uu))
+        assert abs(rt[s.stop, 0] - tgt) < 1e-12 * a_stop
+    l0 = ctx.launch_count()
+    ort.trace_edge_rays(S, y1, y2, U, s.stop, a_stop, backend=ctx)
+    assert ctx.launch_count() - l0 == 1                                                    # one launch for all 6 solves
