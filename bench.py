@@ -187,16 +187,31 @@ def _main(real_stdout):
     d_ex = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_ey = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_mask = torch.empty((nf, NN), dtype=torch.uint8, device=dev)
-    d_stats = torch.zeros((nf, SB), dtype=torch.uint8, device=dev)
-    d_gather = torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) if n > 1 else None
-    ptrs = dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats.data_ptr())
+    # statistics records are double-buffered so the all-gather of step k (NCCL's own stream) overlaps the
+    # trace of step k+1 (launching stream); a buffer is reused only after its gather has completed
+    d_stats2 = [torch.zeros((nf, SB), dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_gather2 = [torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) for _ in range(2)] if n > 1 else None
+    ptrs2 = [dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats2[b].data_ptr())
+             for b in range(2)]
     stream = torch.cuda.current_stream().cuda_stream
+    works = [None, None]
+    state = {"k": 0}
 
     def step():
-        ctx.trace3d_grid_dev(fields, d_ys.data_ptr(), NY, d_xs.data_ptr(), NX, p["stop"], p["a_stop"], ptrs,
+        b = state["k"] & 1
+        state["k"] += 1
+        if works[b] is not None:
+            works[b].wait()
+        ctx.trace3d_grid_dev(fields, d_ys.data_ptr(), NY, d_xs.data_ptr(), NX, p["stop"], p["a_stop"], ptrs2[b],
                              stream=stream, arith=arith, ys_per_field=True)
         if n > 1:   # the one exchange step of the path: all-gather of per-field statistics records
-            dist.all_gather_into_tensor(d_gather.view(-1), d_stats.view(-1))
+            works[b] = dist.all_gather_into_tensor(d_gather2[b].view(-1), d_stats2[b].view(-1), async_op=True)
+
+    def drain():
+        for b in range(2):
+            if works[b] is not None:
+                works[b].wait()
+                works[b] = None
 
     def barrier():
         if n > 1:
@@ -205,6 +220,7 @@ def _main(real_stdout):
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     ctx.profile_enable(True)
     sampler = ClockSampler(local_rank)
@@ -214,6 +230,7 @@ def _main(real_stdout):
     ev0.record()
     for _ in range(args.steps):
         step()
+    drain()
     ev1.record()
     barrier()
     sampler.stop_flag = True
@@ -231,6 +248,9 @@ def _main(real_stdout):
     value = rays_step * inter_ray / (ms_step * 1e-3)
 
     # statistics of the last step, merged across ranks in rank order (Chan) -- evidence, not timed
+    last = (state["k"] - 1) & 1
+    d_stats = d_stats2[last]
+    d_gather = d_gather2[last] if n > 1 else None
     stats = np.frombuffer((d_gather if n > 1 else d_stats.view(1, nf, SB)).cpu().numpy().tobytes(),
                           dtype=ort.STATS_DTYPE).reshape(n, nf)
     merged = [ort.merge_stats(stats[:, f]) for f in range(nf)]
