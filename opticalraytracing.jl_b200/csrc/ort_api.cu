@@ -434,7 +434,32 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * nys, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_xs, xs, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
     ort_stats hstats[ORT_MAX_FIELDS];
-    for (int f = 0; f < n_fields; f++) {
+    // Large sweeps: one launch sequence per field, so the D2H of field f overlaps the trace of field f+1.
+    // Small sweeps are launch-latency bound: all fields in ONE launch sequence (fields = grid dimension y).
+    const bool per_field = n_fields > 1 && tot > ((size_t)1 << 21);
+    if (!per_field) {
+        const int gxa = grid_dims(ctx, arith, opts->ext & 3, n_fields, NN);     // <= gx: partials slot is large enough
+        rc = grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full,
+                          opts->compact ? &comp : nullptr, d_stats, d_partials, d_tiles, gxa, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(hstats, d_stats, sizeof(ort_stats) * (size_t)n_fields, cudaMemcpyDeviceToHost, st));
+        if (opts->compact) CK(cudaStreamSynchronize(st));                        // counts needed for the copy sizes
+        const ort_grid_out& src = opts->compact ? comp : full;
+        if (out->mask) CK(cudaMemcpyAsync(out->mask, full.mask, tot, cudaMemcpyDeviceToHost, st));
+        if (out->flags) CK(cudaMemcpyAsync(out->flags, full.flags, tot, cudaMemcpyDeviceToHost, st));
+        for (int f = 0; f < n_fields; f++) {
+            const size_t o = (size_t)f * NN;
+            const size_t cnt = opts->compact ? (size_t)hstats[f].n_kept : (size_t)NN;
+            if (out->ex) CK(cudaMemcpyAsync(out->ex + o, src.ex + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->ey) CK(cudaMemcpyAsync(out->ey + o, src.ey + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->r) CK(cudaMemcpyAsync(out->r + o, src.r + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->theta) CK(cudaMemcpyAsync(out->theta + o, src.theta + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->wx) CK(cudaMemcpyAsync(out->wx + o, src.wx + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->wy) CK(cudaMemcpyAsync(out->wy + o, src.wy + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+            if (out->opd && (opts->ext & ORT_EXT_OPD)) CK(cudaMemcpyAsync(out->opd + o, src.opd + o, cnt * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int f = 0; per_field && f < n_fields; f++) {
         const size_t o = (size_t)f * NN;
         ort_grid_out ff = full, cc = comp;
 #define OFF(p) if (p) p += o

@@ -94,6 +94,33 @@ def main():
         out[f"candidates_{name}"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "rays_per_s": rays / ms * 1e3,
                                      "intersections_per_s_x7": rays * 7 / ms * 1e3, "tflops_nominal": rays * 513 / ms / 1e9,
                                      "fp64_frac": rays * 513 / ms / 1e9 / peak}
+    # ---- K7: first-order solve + Seidel sums per candidate
+    d_s = torch.empty((C, 16), dtype=torch.float64, device=dev)
+    Pc = ort.prescriptions.COOKE
+    d_Rs = torch.from_numpy(ort.prescriptions.perturbed_triplets(C)).to(dev)
+    ms, best = timed(ctx, lambda: ctx.seidel_candidates_dev(8, C, d_Rs.data_ptr(), Pc["a"], Pc["h"], d_s.data_ptr(), stream=st), reps=5, warm=2)
+    out["seidel_candidates"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "GBps": C * (8 * 4 * 8 + 128) / ms / 1e6}
+
+    # ---- config 1 (the reference's own CPU-runnable case): Cooke triplet, 64 x 64 pupil grid, 3 fields, spot RMS,
+    #      end to end through the public API (host prelude + ray aiming + sweep + compaction + D2H + mirror)
+    import time
+    ort.full_trace_fields(sysm.layout, sysm, [0.0, 0.7, 1.0], 64)
+    l0 = ctx.launch_count(); t0 = time.perf_counter()
+    for _ in range(20):
+        errs = ort.full_trace_fields(sysm.layout, sysm, [0.0, 0.7, 1.0], 64)
+    dt = (time.perf_counter() - t0) / 20
+    out["config1_full_trace_3_fields"] = {"ms": dt * 1e3, "launches_per_call": (ctx.launch_count() - l0) / 20,
+                                          "rays": 3 * 2048, "rms": [e.RMS for e in errs]}
+    try:
+        from oracle import prelude as pre
+        so = pre.solve(Pc["surfaces"], Pc["a"], Pc["h"])
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref = [pre.full_trace(so, H, 64) for H in (0.0, 0.7, 1.0)]
+        out["config1_cpu_oracle_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+    except Exception as e:      # the oracle is optional here
+        out["config1_cpu_oracle_ms"] = str(e)
+
     res = d_o.cpu().numpy()
     out["candidates_rms_range"] = [float(np.nanmin(res[:, 3])), float(np.nanmax(res[:, 3]))]
     print(json.dumps(out, indent=1))
