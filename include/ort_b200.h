@@ -234,6 +234,12 @@ int ort_seidel_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d
                               double h_prime, double lambda, const double *dn /* host */, double *d_out,
                               double *d_per_surface, void *stream);
 
+/* ---- multi-GPU combine (host arithmetic): Chan merge of per-shard records recs[n_shards][n_fields], folded in
+ *      shard (rank) order so every rank gets bit-identical results, and the reference's sigma of the mirrored spot
+ *      (src/PupilSampling.jl:140-146,169-173) from one record. */
+int    ort_merge_stats(const ort_stats *recs, int n_shards, int n_fields, ort_stats *out);
+double ort_rms_from_stats(const ort_stats *s);
+
 /* ---- measurement helper: register-resident DFMA-chain microbenchmark; the FP64 roofline
  *      denominator (MEASURED_PEAKS.json holds no FP64 figure).  Returns TFLOP/s (2 flop per DFMA). */
 int ort_fp64_peak(ort_ctx *ctx, double *tflops, double *ms);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_seidel_candidates",
-    "ort_seidel_candidates_dev", "ort_fp64_peak",
+    "ort_seidel_candidates_dev", "ort_merge_stats", "ort_rms_from_stats", "ort_fp64_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -127,6 +127,9 @@ def load():
     L.ort_seidel_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
     L.ort_seidel_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, _dp,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_merge_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ort_rms_from_stats.argtypes = [C.c_void_p]
+    L.ort_rms_from_stats.restype = C.c_double
     L.ort_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
     _lib = L
     return L
@@ -169,6 +172,22 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+def merge_stats_c(records):
+    """ort_merge_stats: records (n_shards, n_fields) structured array -> (n_fields,)"""
+    rec = np.ascontiguousarray(records, dtype=STATS_DTYPE)
+    ns, nf = rec.shape
+    out = np.zeros(nf, dtype=STATS_DTYPE)
+    rc = load().ort_merge_stats(rec.ctypes.data, ns, nf, out.ctypes.data)
+    if rc != ORT_OK:
+        raise OrtError(rc, "ort_merge_stats")
+    return out
+
+
+def rms_from_stats_c(rec):
+    r = np.ascontiguousarray(np.atleast_1d(rec), dtype=STATS_DTYPE)
+    return float(load().ort_rms_from_stats(r.ctypes.data))
 
 
 def make_fields(fields):

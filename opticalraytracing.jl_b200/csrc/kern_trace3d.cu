@@ -387,25 +387,55 @@ __global__ void __launch_bounds__(256) k_grid_finalize(const RawPart* partials, 
     }
 }
 
-// exclusive scan of the per-tile kept counts of one field (one CTA per field)
-__global__ void __launch_bounds__(1024) k_tile_scan(int* counts, unsigned ntiles)
+// Exclusive scan of the per-tile kept counts, two levels: every CTA scans one chunk of SCAN_CHUNK tiles
+// in place (coalesced, 8 tiles per thread, warp-shuffle scans) and publishes the chunk total; k_compact
+// adds the totals of the preceding chunks (<= a few dozen values).
+#define SCAN_CHUNK 2048
+__global__ void __launch_bounds__(256) k_tile_scan(int* counts, int* chunk_tot, unsigned ntiles, unsigned nchunks)
 {
-    __shared__ unsigned s_sum[1024];
-    int* c = counts + (size_t)blockIdx.x * ntiles;
-    const unsigned per = (ntiles + 1023) / 1024;
-    const unsigned lo = threadIdx.x * per, hi = min(lo + per, ntiles);
-    unsigned sum = 0;
-    for (unsigned j = lo; j < hi; j++) sum += (unsigned)c[j];
-    s_sum[threadIdx.x] = sum;
+    __shared__ int s_warp[8];
+    const unsigned f = blockIdx.y, chunk = blockIdx.x;
+    int* c = counts + (size_t)f * ntiles + (size_t)chunk * SCAN_CHUNK;
+    const unsigned n = min((unsigned)SCAN_CHUNK, ntiles - chunk * SCAN_CHUNK);
+    const unsigned base = threadIdx.x * 8;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = (base + j < n) ? c[base + j] : 0; sum += v[j]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {             // Hillis-Steele inclusive scan
-        unsigned v = (threadIdx.x >= d) ? s_sum[threadIdx.x - d] : 0;
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 8; w++) { if (w < warp) woff += s_warp[w]; tot += s_warp[w]; }
+    int run = woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { if (base + j < n) c[base + j] = run; run += v[j]; }
+    if (threadIdx.x == 0) chunk_tot[(size_t)f * nchunks + chunk] = tot;
+}
+
+// second level: exclusive scan of the chunk totals of one field (one CTA per field; <= 4096 chunks for 2^31 rays)
+__global__ void __launch_bounds__(256) k_chunk_scan(int* chunk_tot, unsigned nchunks)
+{
+    __shared__ int s_warp[8];
+    int* c = chunk_tot + (size_t)blockIdx.x * nchunks;
+    int carry = 0;
+    for (unsigned base0 = 0; base0 < nchunks; base0 += 256) {
+        const unsigned i = base0 + threadIdx.x;
+        const int v = (i < nchunks) ? c[i] : 0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        s_sum[threadIdx.x] += v;
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 8; w++) { if (w < warp) woff += s_warp[w]; tot += s_warp[w]; }
+        if (i < nchunks) c[i] = carry + woff + incl - v;
+        carry += tot;
         __syncthreads();
     }
-    unsigned run = s_sum[threadIdx.x] - sum;
-    for (unsigned j = lo; j < hi; j++) { unsigned v = (unsigned)c[j]; c[j] = (int)run; run += v; }
 }
 
 // order-preserving scatter of up to 7 arrays: one CTA per (tile, field)
@@ -422,6 +452,11 @@ __global__ void __launch_bounds__(ORT_TILE) k_compact(CompactArgs C)
     if (lane == 0) s_warp[warp] = __popc(ball);
     __syncthreads();
     int off = C.tile_offsets[(size_t)f * ntiles + tile];
+    {   // + scanned total of the preceding chunks of this field
+        const unsigned nchunks = (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK, mychunk = tile / SCAN_CHUNK;
+        const int* ct = C.tile_offsets + (size_t)gridDim.y * ntiles + (size_t)f * nchunks;
+        off += ct[mychunk];
+    }
     for (int w = 0; w < warp; w++) off += s_warp[w];
     off += __popc(ball & ((1u << lane) - 1u));
     if (m) {
@@ -620,7 +655,10 @@ cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fiel
 cudaError_t launch_compact(int* tile_counts, const CompactArgs& C, int n_fields, cudaStream_t st)
 {
     const unsigned ntiles = (C.NN + ORT_TILE - 1) / ORT_TILE;
-    k_tile_scan<<<n_fields, 1024, 0, st>>>(tile_counts, ntiles);
+    const unsigned nchunks = (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    // chunk totals live right behind the [n_fields][ntiles] counts (the API layer sizes the buffer for it)
+    k_tile_scan<<<dim3(nchunks, n_fields), 256, 0, st>>>(tile_counts, tile_counts + (size_t)n_fields * ntiles, ntiles, nchunks);
+    k_chunk_scan<<<n_fields, 256, 0, st>>>(tile_counts + (size_t)n_fields * ntiles, nchunks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_compact<<<dim3(ntiles, n_fields), ORT_TILE, 0, st>>>(C);

@@ -69,7 +69,9 @@ int ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
 {
     if (bytes == 0) bytes = 8;
     if (ctx->slot_bytes[id] < bytes) {
-        if (ctx->slot[id]) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaFree(ctx->slot[id]); }
+        // growth is rare: wait for EVERYTHING on the device (the slot may still be in use by work a *_dev call
+        // enqueued on a caller-owned stream) before releasing the old block
+        if (ctx->slot[id]) { cudaDeviceSynchronize(); cudaFree(ctx->slot[id]); }
         ctx->slot[id] = nullptr; ctx->slot_bytes[id] = 0;
         cudaError_t e = cudaMalloc(&ctx->slot[id], bytes);
         if (e != cudaSuccess) return fail(ctx, ORT_ENOMEM, "cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
@@ -339,7 +341,7 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
         double* dd[7] = {dst->ex, dst->ey, dst->r, dst->theta, dst->wx, dst->wy, A.opd ? dst->opd : nullptr};
         for (int a = 0; a < 7; a++) { C.src[a] = dd[a] ? src[a] : nullptr; C.dst[a] = dd[a]; }
         CK(launch_compact(d_tiles, C, n_fields, st));
-        ctx->launches += 2;
+        ctx->launches += 3;
     }
     return ORT_OK;
 }
@@ -384,7 +386,8 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     if (d_out->wy) ENSURE(SL_WY, tot * 8, full.wy);
     if (d_out->opd) ENSURE(SL_OPD, tot * 8, full.opd);
     if (!d_out->mask) ENSURE(SL_MASK, tot, full.mask);
-    int* d_tiles; ENSURE(SL_TILES, sizeof(int) * (size_t)((NN + ORT_TILE - 1) / ORT_TILE + 1) * n_fields, d_tiles);
+    const size_t tiles_per_field = (size_t)(NN + ORT_TILE - 1) / ORT_TILE, tile_stride = tiles_per_field + tiles_per_field / 2048 + 2;
+    int* d_tiles; ENSURE(SL_TILES, sizeof(int) * tile_stride * n_fields, d_tiles);
     return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full, d_out, d_stats,
                         d_partials, d_tiles, gx, st);
 }
@@ -421,7 +424,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     if (out->mask || opts->compact) ENSURE(SL_MASK, tot, full.mask);
     if (out->flags) ENSURE(SL_FLAGS, tot, full.flags);
     if (opts->compact) {
-        ENSURE(SL_TILES, sizeof(int) * (size_t)(ntiles + 1) * n_fields, d_tiles);
+        ENSURE(SL_TILES, sizeof(int) * ((size_t)ntiles + ntiles / 2048 + 2) * n_fields, d_tiles);
         if (out->ex) ENSURE(SL_CEX, tot * 8, comp.ex);
         if (out->ey) ENSURE(SL_CEY, tot * 8, comp.ey);
         if (out->r) ENSURE(SL_CR, tot * 8, comp.r);
@@ -468,7 +471,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
 #undef OFF
         rc = grid_enqueue(ctx, fields + f, 1, d_ys + (opts->ys_per_field ? (size_t)f * ny : 0), ny, d_xs, nx, stop, a_stop, opts, ff,
                           opts->compact ? &cc : nullptr, d_stats + f, d_partials + (size_t)f * gx,
-                          d_tiles ? d_tiles + (size_t)f * (ntiles + 1) : nullptr, gx, st);
+                          d_tiles ? d_tiles + (size_t)f * ((size_t)ntiles + ntiles / 2048 + 2) : nullptr, gx, st);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_field[f], st));
         CK(cudaStreamWaitEvent(cs, ctx->ev_field[f], 0));
@@ -806,6 +809,46 @@ int ort_seidel_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK,
     if (per_surface) CK(cudaMemcpyAsync(per_surface, d_per, np_, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORT_OK;
+}
+
+// Chan merge of per-shard statistics records in the given (rank) order: the combine step after the
+// all-gather of a row-sharded sweep.  Pure host arithmetic; recs is [n_shards][n_fields].
+int ort_merge_stats(const ort_stats* recs, int n_shards, int n_fields, ort_stats* out)
+{
+    if (!recs || !out || n_shards < 1 || n_fields < 1) return ORT_EINVAL;
+    for (int f = 0; f < n_fields; f++) {
+        ort_stats a; memset(&a, 0, sizeof a);
+        a.r_max = -INFINITY;
+        for (int r = 0; r < n_shards; r++) {
+            const ort_stats& b = recs[(size_t)r * n_fields + f];
+            a.n_miss += b.n_miss; a.n_tir += b.n_tir; a.n_domain += b.n_domain; a.n_clip += b.n_clip; a.n_vig += b.n_vig;
+            if (b.n_kept == 0) continue;
+            if (a.n_kept == 0) {
+                a.n_kept = b.n_kept; a.mean_x = b.mean_x; a.mean_y = b.mean_y; a.m2_x = b.m2_x; a.m2_y = b.m2_y;
+                a.r_max = b.r_max; a.mean_opd = b.mean_opd; a.m2_opd = b.m2_opd;
+                continue;
+            }
+            const double na = (double)a.n_kept, nb = (double)b.n_kept, n = na + nb, w = nb / n;
+            const double dx = b.mean_x - a.mean_x, dy = b.mean_y - a.mean_y, dd = b.mean_opd - a.mean_opd;
+            a.mean_x = a.mean_x + dx * w; a.m2_x = a.m2_x + b.m2_x + dx * dx * (na * w);
+            a.mean_y = a.mean_y + dy * w; a.m2_y = a.m2_y + b.m2_y + dy * dy * (na * w);
+            a.mean_opd = a.mean_opd + dd * w; a.m2_opd = a.m2_opd + b.m2_opd + dd * dd * (na * w);
+            a.n_kept += b.n_kept;
+            if (b.r_max > a.r_max) a.r_max = b.r_max;
+        }
+        out[f] = a;
+    }
+    return ORT_OK;
+}
+
+// sigma of the mirrored spot (src/PupilSampling.jl:140-141, 169-173) from one statistics record:
+// x -> [x; -x] has mean 0 and sum of squares 2 (M2x + n mean_x^2); y -> [y; y] doubles M2y.
+double ort_rms_from_stats(const ort_stats* s)
+{
+    if (!s || s->n_kept <= 0) return NAN;
+    const double n = (double)s->n_kept;
+    const double sxx = s->m2_x + n * s->mean_x * s->mean_x;
+    return sqrt((2.0 * sxx + 2.0 * s->m2_y) / (2.0 * n));
 }
 
 int ort_fp64_peak(ort_ctx* ctx, double* tflops, double* ms)

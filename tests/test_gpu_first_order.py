@@ -183,3 +183,42 @@ def test_device_aiming_equals_host_loop(ctx, orc, ort, name):
     l0 = ctx.launch_count()
     ort.trace_edge_rays(S, y1, y2, U, s.stop, a_stop, backend=ctx)
     assert ctx.launch_count() - l0 == 1                                                    # one launch for all 6 solves
+
+
+def test_c_abi_from_plain_c(ctx, ort, tmp_path):
+    """the boundary is a C ABI: examples/full_trace.c compiled with gcc, linked against libort_b200.so and run"""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "full_trace")
+    libdir = os.path.dirname(ort._lib.LIB_PATH)
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "full_trace.c"), "-o", exe, "-L", libdir, "-lort_b200", "-lm",
+                           "-Wl,-rpath," + libdir])
+    P = ort.prescriptions.COOKE
+    s = ort.solve(P["surfaces"], P["a"], P["h"], backend=ctx)
+    p = ort.host._full_trace_setup(s.layout, s, [0.7], 64, None, ctx)
+    args = [repr(float(v)) for v in (p["y1"][0], p["y2"][0], p["y_EP"], p["u"][0], p["h_prime"][0], p["focus"])]
+    out = subprocess.run([exe] + args, capture_output=True, text=True, check=True).stdout
+    kv = dict(item.split("=") for item in out.split())
+    e = ort.full_trace(s, 0.7)
+    assert int(kv["n_kept"]) == len(e.x) // 2
+    assert abs(float(kv["rms"]) - e.RMS) < 1e-12 * 25 and abs(float(kv["ex0"]) - e.x[1]) < 1e-12 * 25
+
+
+def test_merge_stats_c_equals_python(ctx, ort):
+    P = ort.prescriptions.COOKE
+    s = ort.solve(P["surfaces"], P["a"], P["h"], backend=ctx)
+    p = ort.host._full_trace_setup(s.layout, s, [0.0, 1.0], 64, None, ctx)
+    ctx.set_layout(p["ext"], p["K"])
+    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], 64) for j in range(2)])
+    xs = np.linspace(0, p["y_EP"], 32)
+    flds = [dict(u=float(p["u"][j]), h_prime=float(p["h_prime"][j])) for j in range(2)]
+    recs = np.stack([ctx.trace3d_grid(flds, ys[:, lo:hi], xs, p["stop"], p["a_stop"])["stats"]
+                     for lo, hi in (ort.distributed.shard_rows(64, r, 4) for r in range(4))])
+    mc = ort._lib.merge_stats_c(recs)
+    whole = ctx.trace3d_grid(flds, ys, xs, p["stop"], p["a_stop"])["stats"]
+    for f in range(2):
+        mp = ort.merge_stats(recs[:, f])
+        assert mc[f]["n_kept"] == mp["n_kept"] == whole[f]["n_kept"]
+        assert mc[f]["mean_y"] == mp["mean_y"] and mc[f]["m2_x"] == mp["m2_x"]
+        assert abs(ort._lib.rms_from_stats_c(mc[f:f + 1]) - ort.rms_from_stats(whole[f])) < 1e-13
