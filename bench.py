@@ -256,6 +256,7 @@ def _main(real_stdout):
     merged = [ort.merge_stats(stats[:, f]) for f in range(nf)]
     rms = [ort.rms_from_stats(m) for m in merged]
     kept = [int(m["n_kept"]) for m in merged]
+    n_strict = [int(m["n_strict"]) for m in merged]
 
     # ---- e2e: the C-ABI host-pointer call, pinned host buffers, H2D of the grid coordinates and
     #      D2H of spot diagram + mask + statistics inside the timed region.  Two output forms are
@@ -339,6 +340,7 @@ def _main(real_stdout):
             "l2": "outputs 1.43 GB per step > 126 MB L2 (rewritten every step); inputs are 70 KB of grid "
                   "coordinates, cache-resident by design",
             "spot_rms_mm": [round(x, 9) for x in rms], "kept_rays": kept,
+            "rays_retraced_strict": n_strict,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms,

@@ -103,6 +103,8 @@ typedef struct ort_stats {
     int64_t n_miss, n_tir, n_domain, n_clip;   /* rays carrying each flag */
     int64_t n_vig;            /* EXTENSION: rays clipped by a surface aperture */
     double  mean_opd, m2_opd; /* EXTENSION: mean and sum of squared deviations of out->opd over kept rays */
+    int64_t n_strict;         /* rays whose outputs come from the strict re-trace (all of them in ORT_ARITH_STRICT; in
+                                 ORT_ARITH_FAST the guard-band / miss / TIR rays) */
 } ort_stats;
 
 /* Output arrays of a grid sweep; any pointer may be NULL (= not wanted). */

@@ -61,6 +61,7 @@ struct OrtStats            # ort_stats
     n_vig::Int64
     mean_opd::Float64
     m2_opd::Float64
+    n_strict::Int64
 end
 
 struct OrtGridOut          # ort_grid_out
@@ -145,7 +146,7 @@ function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
     xs = collect(range(0.0, y_EP, div(k_rays, 2)))   # :122
     N = length(ys) * length(xs)
     εx = Vector{Float64}(undef, N); εy = similar(εx); r = similar(εx); θ = similar(εx)
-    stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+    stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
     opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0, 1.0))   # compact = 1: the reference's push! order
     GC.@preserve εx εy r θ stats begin
         out = Ref(OrtGridOut(pointer(εx), pointer(εy), pointer(r), pointer(θ), C_NULL, C_NULL, C_NULL,

@@ -54,15 +54,16 @@ class Stats(C.Structure):
     _fields_ = [("n_kept", C.c_int64), ("mean_x", C.c_double), ("mean_y", C.c_double),
                 ("m2_x", C.c_double), ("m2_y", C.c_double), ("r_max", C.c_double),
                 ("n_miss", C.c_int64), ("n_tir", C.c_int64), ("n_domain", C.c_int64),
-                ("n_clip", C.c_int64), ("n_vig", C.c_int64), ("mean_opd", C.c_double), ("m2_opd", C.c_double)]
+                ("n_clip", C.c_int64), ("n_vig", C.c_int64), ("mean_opd", C.c_double), ("m2_opd", C.c_double),
+                ("n_strict", C.c_int64)]
 
 
 STATS_DTYPE = np.dtype([("n_kept", "<i8"), ("mean_x", "<f8"), ("mean_y", "<f8"), ("m2_x", "<f8"),
                         ("m2_y", "<f8"), ("r_max", "<f8"), ("n_miss", "<i8"), ("n_tir", "<i8"),
                         ("n_domain", "<i8"), ("n_clip", "<i8"), ("n_vig", "<i8"), ("mean_opd", "<f8"),
-                        ("m2_opd", "<f8")])
+                        ("m2_opd", "<f8"), ("n_strict", "<i8")])
 STATS_BYTES = STATS_DTYPE.itemsize
-assert STATS_BYTES == C.sizeof(Stats) == 104
+assert STATS_BYTES == C.sizeof(Stats) == 112
 
 
 class GridOut(C.Structure):

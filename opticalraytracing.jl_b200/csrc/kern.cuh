@@ -7,7 +7,7 @@ struct RawPart {
     long long n;
     double s1x, s2x, s1y, s2y, rmax, cx, cy;
     double s1o, s2o, co;                    // EXTENSION: OPD moments about the shift co
-    int nmiss, ntir, ndom, nclip, nvig, pad_;
+    int nmiss, ntir, ndom, nclip, nvig, nstrict;
 };
 
 struct GridArgs {

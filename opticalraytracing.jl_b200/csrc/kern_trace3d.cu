@@ -142,6 +142,7 @@ struct RawAcc {
     int n, nflag_lo, nflag_hi;                  // counts; nflag_* pack (miss, tir) and (domain, clip) as 16+16 bits
     double s1x, s2x, s1y, s2y, rmax;            // rmax holds r (strict) or r^2 (fast)
     double s1o, s2o; int nvig;                  // EXTENSION: OPD moments, vignetted count
+    int nstrict;                                // rays that went through the strict re-trace
 };
 
 __device__ __forceinline__ void raw_add(RawPart& p, const RawPart& q)
@@ -149,7 +150,7 @@ __device__ __forceinline__ void raw_add(RawPart& p, const RawPart& q)
     p.n += q.n; p.s1x += q.s1x; p.s2x += q.s2x; p.s1y += q.s1y; p.s2y += q.s2y;
     p.rmax = fmax(p.rmax, q.rmax);
     p.nmiss += q.nmiss; p.ntir += q.ntir; p.ndom += q.ndom; p.nclip += q.nclip;
-    p.s1o += q.s1o; p.s2o += q.s2o; p.nvig += q.nvig;
+    p.s1o += q.s1o; p.s2o += q.s2o; p.nvig += q.nvig; p.nstrict += q.nstrict;
 }
 
 __device__ __forceinline__ void raw_warp_reduce(RawPart& p)
@@ -169,6 +170,7 @@ __device__ __forceinline__ void raw_warp_reduce(RawPart& p)
         p.s1o += __shfl_down_sync(0xffffffffu, p.s1o, d);
         p.s2o += __shfl_down_sync(0xffffffffu, p.s2o, d);
         p.nvig += __shfl_down_sync(0xffffffffu, p.nvig, d);
+        p.nstrict += __shfl_down_sync(0xffffffffu, p.nstrict, d);
     }
 }
 
@@ -243,6 +245,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         if (A.mask) A.mask[o] = (uint8_t)kept;
         if (A.flags) A.flags[o] = (uint8_t)flags;
         if (sv) {           // miss / TIR / domain flags can only come out of a strict trace
+            acc.nstrict++;
             acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
             acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0);
         }
@@ -276,7 +279,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
 
     RawAcc acc;
-    acc.n = acc.nflag_lo = acc.nflag_hi = acc.nvig = 0;
+    acc.n = acc.nflag_lo = acc.nflag_hi = acc.nvig = acc.nstrict = 0;
     acc.s1x = acc.s2x = acc.s1y = acc.s2y = acc.s1o = acc.s2o = 0.0; acc.rmax = -CUDART_INF;
 
     if (threadIdx.x == 0) {                      // common shift of this field: its centre ray
@@ -349,7 +352,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     }
     RawPart p;
     p.n = acc.n; p.s1x = acc.s1x; p.s2x = acc.s2x; p.s1y = acc.s1y; p.s2y = acc.s2y; p.rmax = acc.rmax;
-    p.cx = cx; p.cy = cy; p.co = co; p.s1o = acc.s1o; p.s2o = acc.s2o; p.nvig = acc.nvig; p.pad_ = 0;
+    p.cx = cx; p.cy = cy; p.co = co; p.s1o = acc.s1o; p.s2o = acc.s2o; p.nvig = acc.nvig; p.nstrict = acc.nstrict;
     p.nmiss = acc.nflag_lo & 0xFFFF; p.ntir = acc.nflag_lo >> 16; p.ndom = acc.nflag_hi & 0xFFFF; p.nclip = acc.nflag_hi >> 16;
     raw_block_reduce<ORT_TILE / 32>(p, s_part);
     if (threadIdx.x == 0) {
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(256) k_grid_finalize(const RawPart* partials, 
     const int f = blockIdx.x;
     RawPart p;
     p.n = 0; p.s1x = p.s2x = p.s1y = p.s2y = p.s1o = p.s2o = 0.0; p.rmax = -CUDART_INF; p.cx = p.cy = p.co = 0.0;
-    p.nmiss = p.ntir = p.ndom = p.nclip = p.nvig = p.pad_ = 0;
+    p.nmiss = p.ntir = p.ndom = p.nclip = p.nvig = p.nstrict = 0;
     for (int j = threadIdx.x; j < nparts; j += 256) raw_add(p, partials[(size_t)f * nparts + j]);
     raw_block_reduce<8>(p, s_part);
     if (threadIdx.x == 0) {
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(256) k_grid_finalize(const RawPart* partials, 
             s.mean_opd = p0.co + p.s1o / n;
             s.m2_opd = fmax(p.s2o - p.s1o * p.s1o / n, 0.0);
         } else { s.mean_x = s.mean_y = s.m2_x = s.m2_y = s.mean_opd = s.m2_opd = 0.0; s.r_max = -CUDART_INF; }
-        s.n_miss = p.nmiss; s.n_tir = p.ntir; s.n_domain = p.ndom; s.n_clip = p.nclip; s.n_vig = p.nvig;
+        s.n_miss = p.nmiss; s.n_tir = p.ntir; s.n_domain = p.ndom; s.n_clip = p.nclip; s.n_vig = p.nvig; s.n_strict = p.nstrict;
         stats[f] = s;
     }
 }

@@ -821,7 +821,7 @@ int ort_merge_stats(const ort_stats* recs, int n_shards, int n_fields, ort_stats
         a.r_max = -INFINITY;
         for (int r = 0; r < n_shards; r++) {
             const ort_stats& b = recs[(size_t)r * n_fields + f];
-            a.n_miss += b.n_miss; a.n_tir += b.n_tir; a.n_domain += b.n_domain; a.n_clip += b.n_clip; a.n_vig += b.n_vig;
+            a.n_miss += b.n_miss; a.n_tir += b.n_tir; a.n_domain += b.n_domain; a.n_clip += b.n_clip; a.n_vig += b.n_vig; a.n_strict += b.n_strict;
             if (b.n_kept == 0) continue;
             if (a.n_kept == 0) {
                 a.n_kept = b.n_kept; a.mean_x = b.mean_x; a.mean_y = b.mean_y; a.m2_x = b.m2_x; a.m2_y = b.m2_y;

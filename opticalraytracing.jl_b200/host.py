@@ -612,7 +612,7 @@ def merge_stats(records):
     out = np.zeros(1, dtype=_lib.STATS_DTYPE)[0]
     out["r_max"] = -np.inf
     for rec in records:
-        for k in ("n_miss", "n_tir", "n_domain", "n_clip", "n_vig"):
+        for k in ("n_miss", "n_tir", "n_domain", "n_clip", "n_vig", "n_strict"):
             out[k] += rec[k]
         nb = float(rec["n_kept"])
         if nb == 0:
