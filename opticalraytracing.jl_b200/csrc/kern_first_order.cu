@@ -158,25 +158,35 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
                 y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);   // :62
         }
 #pragma unroll
-        for (int j = 0; j < PX_RPT; j++) {
+        for (int j = 0; j < PX_RPT; j++)
             w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);       // :67
-            if (CLIP) {
-                // |y| >= a (1 - 2^-20) by high word, or NaN / negative a: do the exact test of :135
-                if ((__double2hiint(y[j]) & 0x7FFFFFFF) >= a_hi && ci[j] == 0) {
-                    if (SS(fabs(y[j]), a) > 1e-13) { ci[j] = row + 1; y[j] = CUDART_NAN; w[j] = CUDART_NAN; }
-                }
+        if (CLIP) {
+            // One integer pre-filter for the thread's 4 rays: only if some |y| >= a (1 - 2^-20) by high word (or is
+            // NaN) run the exact test of :135.  A clipped ray continues as (0, 0) -- finite, so it never re-enters
+            // the exact test -- and is written out as NaN (:136) at the end.
+            int mx = 0;
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++) mx = max(mx, __double2hiint(y[j]) & 0x7FFFFFFF);
+            if (mx >= a_hi) {
+#pragma unroll
+                for (int j = 0; j < PX_RPT; j++)
+                    if (ci[j] == 0 && SS(fabs(y[j]), a) > 1e-13) { ci[j] = row + 1; y[j] = 0.0; w[j] = 0.0; }
             }
-            if (TABLE && valid[j]) {                                 // rt[i+1,:] (NaN after the clip row, :136)
-                if (A.y_all) A.y_all[(size_t)(row + 1) * N + idx[j]] = y[j];
-                if (A.w_all) A.w_all[(size_t)(row + 1) * N + idx[j]] = w[j];
+        }
+        if (TABLE) {
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++) {
+                if (!valid[j]) continue;                             // rt[i+1,:] (NaN after the clip row, :136)
+                if (A.y_all) A.y_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : y[j];
+                if (A.w_all) A.w_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : w[j];
             }
         }
     }
 #pragma unroll
     for (int j = 0; j < PX_RPT; j++) {
         if (!valid[j]) continue;
-        if (A.y) __stcs(A.y + idx[j], y[j]);
-        if (A.w) __stcs(A.w + idx[j], w[j]);
+        if (A.y) __stcs(A.y + idx[j], ci[j] ? CUDART_NAN : y[j]);
+        if (A.w) __stcs(A.w + idx[j], ci[j] ? CUDART_NAN : w[j]);
         if (A.clip_idx) A.clip_idx[idx[j]] = ci[j];
     }
 }

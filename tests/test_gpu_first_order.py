@@ -222,3 +222,15 @@ def test_merge_stats_c_equals_python(ctx, ort):
         assert mc[f]["n_kept"] == mp["n_kept"] == whole[f]["n_kept"]
         assert mc[f]["mean_y"] == mp["mean_y"] and mc[f]["m2_x"] == mp["m2_x"]
         assert abs(ort._lib.rms_from_stats_c(mc[f:f + 1]) - ort.rms_from_stats(whole[f])) < 1e-13
+
+
+def test_tsa_fan_on_gpu(ctx, orc, pre, ort):
+    """a15: TSA (src/SeidelAberrations.jl:116-135) = one batch of the 2-D kernel; vs the oracle prelude and the
+    reference's SA-fit check (test/runtests.jl:277-278)"""
+    P = ort.prescriptions.COOKE
+    s = ort.solve(P["surfaces"], P["a"], P["h"], backend=ctx)
+    so = pre.solve(P["surfaces"], P["a"], P["h"])
+    y, e = ort.TSA(P["surfaces"], s, backend=ctx)
+    yo, eo = pre.tsa(P["surfaces"], so)
+    assert np.max(np.abs(y - yo)) < 1e-12 * 15 and np.max(np.abs(e - eo)) < 1e-12 * 15
+    assert abs(ort.SA(y, e, 9)[0] / -0.186575 - 1) < 0.05

@@ -121,6 +121,35 @@ def main():
     except Exception as e:      # the oracle is optional here
         out["config1_cpu_oracle_ms"] = str(e)
 
+    # ---- config 3 (BASELINE): double-Gauss 1e9-ray dense pupil sweep, one field, on ONE GPU: statistics only
+    #      (0 B/ray of output) and with the spot diagram + mask (17 B/ray = 17 GB)
+    if len(sys.argv) > 3 and sys.argv[3] == "config3":
+        torch.cuda.empty_cache()
+        Pd = ort.prescriptions.DOUBLE_GAUSS
+        sd = ort.solve(Pd["surfaces"], Pd["a"], Pd["h"])
+        pd_ = ort.host._full_trace_setup(sd.layout, sd, [0.7], 64, None, ctx)
+        ctx.set_layout(pd_["ext"], pd_["K"])
+        ny3, nx3 = 44722, 22361
+        ys3 = torch.from_numpy(np.linspace(pd_["y1"][0], pd_["y2"][0], ny3)).to(dev)
+        xs3 = torch.from_numpy(np.linspace(0.0, pd_["y_EP"], nx3)).to(dev)
+        st3 = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
+        fld3 = dict(u=float(pd_["u"][0]), h_prime=float(pd_["h_prime"][0]))
+        NN3 = ny3 * nx3
+        ms, best = timed(ctx, lambda: ctx.trace3d_grid_dev([fld3], ys3.data_ptr(), ny3, xs3.data_ptr(), nx3, pd_["stop"], pd_["a_stop"],
+                                                          dict(stats=st3.data_ptr()), stream=st), reps=3, warm=1)
+        rec = np.frombuffer(st3.cpu().numpy().tobytes(), dtype=ort.STATS_DTYPE)[0]
+        out["config3_1e9_rays_stats_only"] = {"rays": NN3, "ms": ms, "rays_per_s": NN3 / ms * 1e3, "intersections_per_s_x10": NN3 * 10 / ms * 1e3,
+                                              "fp64_frac": NN3 * 723 / ms / 1e9 / peak, "kept": int(rec["n_kept"]), "rms_mm": ort.rms_from_stats(rec),
+                                              "n_strict": int(rec["n_strict"])}
+        ex3 = torch.empty(NN3, dtype=torch.float64, device=dev); ey3 = torch.empty(NN3, dtype=torch.float64, device=dev)
+        mk3 = torch.empty(NN3, dtype=torch.uint8, device=dev)
+        ms, best = timed(ctx, lambda: ctx.trace3d_grid_dev([fld3], ys3.data_ptr(), ny3, xs3.data_ptr(), nx3, pd_["stop"], pd_["a_stop"],
+                                                          dict(ex=ex3.data_ptr(), ey=ey3.data_ptr(), mask=mk3.data_ptr(), stats=st3.data_ptr()),
+                                                          stream=st), reps=3, warm=1)
+        out["config3_1e9_rays_spot_and_mask"] = {"rays": NN3, "ms": ms, "rays_per_s": NN3 / ms * 1e3, "GBps": NN3 * 17 / ms / 1e6,
+                                                 "fp64_frac": NN3 * 723 / ms / 1e9 / peak, "mask_sum_equals_kept": int(mk3.sum()) == int(rec["n_kept"])}
+        del ex3, ey3, mk3
+
     res = d_o.cpu().numpy()
     out["candidates_rms_range"] = [float(np.nanmin(res[:, 3])), float(np.nanmax(res[:, 3]))]
     print(json.dumps(out, indent=1))
