@@ -121,6 +121,31 @@ def main():
     except Exception as e:      # the oracle is optional here
         out["config1_cpu_oracle_ms"] = str(e)
 
+    # ---- extension kernels: OPD accumulation (+ per-surface apertures) on the bench grid, one field
+    torch.cuda.empty_cache()
+    Pd = ort.prescriptions.DOUBLE_GAUSS
+    sd = ort.solve(Pd["surfaces"], Pd["a"], Pd["h"])
+    pe = ort.host._full_trace_setup(sd.layout, sd, [0.7], 64, None, ctx)
+    ctx.set_layout(pe["ext"], pe["K"])
+    ctx.set_apertures(np.append(Pd["a"], np.inf))
+    nyb, nxb = 5792, 2896
+    ysb = torch.from_numpy(np.linspace(pe["y1"][0], pe["y2"][0], nyb)).to(dev)
+    xsb = torch.from_numpy(np.linspace(0.0, pe["y_EP"], nxb)).to(dev)
+    stb = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
+    bufs = {k: torch.empty(nyb * nxb, dtype=torch.float64, device=dev) for k in ("ex", "ey", "opd")}
+    bufs["mask"] = torch.empty(nyb * nxb, dtype=torch.uint8, device=dev)
+    fldb = dict(u=float(pe["u"][0]), h_prime=float(pe["h_prime"][0]), opd_yc=float(pe["h_prime"][0]), opd_radius=float(pe["focus"] - sd.XP.t),
+                opl_ref=150.0)
+    pt = {k: v.data_ptr() for k, v in bufs.items()}; pt["stats"] = stb.data_ptr()
+    for name, ext in (("opd", ort.EXT_OPD), ("opd_vignette", ort.EXT_OPD | ort.EXT_VIGNETTE)):
+        ms, best = timed(ctx, lambda: ctx.trace3d_grid_dev([fldb], ysb.data_ptr(), nyb, xsb.data_ptr(), nxb, pe["stop"], pe["a_stop"], pt,
+                                                          stream=st, ext=ext, opd_scale=-1.0 / 587.5618e-6), reps=5, warm=2)
+        rec = np.frombuffer(stb.cpu().numpy().tobytes(), dtype=ort.STATS_DTYPE)[0]
+        out[f"grid_ext_{name}"] = {"rays": nyb * nxb, "ms": ms, "rays_per_s": nyb * nxb / ms * 1e3, "fp64_frac_of_723": nyb * nxb * 723 / ms / 1e9 / peak,
+                                   "kept": int(rec["n_kept"]), "n_vig": int(rec["n_vig"]), "rms_opd_waves": float(np.sqrt(rec["m2_opd"] / max(rec["n_kept"], 1)))}
+    ctx.set_apertures(None)
+    del bufs
+
     # ---- config 3 (BASELINE): double-Gauss 1e9-ray dense pupil sweep, one field, on ONE GPU: statistics only
     #      (0 B/ray of output) and with the spot diagram + mask (17 B/ray = 17 GB)
     if len(sys.argv) > 3 and sys.argv[3] == "config3":
