@@ -128,66 +128,92 @@ template <int ARITH, bool TABLE, bool CLIP>
 __global__ void __launch_bounds__(256)
 k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
 {
+    // Persistent CTAs, tile-strided, with a software prefetch: the loads of tile k+1 are issued before the
+    // 40-row arithmetic of tile k, so HBM latency hides behind the FP64 work instead of in front of it.
     const long long N = A.N;
-    const long long base = (long long)blockIdx.x * (256 * PX_RPT) + threadIdx.x;
-    double y[PX_RPT], w[PX_RPT];
-    int ci[PX_RPT];
-    long long idx[PX_RPT];
-    bool valid[PX_RPT];
+    const long long per = 256 * PX_RPT;
+    const long long ntiles = (N + per - 1) / per;
+    const int k = L.k;
+    double yn[PX_RPT], wn[PX_RPT];
+    long long tile = blockIdx.x;
+    if (tile < ntiles) {
 #pragma unroll
-    for (int j = 0; j < PX_RPT; j++) {
-        const long long i = base + (long long)j * 256;
-        valid[j] = i < N;
-        idx[j] = valid[j] ? i : N - 1;               // padded lanes redo the last ray: warp stays convergent
-        y[j] = __ldcs(A.y0 + idx[j]); w[j] = __ldcs(A.w0 + idx[j]);
-        ci[j] = 0;
-        if (TABLE && valid[j]) {
-            if (A.y_all) A.y_all[idx[j]] = y[j];
-            if (A.w_all) A.w_all[idx[j]] = w[j];
+        for (int j = 0; j < PX_RPT; j++) {
+            const long long i = min(tile * per + (long long)j * 256 + threadIdx.x, N - 1);
+            yn[j] = __ldcs(A.y0 + i); wn[j] = __ldcs(A.w0 + i);
         }
     }
-    const int k = L.k;
-    for (int row = 0; row < k; row++) {
-        const double tau = L.tau[row], phi = L.phi[row];
-        const bool fin = isfinite(tau);                  // uniform (:62)
-        const double a = CLIP ? L.a[row] : 0.0;
-        const int a_hi = CLIP ? (__double2hiint(a) - 1) : 0;
-        if (fin) {                                       // uniform branch, not a per-ray select
+    for (; tile < ntiles; tile += gridDim.x) {
+        double y[PX_RPT], w[PX_RPT];
+        int ci[PX_RPT];
+        long long idx[PX_RPT];
+        bool valid[PX_RPT];
 #pragma unroll
-            for (int j = 0; j < PX_RPT; j++)
-                y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);   // :62
+        for (int j = 0; j < PX_RPT; j++) {
+            const long long i = tile * per + (long long)j * 256 + threadIdx.x;
+            valid[j] = i < N;
+            idx[j] = valid[j] ? i : N - 1;           // padded lanes redo the last ray: warp stays convergent
+            y[j] = yn[j]; w[j] = wn[j];
+            ci[j] = 0;
         }
+        const long long nxt = tile + gridDim.x;
+        if (nxt < ntiles) {                          // prefetch the next tile of this CTA
 #pragma unroll
-        for (int j = 0; j < PX_RPT; j++)
-            w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);       // :67
-        if (CLIP) {
-            // One integer pre-filter for the thread's 4 rays: only if some |y| >= a (1 - 2^-20) by high word (or is
-            // NaN) run the exact test of :135.  A clipped ray continues as (0, 0) -- finite, so it never re-enters
-            // the exact test -- and is written out as NaN (:136) at the end.
-            int mx = 0;
-#pragma unroll
-            for (int j = 0; j < PX_RPT; j++) mx = max(mx, __double2hiint(y[j]) & 0x7FFFFFFF);
-            if (mx >= a_hi) {
-#pragma unroll
-                for (int j = 0; j < PX_RPT; j++)
-                    if (ci[j] == 0 && SS(fabs(y[j]), a) > 1e-13) { ci[j] = row + 1; y[j] = 0.0; w[j] = 0.0; }
+            for (int j = 0; j < PX_RPT; j++) {
+                const long long i = min(nxt * per + (long long)j * 256 + threadIdx.x, N - 1);
+                yn[j] = __ldcs(A.y0 + i); wn[j] = __ldcs(A.w0 + i);
             }
         }
         if (TABLE) {
 #pragma unroll
             for (int j = 0; j < PX_RPT; j++) {
-                if (!valid[j]) continue;                             // rt[i+1,:] (NaN after the clip row, :136)
-                if (A.y_all) A.y_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : y[j];
-                if (A.w_all) A.w_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : w[j];
+                if (!valid[j]) continue;
+                if (A.y_all) A.y_all[idx[j]] = y[j];
+                if (A.w_all) A.w_all[idx[j]] = w[j];
             }
         }
-    }
+        for (int row = 0; row < k; row++) {
+            const double tau = L.tau[row], phi = L.phi[row];
+            const bool fin = isfinite(tau);                  // uniform (:62)
+            const double a = CLIP ? L.a[row] : 0.0;
+            const int a_hi = CLIP ? (__double2hiint(a) - 1) : 0;
+            if (fin) {                                       // uniform branch, not a per-ray select
 #pragma unroll
-    for (int j = 0; j < PX_RPT; j++) {
-        if (!valid[j]) continue;
-        if (A.y) __stcs(A.y + idx[j], ci[j] ? CUDART_NAN : y[j]);
-        if (A.w) __stcs(A.w + idx[j], ci[j] ? CUDART_NAN : w[j]);
-        if (A.clip_idx) A.clip_idx[idx[j]] = ci[j];
+                for (int j = 0; j < PX_RPT; j++)
+                    y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);   // :62
+            }
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++)
+                w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);       // :67
+            if (CLIP) {
+                // One integer pre-filter for the thread's 4 rays: only if some |y| >= a (1 - 2^-20) by high word (or
+                // is NaN) run the exact test of :135.  A clipped ray continues as (0, 0) -- finite, so it never
+                // re-enters the exact test -- and is written out as NaN (:136) at the end.
+                int mx = 0;
+#pragma unroll
+                for (int j = 0; j < PX_RPT; j++) mx = max(mx, __double2hiint(y[j]) & 0x7FFFFFFF);
+                if (mx >= a_hi) {
+#pragma unroll
+                    for (int j = 0; j < PX_RPT; j++)
+                        if (ci[j] == 0 && SS(fabs(y[j]), a) > 1e-13) { ci[j] = row + 1; y[j] = 0.0; w[j] = 0.0; }
+                }
+            }
+            if (TABLE) {
+#pragma unroll
+                for (int j = 0; j < PX_RPT; j++) {
+                    if (!valid[j]) continue;                         // rt[i+1,:] (NaN after the clip row, :136)
+                    if (A.y_all) A.y_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : y[j];
+                    if (A.w_all) A.w_all[(size_t)(row + 1) * N + idx[j]] = ci[j] ? CUDART_NAN : w[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX_RPT; j++) {
+            if (!valid[j]) continue;
+            if (A.y) __stcs(A.y + idx[j], ci[j] ? CUDART_NAN : y[j]);
+            if (A.w) __stcs(A.w + idx[j], ci[j] ? CUDART_NAN : w[j]);
+            if (A.clip_idx) A.clip_idx[idx[j]] = ci[j];
+        }
     }
 }
 
@@ -348,8 +374,9 @@ cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st)
 {
     const long long per = 256 * PX_RPT;
-    const unsigned nb = (unsigned)((A.N + per - 1) / per);
-    if (nb == 0) return cudaSuccess;
+    const long long ntl = (A.N + per - 1) / per;
+    if (ntl == 0) return cudaSuccess;
+    const unsigned nb = (unsigned)(ntl < 148 * 8 ? ntl : 148 * 8);     // persistent: 8 CTAs of 256 threads per SM
     const bool table = A.y_all || A.w_all;
     const bool clip = L.clip != 0;
 #define PX_LAUNCH(AR, TB, CL) k_paraxial<AR, TB, CL><<<nb, 256, 0, st>>>(L, A)
