@@ -222,31 +222,43 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
 // src/TransferMatrix.jl:8-17.  Pure HBM streaming: 16 B in, 16 B out per ray, 128-bit accesses.
 // The reverse path restates the 2x2 partially pivoted LU that Julia's `\` performs.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 transfer_one(const TransferArgs& A, double2 v)
+{
+    const double a11 = A.E[0], a21 = A.E[1], a12 = A.E[2], a22 = A.E[3];
+    double2 o;
+    if (!A.reverse) {
+        o.x = SA(SM(a11, v.x), SM(a12, v.y));
+        o.y = SA(SM(a21, v.x), SM(a22, v.y));
+    } else if (a21 == 0.0) {
+        o.y = SD(v.y, a22); o.x = SD(SS(v.x, SM(a12, o.y)), a11);
+    } else if (a12 == 0.0) {
+        o.x = SD(v.x, a11); o.y = SD(SS(v.y, SM(a21, o.x)), a22);
+    } else {
+        double p11 = a11, p12 = a12, p21 = a21, p22 = a22, b1 = v.x, b2 = v.y;
+        if (fabs(a21) > fabs(a11)) { p11 = a21; p12 = a22; p21 = a11; p22 = a12; b1 = v.y; b2 = v.x; }
+        const double l = SD(p21, p11);
+        const double u22 = SS(p22, SM(l, p12));
+        const double y2 = SS(b2, SM(l, b1));
+        o.y = SD(y2, u22);
+        o.x = SD(SS(b1, SM(p12, o.y)), p11);
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
 {
+    // grid-stride, 4 independent 128-bit loads in flight per thread
     const long long stride = (long long)gridDim.x * 256;
-    const double a11 = A.E[0], a21 = A.E[1], a12 = A.E[2], a22 = A.E[3];
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < A.N; i += stride) {
-        const double2 v = __ldcs(A.v_in + i);
-        double2 o;
-        if (!A.reverse) {
-            o.x = SA(SM(a11, v.x), SM(a12, v.y));
-            o.y = SA(SM(a21, v.x), SM(a22, v.y));
-        } else if (a21 == 0.0) {
-            o.y = SD(v.y, a22); o.x = SD(SS(v.x, SM(a12, o.y)), a11);
-        } else if (a12 == 0.0) {
-            o.x = SD(v.x, a11); o.y = SD(SS(v.y, SM(a21, o.x)), a22);
-        } else {
-            double p11 = a11, p12 = a12, p21 = a21, p22 = a22, b1 = v.x, b2 = v.y;
-            if (fabs(a21) > fabs(a11)) { p11 = a21; p12 = a22; p21 = a11; p22 = a12; b1 = v.y; b2 = v.x; }
-            const double l = SD(p21, p11);
-            const double u22 = SS(p22, SM(l, p12));
-            const double y2 = SS(b2, SM(l, b1));
-            o.y = SD(y2, u22);
-            o.x = SD(SS(b1, SM(p12, o.y)), p11);
-        }
-        __stcs(A.v_out + i, o);
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < A.N; i += 4 * stride) {
+        const double2 v0 = __ldcs(A.v_in + i), v1 = __ldcs(A.v_in + i + stride);
+        const double2 v2 = __ldcs(A.v_in + i + 2 * stride), v3 = __ldcs(A.v_in + i + 3 * stride);
+        __stcs(A.v_out + i, transfer_one(A, v0));
+        __stcs(A.v_out + i + stride, transfer_one(A, v1));
+        __stcs(A.v_out + i + 2 * stride, transfer_one(A, v2));
+        __stcs(A.v_out + i + 3 * stride, transfer_one(A, v3));
     }
+    for (; i < A.N; i += stride) __stcs(A.v_out + i, transfer_one(A, __ldcs(A.v_in + i)));
 }
 
 // ------------------------------------------------------------------------------------------
