@@ -102,6 +102,11 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     memcpy(&bits, &thr1, 8);
     S.gr_thr = (int32_t)(bits >> 32);
     S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
+    {
+        const double eq = isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : INFINITY;   // |R| (1 - 2^-20)
+        int64_t eb; memcpy(&eb, &eq, 8);
+        S.eq_thr = (int32_t)(eb >> 32); S.pad2_ = 0;
+    }
     S.a = INFINITY; S.a2 = INFINITY;
 }
 
