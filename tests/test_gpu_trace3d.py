@@ -299,3 +299,46 @@ def test_wavefront_api(ctx, ort):
     rho = e.r[:n]
     c = np.linalg.lstsq(np.column_stack([rho ** 2, rho ** 4, rho ** 6, rho ** 8]), w.opd[:n], rcond=None)[0]
     assert abs(c[1] / (2 * s.marginal.u[-1] / 587.5618e-6 * (-0.186575) / 8) - 1) < 0.03
+
+
+def test_many_fields_one_call_equals_per_field_calls(ctx, ort, pre):
+    """fields are a grid dimension of the kernel: 11 fields (own aimed y-range each) in ONE call -- host-pointer path
+    (single launch sequence) and device-pointer path, with ordered compaction -- equal 11 single-field calls bit for bit"""
+    import torch
+    P = ort.prescriptions.DOUBLE_GAUSS
+    s = ort.solve(P["surfaces"], P["a"], P["h"], backend=ctx)
+    Hs = np.linspace(0.0, 1.0, 11)
+    p = ort.host._full_trace_setup(s.layout, s, Hs, 64, None, ctx)
+    ctx.set_layout(p["ext"], p["K"])
+    ny, nx = 53, 29                                   # ragged: 1537 rays per field, not a multiple of the 256-ray tile
+    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], ny) for j in range(11)])
+    xs = np.linspace(0.0, p["y_EP"], nx)
+    flds = [dict(u=float(p["u"][j]), h_prime=float(p["h_prime"][j])) for j in range(11)]
+    want = ("ex", "ey", "r", "theta", "mask", "flags", "stats")
+    for compact in (False, True):
+        allr = ctx.trace3d_grid(flds, ys, xs, p["stop"], p["a_stop"], compact=compact, want=want)
+        for j in range(11):
+            one = ctx.trace3d_grid([flds[j]], ys[j], xs, p["stop"], p["a_stop"], compact=compact, want=want)
+            n = int(one["stats"]["n_kept"][0]) if compact else ny * nx
+            assert allr["stats"][j].tobytes() == one["stats"][0].tobytes()
+            assert np.array_equal(allr["mask"][j], one["mask"][0]) and np.array_equal(allr["flags"][j], one["flags"][0])
+            for k in ("ex", "ey", "r", "theta"):
+                assert np.array_equal(allr[k][j][:n], one[k][0][:n], equal_nan=True), (k, j, compact)
+        # device-pointer path, all fields in one enqueue
+        dev = torch.device("cuda", 0)
+        NN = ny * nx
+        d = {k: torch.empty((11, NN), dtype=torch.float64, device=dev) for k in ("ex", "ey", "r", "theta")}
+        d["mask"] = torch.empty((11, NN), dtype=torch.uint8, device=dev)
+        st = torch.zeros((11, ort.STATS_BYTES), dtype=torch.uint8, device=dev)
+        d_ys, d_xs = torch.from_numpy(ys).to(dev), torch.from_numpy(xs).to(dev)
+        ptrs = {k: v.data_ptr() for k, v in d.items()}
+        ptrs["stats"] = st.data_ptr()
+        ctx.trace3d_grid_dev(flds, d_ys.data_ptr(), ny, d_xs.data_ptr(), nx, p["stop"], p["a_stop"], ptrs,
+                             stream=torch.cuda.current_stream().cuda_stream, compact=compact, ys_per_field=True)
+        torch.cuda.synchronize()
+        recs = np.frombuffer(st.cpu().numpy().tobytes(), dtype=ort.STATS_DTYPE)
+        for j in range(11):
+            n = int(recs[j]["n_kept"]) if compact else NN
+            assert recs[j].tobytes() == allr["stats"][j].tobytes()
+            assert np.array_equal(d["ex"][j][:n].cpu().numpy(), allr["ex"][j][:n], equal_nan=True)
+            assert np.array_equal(d["theta"][j][:n].cpu().numpy(), allr["theta"][j][:n], equal_nan=True)
