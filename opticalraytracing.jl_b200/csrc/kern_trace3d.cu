@@ -571,7 +571,7 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
 }
 
 template <int ARITH>
-__global__ void __launch_bounds__(ORT_TILE)
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? 3 : 2)
 k_candidates(CandArgs A)
 {
     __shared__ SurfK s_surf[ORT_MAX_ROWS - 1];
@@ -587,25 +587,44 @@ k_candidates(CandArgs A)
     __syncthreads();
     Acc acc; acc_zero(acc);
     const unsigned NN = (unsigned)A.ny * (unsigned)A.nx;
-    for (unsigned i = threadIdx.x; i < NN; i += ORT_TILE) {
-        const unsigned iy = i / (unsigned)A.nx, ix = i - iy * (unsigned)A.nx;
-        const double y0 = __ldg(A.ys + iy), x0 = __ldg(A.xs + ix);
-        Hit h; int amb = 0; double ri = 0.0, r2 = 0.0; bool clip;
-        if (ARITH == ORT_ARITH_FAST) {
-            { const double uu = A.u, vv = A.v; trace_fast<1, false>(s_surf, nsurf, A.stop, Rc[2 * rows], &y0, &x0, &uu, &vv, &h, &amb); }
-            r2 = fma(h.xs, h.xs, h.ys * h.ys);
-            amb |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);
-            clip = r2 > A.a_stop2;
+    constexpr int RPT = (ARITH == ORT_ARITH_FAST) ? 2 : 1;      // 2 rays per thread share the LDS of the prescription
+    const double n0 = Rc[2 * rows];
+    double K0[3] = {0.0, 0.0, 0.0};                             // collimated field: K = n0 normalize([v, u, 1]) once
+    if (ARITH == ORT_ARITH_FAST) {
+        const double inv = n0 * fast_rsqrt(fma(A.v, A.v, fma(A.u, A.u, 1.0)));
+        K0[0] = A.v * inv; K0[1] = A.u * inv; K0[2] = inv;
+    }
+    for (unsigned i0 = threadIdx.x; i0 < NN; i0 += ORT_TILE * RPT) {
+        double y0[RPT], x0[RPT], uu[RPT], vv[RPT];
+        bool valid[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            const unsigned i = i0 + j * ORT_TILE;
+            valid[j] = i < NN;
+            const unsigned ic = valid[j] ? i : NN - 1;
+            const unsigned iy = ic / (unsigned)A.nx, ix = ic - iy * (unsigned)A.nx;
+            y0[j] = __ldg(A.ys + iy); x0[j] = __ldg(A.xs + ix); uu[j] = A.u; vv[j] = A.v;
         }
-        if (ARITH == ORT_ARITH_STRICT || amb < 0) {
-            h = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, A.stop, y0, x0, A.u, A.v)
-                                            : trace_strict_cold<false>(s_surf, nsurf, A.stop, y0, x0, A.u, A.v);
-            ri = jl_hypot(h.xs, h.ys);
-            clip = ri > A.a_stop;
-            r2 = ri * ri;
+        Hit h[RPT]; int amb[RPT];
+        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT, false>(s_surf, nsurf, A.stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            double ri = 0.0, r2 = 0.0; bool clip = false;
+            if (ARITH == ORT_ARITH_FAST) {
+                r2 = fma(h[j].xs, h[j].xs, h[j].ys * h[j].ys);
+                amb[j] |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);
+                clip = r2 > A.a_stop2;
+            }
+            if (ARITH == ORT_ARITH_STRICT || amb[j] < 0) {
+                h[j] = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, A.stop, y0[j], x0[j], A.u, A.v)
+                                                   : trace_strict_cold<false>(s_surf, nsurf, A.stop, y0[j], x0[j], A.u, A.v);
+                ri = jl_hypot(h[j].xs, h[j].ys);
+                clip = ri > A.a_stop;
+                r2 = ri * ri;
+            }
+            const bool drop = clip || is_nan_bits(h[j].xf) || is_nan_bits(h[j].yf);
+            if (valid[j] && !drop) acc_add(acc, h[j].xf, h[j].yf - A.h_prime, r2);
         }
-        const bool drop = clip || is_nan_bits(h.xf) || is_nan_bits(h.yf);
-        if (!drop) acc_add(acc, h.xf, h.yf - A.h_prime, r2);
     }
     Part p = acc_to_part(acc, true);
     part_block_reduce<ORT_TILE / 32>(p, s_part);
