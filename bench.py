@@ -267,15 +267,17 @@ def _main(real_stdout):
     h_ex, h_ey = ort.PinnedArray((nf, NN)), ort.PinnedArray((nf, NN))
     h_mask = ort.PinnedArray((nf, NN), dtype=np.uint8)
     out = dict(ex=h_ex.array, ey=h_ey.array, mask=h_mask.array)
+    h_ys, h_xs = ort.PinnedArray(wl["ys"].shape), ort.PinnedArray(wl["xs"].shape)      # inputs come from pinned memory too
+    h_ys.array[...] = wl["ys"]; h_xs.array[...] = wl["xs"]
     e2e = {}
     for form, compact in (("full_grid", False), ("compacted", True)):
-        r = ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith, compact=compact,
+        r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], arith=arith, compact=compact,
                              want=("ex", "ey", "mask"), out=out)
         barrier()
         l1 = ctx.launch_count()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            r = ctx.trace3d_grid(fields, wl["ys"], wl["xs"], p["stop"], p["a_stop"], arith=arith, compact=compact,
+            r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], arith=arith, compact=compact,
                                  want=("ex", "ey", "mask"), out=out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
