@@ -222,6 +222,31 @@ int ort_trace3d_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *
                                const double *d_xs, int nx, int stop, double a_stop, int arith,
                                double *d_out, void *stream);
 
+/* ---- per-candidate prelude of full_trace: what src/PupilSampling.jl:85-108 does before the grid
+ *      loop, for C candidate prescriptions at once, one thread per candidate: first-order solve (src/RayTracing.jl
+ *      :208-221, :246-263, stop = argmin a ./ y), real chief ray traced backwards through the reversed prescription
+ *      (:265-296, the Layout branch :272-274), real marginal ray (:223-240), field angle U = |H| * Ubar and the two
+ *      edge rays (src/PupilSampling.jl:67-83; the roots the reference's BFGS-on-abs converges to, found by secant).
+ *      RtnK[C][4][rows] WITHOUT the image-plane row, shared apertures a[rows-1] (host), image height h_prime of
+ *      solve(surfaces, a, h_prime), relative field H, aspheric = the Layout{Aspheric} dispatch of the forward 2-D traces.
+ *      out[C][24] = y1, y2, y_EP, u = tan U, h' = u f, focus (BFD), stop, a_stop, EP_t, Ubar, f, status (0 = ok;
+ *      bit 0 chief / bit 1 marginal / bit 2 edge-ray aiming failed, 8 = unusable last row), marginal nu[end], U,
+ *      [14] = 1 when [16..23] hold the two edge rays (y1, y2 at x = 0) taken through the strict 3-D trace: keep, eps_x,
+ *      eps_y, r^2 each -- they sit exactly on the stop rim, i.e. always inside the guard band of the FAST clip test, so
+ *      the sweep reads them from here instead of serialising a strict re-trace in every CTA.
+ *      ort_trace3d_candidates_aimed consumes these records: every candidate is traced over ITS OWN aimed pupil grid
+ *      ys = range(y1, y2, ny), xs = range(0, y_EP, nx), with its own stop / a_stop / u / h' and the image plane appended
+ *      at its own focus (:111-114); out[C][4] as ort_trace3d_candidates (NaN for a candidate whose prelude failed). */
+#define ORT_AIM_NOUT 24
+int ort_aim_candidates(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *a, double h_prime,
+                       double H, int aspheric, double *out);
+int ort_aim_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a /* host */,
+                           double h_prime, double H, int aspheric, double *d_out, void *stream);
+int ort_trace3d_candidates_aimed(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *aim, int ny,
+                                 int nx, int arith, double *out);
+int ort_trace3d_candidates_aimed_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *d_aim,
+                                     int ny, int nx, int arith, double *d_out, void *stream);
+
 /* ---- candidate-batched first-order solve + Seidel sums: what the reference's optimize()
  *      evaluates per candidate (src/Optimization.jl:32-45): Lens(surfaces) src/RayTracing.jl:38-53, paraxial marginal
  *      and chief rays :208-221, :246-263, aberrations() src/SeidelAberrations.jl:6-53.  RtnK[C][4][rows] (K unused),

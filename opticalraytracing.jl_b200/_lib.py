@@ -16,6 +16,7 @@ MAX_ROWS, MAX_FIELDS, MAX_LENS = 64, 32, 128
 FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP, FLAG_VIGN = 1, 2, 4, 8, 16
 EXT_OPD, EXT_VIGNETTE = 1, 2
 STRICT, FAST = 0, 1
+AIM_NOUT = 24
 
 # every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
@@ -24,7 +25,8 @@ SYMBOLS = [
     "ort_set_layout", "ort_set_apertures",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
-    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_seidel_candidates",
+    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev",
+    "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_seidel_candidates",
     "ort_seidel_candidates_dev", "ort_merge_stats", "ort_rms_from_stats", "ort_fp64_peak",
 ]
 
@@ -128,6 +130,12 @@ def load():
     L.ort_seidel_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
     L.ort_seidel_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, _dp,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_aim_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
+    L.ort_aim_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p]
+    L.ort_trace3d_candidates_aimed.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]
+    L.ort_trace3d_candidates_aimed_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                   C.c_int, C.c_void_p, C.c_void_p]
     L.ort_merge_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.ort_rms_from_stats.argtypes = [C.c_void_p]
     L.ort_rms_from_stats.restype = C.c_double
@@ -427,6 +435,39 @@ class Context:
         self._ck(self.L.ort_seidel_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(lam), _p(dn_),
                                               _p(out), _p(per)))
         return (out, per) if per_surface else out
+
+    def aim_candidates(self, RtnK, a, h_prime, H, aspheric=False):
+        """per-candidate full_trace prelude -> (C, 24) records (see ort_b200.h: ort_aim_candidates)"""
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        assert four == 4
+        a = _d(a)
+        assert a.shape == (rows - 1,)
+        out = np.empty((Cn, AIM_NOUT), dtype=np.float64)
+        self._ck(self.L.ort_aim_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(H), int(bool(aspheric)),
+                                           _p(out)))
+        return out
+
+    def aim_candidates_dev(self, rows, Cn, d_RtnK, a, h_prime, H, d_out, aspheric=False, stream=0):
+        a = _d(a)
+        self._ck(self.L.ort_aim_candidates_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), _p(a), float(h_prime),
+                                               float(H), int(bool(aspheric)), C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def trace3d_candidates_aimed(self, RtnK, aim, ny, nx, arith=FAST):
+        """every candidate over its own aimed pupil grid -> (C, 4) = n_kept, mean_x, mean_y, RMS"""
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        aim = _d(aim)
+        assert four == 4 and aim.shape == (Cn, AIM_NOUT)
+        out = np.empty((Cn, 4), dtype=np.float64)
+        self._ck(self.L.ort_trace3d_candidates_aimed(self.h, rows, Cn, _p(RtnK), _p(aim), int(ny), int(nx), int(arith),
+                                                     _p(out)))
+        return out
+
+    def trace3d_candidates_aimed_dev(self, rows, Cn, d_RtnK, d_aim, ny, nx, d_out, arith=FAST, stream=0):
+        self._ck(self.L.ort_trace3d_candidates_aimed_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), C.c_void_p(d_aim),
+                                                         int(ny), int(nx), int(arith), C.c_void_p(d_out),
+                                                         C.c_void_p(stream)))
 
     def seidel_candidates_dev(self, rows, Cn, d_RtnK, a, h_prime, d_out, lam=587.5618e-6, dn=None, stream=0):
         a = _d(a)

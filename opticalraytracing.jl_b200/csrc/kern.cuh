@@ -49,6 +49,7 @@ struct CandArgs {
     const double* RtnK;
     const double *ys, *xs; int ny, nx;
     int stop; double a_stop, a_stop2, u, v, h_prime;
+    const double* aim;                      // NULL, or [C][ORT_AIM_NOUT]: per-candidate grid, stop, field, focus
     double* out;
 };
 
@@ -58,6 +59,15 @@ struct SeidelArgs {
     double h_prime, lambda;
     double a[ORT_MAX_ROWS], dn[ORT_MAX_ROWS];
     double* out; double* per;
+};
+
+struct AimCandArgs {
+    int rows; long long C;
+    const double* RtnK;
+    double a[ORT_MAX_ROWS];
+    double h_prime, H;
+    int aspheric;
+    double* out;                            // [C][ORT_AIM_NOUT]
 };
 
 struct LensK {                              // paraxial Lens rows in the constant bank
@@ -113,6 +123,8 @@ cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st);
 cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
 cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st);
+cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st);
+cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, cudaStream_t st);
 cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
                              long long* dfma_per_launch);

@@ -9,7 +9,8 @@
 // last ulp too), so parity here is 1e-12 relative, not bit-exact.
 // ------------------------------------------------------------------------------------------
 // one iteration of the surface loop of src/RayTracing.jl:151-167; returns ts[i] (:160)
-__device__ __forceinline__ double trace2d_step(const SurfK& S, int aspheric, double& y, double& U, double& sprev,
+template <class SurfT>
+__device__ __forceinline__ double trace2d_step(const SurfT& S, int aspheric, double& y, double& U, double& sprev,
                                                unsigned& flags)
 {
     const double tU = tan(U);
@@ -28,7 +29,7 @@ __device__ __forceinline__ double trace2d_step(const SurfK& S, int aspheric, dou
     y = SA(y, SM(sg, tU));                                   // :158
     sprev = sg;                                              // ts[i+1] -= s :161
     double theta;
-    if (!aspheric) {                                         // asin(tilt(y, R))  :162, :101
+    if (Ks == 0.0) {                                         // iszero(Ks) && p === zero, per surface: asin(tilt(y, R))  :162, :101
         double q = SD(y, S.R);
         if (fabs(q) > 1.0) flags |= ORT_FLAG_DOMAIN;
         theta = asin(q);
@@ -352,6 +353,147 @@ __global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelAr
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-candidate prelude of full_trace (src/PupilSampling.jl:85-108): first-order solve
+// (src/RayTracing.jl:208-221, 246-263), real chief ray traced backwards through the reversed prescription
+// (:265-296), real marginal ray (:223-240), edge rays (src/PupilSampling.jl:67-83; the two roots of the
+// reference's BFGS-on-abs, by secant).  One thread per candidate prescription; every function evaluation is
+// a 2-D meridional trace with the surface rows read straight from the candidate's RtnK block.
+// ------------------------------------------------------------------------------------------
+struct Surf2 { double R, K, t, n1, n2, sgnR; };
+struct CandView { const double *R, *t, *n, *K; int rows; double bfd; };
+
+template <bool REV>
+__device__ __forceinline__ Surf2 cand_surf(const CandView& V, int j)
+{
+    Surf2 S;
+    if (!REV) { S.R = V.R[j + 1]; S.K = V.K[j + 1]; S.t = V.t[j]; S.n1 = V.n[j]; S.n2 = V.n[j + 1]; }
+    else {      // rev_R = -[Inf; R[end:-1:2]], rev_t = t[end:-1:1] with rev_t[1] = BFD, reverse(K) (:267-274)
+        const int r = V.rows - 1 - j;
+        S.R = -V.R[r]; S.K = V.K[r - 1]; S.t = (j == 0) ? V.bfd : V.t[r]; S.n1 = V.n[r]; S.n2 = V.n[r - 1];
+    }
+    S.sgnR = (S.R < 0.0) ? -1.0 : ((S.R > 0.0) ? 1.0 : S.R);
+    return S;
+}
+
+template <bool REV>
+__device__ __noinline__ double cand_height(const CandView& V, int upto, int aspheric, double y, double U)
+{
+    double sprev = 0.0; unsigned fl = 0;
+    for (int j = 0; j < upto; j++) { const Surf2 S = cand_surf<REV>(V, j); trace2d_step(S, aspheric, y, U, sprev, fl); }
+    return y;
+}
+
+// the reference's secant loop (:229-233, :282-286): x <- x - f eps / (f(x + eps) - f), until |f| <= tol
+template <bool REV, bool VARY_U>
+__device__ __forceinline__ bool cand_secant0(const CandView& V, int upto, int aspheric, double& x, double other,
+                                             double tgt, double tol)
+{
+    const double eps = 1.4901161193847656e-08;
+    double f = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, x) : cand_height<REV>(V, upto, aspheric, x, other), tgt);
+    int it = 0;
+    while (fabs(f) > tol) {
+        if (++it > 100 || !isfinite(f)) return false;
+        const double xe = SA(x, eps);
+        const double fe = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, xe) : cand_height<REV>(V, upto, aspheric, xe, other), tgt);
+        x = SS(x, SD(SM(f, eps), SS(fe, f)));
+        f = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, x) : cand_height<REV>(V, upto, aspheric, x, other), tgt);
+    }
+    return isfinite(f);
+}
+
+// root polish of the edge rays (same iteration as k_aim2d mode 1)
+__device__ __forceinline__ bool cand_polish(const CandView& V, int upto, int aspheric, double& x, double U, double tgt,
+                                            double scale)
+{
+    const double eps = 1.4901161193847656e-08;
+    double f_prev = 0.0;
+    for (int it = 0; it < 60; it++) {
+        const double h = SM(eps, fmax(1.0, fabs(x)));
+        const double f = SS(cand_height<false>(V, upto, aspheric, x, U), tgt);
+        const double fh = SS(cand_height<false>(V, upto, aspheric, SA(x, h), U), tgt);
+        if (!isfinite(f)) return false;
+        bool done = fabs(f) <= SM(4e-16, scale);
+        if (it > 0) done = done || (fabs(f) >= fabs(f_prev) && fabs(f_prev) <= SM(1e-13, scale));
+        if (done) break;
+        x = SS(x, SD(SM(f, h), SS(fh, f)));
+        f_prev = f;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ AimCandArgs A)
+{
+    const long long c = (long long)blockIdx.x * 64 + threadIdx.x;
+    if (c >= A.C) return;
+    const int rows = A.rows, k = rows - 1;
+    CandView V;
+    V.R = A.RtnK + (size_t)c * 4 * rows; V.t = V.R + rows; V.n = V.t + rows; V.K = V.n + rows; V.rows = rows; V.bfd = 0.0;
+    double* out = A.out + (size_t)c * ORT_AIM_NOUT;
+    for (int j = 0; j < ORT_AIM_NOUT; j++) out[j] = CUDART_NAN;
+    const double tl = V.t[rows - 1];
+    if (!(tl == 0.0 || !isfinite(tl))) { out[11] = 8.0; return; }     // Lens() would keep the last row
+    // ---- first-order solve: both fundamental rays (:209, :252), stop = argmin a ./ y (:215-216)
+    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
+    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0, yfirst = 0.0, zsum = 0.0;
+    int stop = 1;
+    for (int i = 0; i < k; i++) {
+        double ti = V.t[i];
+        if (i == 0 && !isfinite(ti)) ti = 0.0;
+        const double tau = SD(ti, V.n[i]);
+        const double phi = SD(SS(V.n[i + 1], V.n[i]), V.R[i + 1]);
+        const double tz = SM(tau, V.n[i]);                            // t = tau .* n, z = cumsum(t)  (Types.jl:41-46)
+        zsum = (i == 0) ? tz : SA(zsum, tz);
+        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
+        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        const double v = SD(A.a[i], y1);
+        if (i == 0) yfirst = y1;
+        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }
+    }
+    const double f = -SD(1.0, w1);
+    const double nlast = V.n[rows - 1];
+    const double ymk = SM(y1, s), numk = SM(w1, s);                   // marginal (y, nu) after the last surface
+    const double bfd = SS(SA(zsum, SD(-ymk, SD(numk, nlast))), zsum); // marginal.z[end] - marginal.z[end-1]  (Types.jl:44-46)
+    const double nub = SD(SM(-numk, A.h_prime), SM(yfirst, s));       // :256
+    const double nuck = SM(nub, SS(w2, SD(SM(numk, ys2), SM(ys1, s))));   // chief nu after the last surface :258
+    V.bfd = bfd;
+    const double a_stop_signed = A.a[stop - 1];
+    const double a_stop = fabs(a_stop_signed);
+    const double tol = 1.4901161193847656e-08;
+    int status = 0;
+    // ---- real chief ray, backwards (:265-296)
+    const double ybp = A.h_prime;
+    double ubp = -SD(nuck, nlast);
+    const int rstop = rows - stop;
+    if (!cand_secant0<true, true>(V, rstop, 1, ubp, ybp, 0.0, tol)) status |= 1;
+    double EP_t, Ubar;
+    {
+        double y = ybp, U = ubp, sprev = 0.0, csum = 0.0; unsigned fl = 0;
+        for (int j = 0; j < k; j++) {
+            const Surf2 S = cand_surf<true>(V, j);
+            const double ts = trace2d_step(S, 1, y, U, sprev, fl);
+            csum = (j == 0) ? ts : SA(csum, ts);                       // z = cumsum(ts)  (Types.jl:61-63)
+        }
+        const double ts_last = SS(V.t[0], sprev);
+        const double z1 = SS(SA(csum, ts_last), csum);                 // z[2] = ray.z[end] - ray.z[end-1]  :292
+        Ubar = -U;                                                     // u_bar[1] = -ray.u[end]  :289
+        EP_t = SA(SD(-y, tan(Ubar)), z1);                              // :293
+    }
+    // ---- real marginal ray (:223-240)
+    double ym = SM(1.0, s);
+    if (!cand_secant0<false, false>(V, stop, A.aspheric, ym, 0.0, a_stop_signed, tol)) status |= 2;
+    const double y_EP = fabs(ym);
+    // ---- field point and edge rays (src/PupilSampling.jl:92-100)
+    const double U = SM(fabs(A.H), Ubar);
+    const double u = tan(U);
+    double e1 = SS(y_EP, SM(u, EP_t)), e2 = SS(-y_EP, SM(u, EP_t));
+    if (!cand_polish(V, stop, A.aspheric, e1, U, a_stop, a_stop)) status |= 4;
+    if (!cand_polish(V, stop, A.aspheric, e2, U, -a_stop, a_stop)) status |= 4;
+    out[0] = e1; out[1] = e2; out[2] = y_EP; out[3] = u; out[4] = SM(u, f); out[5] = bfd;
+    out[6] = (double)stop; out[7] = a_stop; out[8] = EP_t; out[9] = Ubar; out[10] = f; out[11] = (double)status;
+    out[12] = numk; out[13] = U; out[14] = 0.0; out[15] = 0.0;     // 14..23: k_aim_edges
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 roofline denominator: 8 independent DFMA chains per thread, register resident.
 // ------------------------------------------------------------------------------------------
 #define PEAK_CHAINS 8
@@ -423,6 +565,13 @@ cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st)
 {
     if (A.C == 0) return cudaSuccess;
     k_seidel<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st)
+{
+    if (A.C == 0) return cudaSuccess;
+    k_aim_candidates<<<(unsigned)((A.C + 63) / 64), 64, 0, st>>>(A);
     return cudaGetLastError();
 }
 

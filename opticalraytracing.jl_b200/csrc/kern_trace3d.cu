@@ -570,70 +570,161 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.a = CUDART_INF; S.a2 = CUDART_INF;
 }
 
-template <int ARITH>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? 3 : 2)
+// AIMED: every candidate carries its own prelude record (k_aim_candidates): stop, stop radius, field slope,
+// image height, focus (the image plane [Inf 0 1] is appended here, t[end-1] = focus, src/PupilSampling.jl:111-114)
+// and its own aimed pupil grid ys = range(y1, y2, ny), xs = range(0, y_EP, nx) (:121-122).
+template <int ARITH, bool AIMED>
+__global__ void __launch_bounds__(ORT_TILE, 3)
 k_candidates(CandArgs A)
 {
-    __shared__ SurfK s_surf[ORT_MAX_ROWS - 1];
+    __shared__ SurfK s_surf[ORT_MAX_ROWS];
     __shared__ Part s_part[ORT_TILE / 32];
     const long long c = blockIdx.x;
-    const int rows = A.rows, nsurf = rows - 1;
+    const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
     const double* Rc = A.RtnK + (size_t)c * 4 * rows;
-    if (threadIdx.x < nsurf) {
+    const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
+    if (threadIdx.x < rows - 1) {
         const int i = threadIdx.x;
         derive_surface(s_surf[i], Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i],
                        Rc[2 * rows + i + 1]);
+    } else if (AIMED && threadIdx.x == rows - 1) {
+        derive_surface(s_surf[rows - 1], CUDART_INF, 0.0, rec[5], Rc[3 * rows - 1], 1.0);
     }
     __syncthreads();
+    // per-candidate scalars live in shared memory (the shared-grid variant reads them from the constant bank):
+    // re-read by LDS broadcast where used, so they cost no registers across the surface loop
+    __shared__ double s_par[10];
+    __shared__ int s_stop;
+    if (threadIdx.x == ORT_TILE - 1) {
+        if (AIMED) {
+            const int st = (int)rec[6];
+            const bool good = rec[11] == 0.0 && st >= 1 && st <= rows - 1;     // NaN record / failed prelude -> NaN result
+            s_stop = good ? st : 0;
+            s_par[0] = rec[0]; s_par[1] = rec[1]; s_par[2] = SD(SS(rec[1], rec[0]), (double)(A.ny - 1));
+            s_par[3] = rec[2]; s_par[4] = SD(rec[2], (double)(A.nx - 1));
+            s_par[5] = rec[7]; s_par[6] = rec[7] * rec[7]; s_par[7] = rec[3]; s_par[8] = rec[4];
+        } else {
+            s_stop = A.stop;
+            s_par[5] = A.a_stop; s_par[6] = A.a_stop2; s_par[7] = A.u; s_par[8] = A.h_prime;
+        }
+    }
+    __syncthreads();
+    const volatile double* par = s_par;
+    const int stop = s_stop;
+    const bool ok = stop > 0;
+#define CAND_PAR(i, shared_grid_value) (AIMED ? par[i] : (shared_grid_value))
     Acc acc; acc_zero(acc);
     const unsigned NN = (unsigned)A.ny * (unsigned)A.nx;
     constexpr int RPT = (ARITH == ORT_ARITH_FAST) ? 2 : 1;      // 2 rays per thread share the LDS of the prescription
     const double n0 = Rc[2 * rows];
     double K0[3] = {0.0, 0.0, 0.0};                             // collimated field: K = n0 normalize([v, u, 1]) once
     if (ARITH == ORT_ARITH_FAST) {
-        const double inv = n0 * fast_rsqrt(fma(A.v, A.v, fma(A.u, A.u, 1.0)));
-        K0[0] = A.v * inv; K0[1] = A.u * inv; K0[2] = inv;
+        const double fu = CAND_PAR(7, A.u);
+        const double inv = n0 * fast_rsqrt(fma(A.v, A.v, fma(fu, fu, 1.0)));
+        K0[0] = A.v * inv; K0[1] = fu * inv; K0[2] = inv;
     }
-    for (unsigned i0 = threadIdx.x; i0 < NN; i0 += ORT_TILE * RPT) {
+    // The two aimed edge rays (first / last grid row at x = 0) cross the stop exactly at its rim by construction
+    // (src/PupilSampling.jl:67-83): they always land in the guard band of the clip test.  Lanes 0 and 1 of warp 0 take
+    // them through the strict trace side by side up front; the fast loop skips them.
+    const unsigned edge_b = (unsigned)(A.ny - 1) * (unsigned)A.nx;
+    constexpr bool EDGE_FIRST = AIMED && ARITH == ORT_ARITH_FAST;
+    if (EDGE_FIRST && ok && threadIdx.x < 2) {
+        if (rec[14] == 1.0) {           // traced by k_aim_edges, one thread per edge ray across the whole population
+            const double* e = rec + 16 + 4 * threadIdx.x;
+            if (e[0] == 1.0) acc_add(acc, e[1], e[2], e[3]);
+        } else {                        // hand-made record without edge data
+            const double ye = threadIdx.x ? par[1] : par[0];
+            const Hit he = trace_strict_cold<false>(s_surf, nsurf, stop, ye, 0.0, par[7], A.v);
+            const double ri = jl_hypot(he.xs, he.ys);
+            if (!(ri > par[5] || is_nan_bits(he.xf) || is_nan_bits(he.yf))) acc_add(acc, he.xf, he.yf - par[8], ri * ri);
+        }
+    }
+    for (unsigned i0 = threadIdx.x; ok && i0 < NN; i0 += ORT_TILE * RPT) {
         double y0[RPT], x0[RPT], uu[RPT], vv[RPT];
         bool valid[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             const unsigned i = i0 + j * ORT_TILE;
-            valid[j] = i < NN;
-            const unsigned ic = valid[j] ? i : NN - 1;
+            valid[j] = i < NN && !(EDGE_FIRST && (i == 0 || i == edge_b));
+            const unsigned ic = i < NN ? i : NN - 1;
             const unsigned iy = ic / (unsigned)A.nx, ix = ic - iy * (unsigned)A.nx;
-            y0[j] = __ldg(A.ys + iy); x0[j] = __ldg(A.xs + ix); uu[j] = A.u; vv[j] = A.v;
+            if (AIMED) {        // range(a, b, n)[i] = a + i * step, last point exactly b
+                y0[j] = (iy == (unsigned)A.ny - 1) ? par[1] : SA(par[0], SM((double)iy, par[2]));
+                x0[j] = (ix == (unsigned)A.nx - 1) ? par[3] : SM((double)ix, par[4]);
+            } else { y0[j] = __ldg(A.ys + iy); x0[j] = __ldg(A.xs + ix); }
+            uu[j] = 0.0; vv[j] = A.v;                           // the fast path takes the direction from K0
         }
         Hit h[RPT]; int amb[RPT];
-        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT, false>(s_surf, nsurf, A.stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT, false>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             double ri = 0.0, r2 = 0.0; bool clip = false;
             if (ARITH == ORT_ARITH_FAST) {
+                const double a_stop2 = CAND_PAR(6, A.a_stop2);
                 r2 = fma(h[j].xs, h[j].xs, h[j].ys * h[j].ys);
-                amb[j] |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);
-                clip = r2 > A.a_stop2;
+                amb[j] |= tiny_vs_bit(r2 - a_stop2, a_stop2);
+                clip = r2 > a_stop2;
             }
-            if (ARITH == ORT_ARITH_STRICT || amb[j] < 0) {
-                h[j] = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, A.stop, y0[j], x0[j], A.u, A.v)
-                                                   : trace_strict_cold<false>(s_surf, nsurf, A.stop, y0[j], x0[j], A.u, A.v);
+            if (ARITH == ORT_ARITH_STRICT || (amb[j] < 0 && valid[j])) {
+                const double fu = CAND_PAR(7, A.u);
+                h[j] = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, stop, y0[j], x0[j], fu, A.v)
+                                                   : trace_strict_cold<false>(s_surf, nsurf, stop, y0[j], x0[j], fu, A.v);
                 ri = jl_hypot(h[j].xs, h[j].ys);
-                clip = ri > A.a_stop;
+                clip = ri > CAND_PAR(5, A.a_stop);
                 r2 = ri * ri;
             }
             const bool drop = clip || is_nan_bits(h[j].xf) || is_nan_bits(h[j].yf);
-            if (valid[j] && !drop) acc_add(acc, h[j].xf, h[j].yf - A.h_prime, r2);
+            if (valid[j] && !drop) acc_add(acc, h[j].xf, h[j].yf - CAND_PAR(8, A.h_prime), r2);
         }
     }
+#undef CAND_PAR
     Part p = acc_to_part(acc, true);
     part_block_reduce<ORT_TILE / 32>(p, s_part);
     if (threadIdx.x == 0) {
         double* o = A.out + 4 * c;
-        o[0] = (double)p.n;
-        if (p.n > 0) { o[1] = p.mx; o[2] = p.my; o[3] = sqrt((p.m2x + p.m2y) / (double)p.n); }
+        o[0] = ok ? (double)p.n : CUDART_NAN;
+        if (ok && p.n > 0) { o[1] = p.mx; o[2] = p.my; o[3] = sqrt((p.m2x + p.m2y) / (double)p.n); }
         else { o[1] = o[2] = o[3] = CUDART_NAN; }
     }
+}
+
+// The two aimed edge rays of every candidate in the strict trace, 2 threads per candidate: results land in slots
+// 14..23 of the prelude record so the FAST population sweep does not serialise a strict re-trace in every CTA.
+struct CandSurfGen {
+    const double* Rc; int rows; double focus;
+    __device__ __forceinline__ SurfK operator[](int i) const
+    {
+        SurfK S;
+        if (i < rows - 1) derive_surface(S, Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i], Rc[2 * rows + i + 1]);
+        else derive_surface(S, CUDART_INF, 0.0, focus, Rc[3 * rows - 1], 1.0);
+        return S;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const double* RtnK, double* aim)
+{
+    const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    const long long c = t >> 1;
+    const int e = (int)(t & 1);
+    if (c >= C) return;
+    double* rec = aim + (size_t)c * ORT_AIM_NOUT;
+    const int stop = (int)rec[6];
+    const bool good = rec[11] == 0.0 && stop >= 1 && stop <= rows - 1;
+    double* o = rec + 16 + 4 * e;
+    if (!good) { if (e == 0) { rec[14] = 0.0; rec[15] = 0.0; } o[0] = o[1] = o[2] = o[3] = CUDART_NAN; return; }
+    CandSurfGen gen; gen.Rc = RtnK + (size_t)c * 4 * rows; gen.rows = rows; gen.focus = rec[5];
+    const Hit h = trace_strict<false>(gen, rows, stop, rec[e], 0.0, rec[3], 0.0);
+    const double ri = jl_hypot(h.xs, h.ys);
+    const bool drop = ri > rec[7] || is_nan_bits(h.xf) || is_nan_bits(h.yf);
+    o[0] = drop ? 0.0 : 1.0; o[1] = h.xf; o[2] = h.yf - rec[4]; o[3] = ri * ri;
+    if (e == 0) { rec[14] = 1.0; rec[15] = 0.0; }
+}
+
+cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, cudaStream_t st)
+{
+    if (C == 0) return cudaSuccess;
+    k_aim_edges<<<(unsigned)((2 * C + 127) / 128), 128, 0, st>>>(rows, C, RtnK, aim);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -706,7 +797,12 @@ cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream
 cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st)
 {
     if (A.C == 0) return cudaSuccess;
-    if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
-    else k_candidates<ORT_ARITH_STRICT><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+    if (A.aim) {
+        if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, true><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+        else k_candidates<ORT_ARITH_STRICT, true><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+    } else {
+        if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, false><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+        else k_candidates<ORT_ARITH_STRICT, false><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+    }
     return cudaGetLastError();
 }

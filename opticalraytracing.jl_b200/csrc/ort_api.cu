@@ -774,6 +774,86 @@ int ort_trace3d_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK
     return ORT_OK;
 }
 
+int ort_aim_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* a, double h_prime,
+                           double H, int aspheric, double* d_out, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS - 1) return fail(ctx, ORT_EINVAL, "aim_candidates: rows = %d", rows);
+    if (C < 0 || C >= (1LL << 31) || !d_RtnK || !a || !d_out) return fail(ctx, ORT_EINVAL, "aim_candidates: bad input");
+    if (!(fabs(H) <= 1.0)) return fail(ctx, ORT_EINVAL, "aim_candidates: DomainError |H| <= 1");    // src/PupilSampling.jl:88-89
+    CK(cudaSetDevice(ctx->device));
+    AimCandArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.h_prime = h_prime; A.H = H; A.aspheric = aspheric; A.out = d_out;
+    for (int i = 0; i + 1 < rows; i++) A.a[i] = a[i];
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_aim_candidates(A, (cudaStream_t)stream));
+        CK(launch_aim_edges(rows, C, d_RtnK, d_out, (cudaStream_t)stream));
+    }
+    if (C > 0) ctx->launches += 2;
+    return ORT_OK;
+}
+
+int ort_aim_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, const double* a, double h_prime,
+                       double H, int aspheric, double* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (C < 0 || !RtnK || !a || !out || rows < 2) return fail(ctx, ORT_EINVAL, "aim_candidates: bad input");
+    if (C == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)C * 4 * (size_t)rows * 8, no = (size_t)C * ORT_AIM_NOUT * 8;
+    double *d_p, *d_o;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT1, no, d_o);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
+    int rc = ort_aim_candidates_dev(ctx, rows, C, d_p, a, h_prime, H, aspheric, d_o, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, no, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+int ort_trace3d_candidates_aimed_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* d_aim,
+                                     int ny, int nx, int arith, double* d_out, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS - 1) return fail(ctx, ORT_EINVAL, "candidates_aimed: rows = %d", rows);
+    if (C < 0 || C >= (1LL << 31) || !d_RtnK || !d_aim || !d_out) return fail(ctx, ORT_EINVAL, "candidates_aimed: bad input");
+    if ((long long)ny * nx >= (1LL << 31) || ny < 2 || nx < 2) return fail(ctx, ORT_EINVAL, "candidates_aimed: bad grid");
+    if (arith != ORT_ARITH_STRICT && arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "candidates_aimed: arith = %d", arith);
+    CK(cudaSetDevice(ctx->device));
+    CandArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.aim = d_aim; A.ny = ny; A.nx = nx; A.stop = 1;
+    A.v = 0.0;                                       // V = 0 (meridional field, src/PupilSampling.jl:98)
+    A.out = d_out;
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_candidates(A, arith, (cudaStream_t)stream));
+    }
+    if (C > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_trace3d_candidates_aimed(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, const double* aim, int ny,
+                                 int nx, int arith, double* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (C < 0 || !RtnK || !aim || !out || rows < 2) return fail(ctx, ORT_EINVAL, "candidates_aimed: bad input");
+    if (C == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)C * 4 * (size_t)rows * 8, na = (size_t)C * ORT_AIM_NOUT * 8;
+    double *d_p, *d_a, *d_o;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT1, na, d_a); ENSURE(SL_OUT0, (size_t)C * 32, d_o);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_a, aim, na, cudaMemcpyHostToDevice, st));
+    int rc = ort_trace3d_candidates_aimed_dev(ctx, rows, C, d_p, d_a, ny, nx, arith, d_o, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, (size_t)C * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
 int ort_seidel_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* a, double h_prime,
                               double lambda, const double* dn, double* d_out, double* d_per_surface, void* stream)
 {

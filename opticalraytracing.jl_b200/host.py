@@ -780,6 +780,25 @@ def seidel_merit(backend, RtnK, a, h_prime, aberr=("W040", "W131", "W222", "W220
     return np.abs(out[:, cols]) @ w, out
 
 
+AIM_FIELDS = ("y1", "y2", "y_EP", "u", "h_prime", "focus", "stop", "a_stop", "EP_t", "Ubar", "f", "status", "nu", "U")
+
+
+def full_trace_candidates(RtnK, a, h_prime, H, k_rays=SPOT_RAYS, aspheric=False, backend=None, arith=_lib.FAST):
+    """full_trace(surfaces, system, H, k_rays) (src/PupilSampling.jl:85-147) for a POPULATION of candidate
+    prescriptions RtnK[C][4][rows] sharing apertures `a` and image height h' of solve(surfaces, a, h'): every
+    candidate gets its own first-order solve, aimed chief / marginal / edge rays (:90-100) and its own pupil grid
+    (:121-122), then its own spot statistics -- two launches for the whole population.  This is the real-ray merit
+    the reference could only evaluate one `full_trace` at a time.
+    Returns (spot (C, 4) = n_kept, mean_x, mean_y, RMS of the unmirrored half pupil, aim (C, 24), see AIM_FIELDS);
+    the mirrored RMS of RealRayError is sqrt(RMS^2 + mean_x^2)  (x mirrors to mean 0, :140-141)."""
+    if not abs(H) <= 1.0:
+        raise ValueError("DomainError: Domain: |H| <= 1.0")                      # :89
+    be = _be(backend)
+    aim = be.aim_candidates(RtnK, a, h_prime, H, aspheric=aspheric)
+    spot = be.trace3d_candidates_aimed(RtnK, aim, int(k_rays), int(k_rays) // 2, arith=arith)
+    return spot, aim
+
+
 def wavegrad(eps, lam=LAMBDA):
     """wavegrad(eps::RealRayError, lambda) -- src/PupilSampling.jl:165-167"""
     return eps.x * eps.nu / lam, eps.y * eps.nu / lam

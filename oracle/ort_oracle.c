@@ -262,7 +262,7 @@ ORC_API unsigned orc_trace2d(int rows, const double *R, const double *t, const d
         y += s * tan(U);                                       /* :158 */
         ts[i] += s; ts[i + 1] -= s;                            /* :160-161 */
         double theta;
-        if (!aspheric) {
+        if (Ks == 0.0) {                                       /* iszero(Ks) && ps === zero, per surface  :162 */
             double q = y / Rs;                                 /* tilt(y,R) :101 */
             if (fabs(q) > 1.0) flags |= F_DOMAIN;              /* Julia asin throws */
             theta = asin(q);

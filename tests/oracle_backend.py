@@ -50,6 +50,26 @@ class OracleBackend:
         per = np.stack([orc.seidel(np.asarray(c)[:3].T, a, h_prime, lam=lam, dn=dn)[1] for c in RtnK])
         return out, per
 
+    def aim_candidates(self, RtnK, a, h_prime, H, aspheric=False):
+        from oracle import prelude as pre
+        out = np.full((len(RtnK), 24), np.nan)
+        for c, blk in enumerate(np.asarray(RtnK, dtype=np.float64)):
+            S, K = blk[:3].T.copy(), blk[3].copy()
+            sysm = pre.solve(S, a, h_prime)
+            p = pre.full_trace_inputs(sysm, H, 64, K=K, aspheric=aspheric)
+            out[c, :16] = (p.y1, p.y2, p.y_EP, p.u, p.h_prime, p.focus, p.stop, p.a_stop, p.EP_t,
+                           p.U / abs(H) if H else np.nan, sysm.f, 0.0, p.nu, p.U, 0.0, 0.0)
+        return out
+
+    def trace3d_candidates_aimed(self, RtnK, aim, ny, nx, arith=1):
+        out = np.empty((len(RtnK), 4))
+        for c, blk in enumerate(np.asarray(RtnK, dtype=np.float64)):
+            y1, y2, y_EP, u, hp, focus, stop, a_stop = aim[c, :8]
+            ext = np.concatenate([blk, np.array([[np.inf], [0.0], [1.0], [0.0]])], axis=1)
+            ext[1, -2] = focus
+            out[c] = orc.candidates(ext[None], np.linspace(y1, y2, ny), np.linspace(0.0, y_EP, nx), int(stop), a_stop, hp, u)[0]
+        return out
+
     def transfer_batch(self, M, tau, taup, v_in, reverse=False):
         return orc.transfer_batch(M, tau, taup, v_in, reverse=reverse)
 

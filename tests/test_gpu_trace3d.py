@@ -224,6 +224,64 @@ def test_candidates(ctx, orc, pre, ort):
         assert np.max(np.abs(out[:, 3] / ref[:, 3] - 1)) < 1e-11     # RMS about the centroid
 
 
+@pytest.mark.parametrize("H", [0.0, 0.7, 1.0])
+def test_candidates_aimed(ctx, orc, pre, ort, H):
+    """the whole full_trace prelude per candidate on the device, then every candidate over
+    its own aimed pupil grid.  (a) the prelude records against the CPU restatement of the reference prelude;
+    (b) the spot statistics against the oracle grid trace on IDENTICAL inputs (the device's records)."""
+    P = ort.prescriptions.COOKE
+    C = 40
+    RtnK = ort.prescriptions.perturbed_triplets(C)
+    aim = ctx.aim_candidates(RtnK, P["a"], P["h"], H)
+    assert np.all(aim[:, 11] == 0.0)
+    sub = range(0, C, 5)
+    for c in sub:
+        S = RtnK[c, :3].T.copy()
+        sysm = pre.solve(S, P["a"], P["h"])
+        p = pre.full_trace_inputs(sysm, H, 64)
+        ref = np.array([p.y1, p.y2, p.y_EP, p.u, p.h_prime, p.focus, p.stop, p.a_stop, p.EP_t])
+        got = aim[c, :9]
+        assert got[6] == ref[6] and got[7] == ref[7]                  # stop index and stop radius exact
+        assert got[5] == ref[5] and aim[c, 10] == sysm.f              # first-order quantities bit-exact (no libm)
+        # aimed quantities: both sides stop the reference's secant at |f| <= sqrt(eps) (:229), so they agree to the
+        # libm last-ulp differences amplified by that loop, far inside the loop's own tolerance
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-9
+        assert aim[c, 12] == sysm.marginal.nu[-1]
+    for arith in (ort.STRICT, ort.FAST):
+        out = ctx.trace3d_candidates_aimed(RtnK, aim, 64, 32, arith=arith)
+        for c in sub:
+            y1, y2, y_EP, u, hp, focus, stop, a_stop = aim[c, :8]
+            ext = np.concatenate([RtnK[c], np.array([[np.inf], [0.0], [1.0], [0.0]])], axis=1)
+            ext[1, -2] = focus
+            ref = orc.candidates(ext[None], np.linspace(y1, y2, 64), np.linspace(0.0, y_EP, 32), int(stop), a_stop, hp, u)[0]
+            assert out[c, 0] == ref[0]
+            assert np.max(np.abs(out[c, 1:3] - ref[1:3])) / 25.0 < TOL
+            assert abs(out[c, 3] / ref[3] - 1) < 1e-10
+    # the aimed population agrees with the product's own single-system full_trace (same algorithm, one system)
+    S0 = RtnK[3, :3].T.copy()
+    system = ort.solve(S0, P["a"], P["h"], backend=ctx)
+    e = ort.full_trace(S0, system, H, 64, backend=ctx, arith=ort.STRICT)
+    spot, _ = ort.full_trace_candidates(RtnK[3:4], P["a"], P["h"], H, 64, backend=ctx, arith=ort.STRICT)
+    assert spot[0, 0] * 2 == len(e.x)
+    assert abs(math.sqrt(spot[0, 3] ** 2 + spot[0, 1] ** 2) / e.RMS - 1) < 1e-9
+
+
+def test_candidates_aimed_failures(ctx, ort):
+    """a candidate whose prelude cannot be completed gives NaN statistics and a status, never an error"""
+    P = ort.prescriptions.COOKE
+    RtnK = ort.prescriptions.perturbed_triplets(4)
+    RtnK[1, 0, 1] = 1.0                        # first surface radius 1 mm: the marginal ray misses it
+    RtnK[2, 1, -1] = 3.0                       # last row has a finite thickness: Lens() keeps it, solve() cannot use it
+    aim = ctx.aim_candidates(RtnK, P["a"], P["h"], 0.7)
+    assert aim[0, 11] == 0.0 and aim[3, 11] == 0.0
+    assert aim[1, 11] != 0.0 and aim[2, 11] == 8.0
+    out = ctx.trace3d_candidates_aimed(RtnK, aim, 16, 8)
+    assert np.all(np.isnan(out[1])) and np.all(np.isnan(out[2]))
+    assert np.all(np.isfinite(out[0])) and np.all(np.isfinite(out[3]))
+    with pytest.raises(ort.OrtError):
+        ctx.aim_candidates(RtnK, P["a"], P["h"], 1.5)
+
+
 # ------------------------------------------------------------------------------------------------
 # EXTENSION (SURVEY.md section 8 f3/f4): OPL / OPD accumulation and per-surface aperture clipping
 # ------------------------------------------------------------------------------------------------

@@ -186,3 +186,21 @@ def test_aberrations_and_ray_error_functors(ort, be, cooke):
         ab0(1.5, 0.0, 0.0)
     merit, table = ort.seidel_merit(be, ort.prescriptions.perturbed_triplets(16), P["a"], P["h"])
     assert merit.shape == (16,) and np.all(merit > 0) and table.shape == (16, 16)
+
+
+def test_full_trace_candidates_host_logic(ort, be, cooke):
+    """population form == the single-system full_trace, candidate by candidate (oracle backend)"""
+    import math
+    P = ort.prescriptions.COOKE
+    a, h = P["a"], P["h"]
+    RtnK = ort.prescriptions.perturbed_triplets(3)
+    spot, aim = ort.full_trace_candidates(RtnK, a, h, 0.7, 32, backend=be)
+    assert spot.shape == (3, 4) and aim.shape == (3, 24)
+    for c in range(3):
+        Sc = RtnK[c, :3].T.copy()
+        system = ort.solve(Sc, a, h, backend=be)
+        e = ort.full_trace(Sc, system, 0.7, 32, backend=be)
+        assert spot[c, 0] * 2 == len(e.x)
+        assert abs(math.sqrt(spot[c, 3] ** 2 + spot[c, 1] ** 2) / e.RMS - 1) < 1e-9
+    with pytest.raises(ValueError):
+        ort.full_trace_candidates(RtnK, a, h, 1.2, backend=be)

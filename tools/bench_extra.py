@@ -94,6 +94,21 @@ def main():
         out[f"candidates_{name}"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "rays_per_s": rays / ms * 1e3,
                                      "intersections_per_s_x7": rays * 7 / ms * 1e3, "tflops_nominal": rays * 513 / ms / 1e9,
                                      "fp64_frac": rays * 513 / ms / 1e9 / peak}
+    # ---- f1: per-candidate prelude (solve + aimed chief / marginal / edge rays) and the aimed population sweep
+    d_Rn = torch.from_numpy(base.copy()).to(dev)
+    d_aim = torch.empty((C, 24), dtype=torch.float64, device=dev)
+    d_oa = torch.empty((C, 4), dtype=torch.float64, device=dev)
+    Pq = ort.prescriptions.COOKE
+    ms, best = timed(ctx, lambda: ctx.aim_candidates_dev(8, C, d_Rn.data_ptr(), Pq["a"], Pq["h"], 0.7, d_aim.data_ptr(), stream=st), reps=5, warm=2)
+    out["aim_candidates"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "failed": int((d_aim[:, 11] != 0).sum())}
+    for name, arith in (("fast", ort.FAST), ("strict", ort.STRICT)):
+        ms, best = timed(ctx, lambda: ctx.trace3d_candidates_aimed_dev(8, C, d_Rn.data_ptr(), d_aim.data_ptr(), 64, 64, d_oa.data_ptr(),
+                                                                      arith=arith, stream=st), reps=5, warm=2)
+        rays = C * 4096
+        out[f"candidates_aimed_{name}"] = {"ms": ms, "candidates_per_s": C / ms * 1e3, "rays_per_s": rays / ms * 1e3,
+                                           "fp64_frac": rays * 513 / ms / 1e9 / peak}
+    ra = d_oa.cpu().numpy()
+    out["candidates_aimed_rms_range"] = [float(np.nanmin(ra[:, 3])), float(np.nanmax(ra[:, 3]))]
     # ---- K7: first-order solve + Seidel sums per candidate
     d_s = torch.empty((C, 16), dtype=torch.float64, device=dev)
     Pc = ort.prescriptions.COOKE
