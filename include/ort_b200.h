@@ -261,6 +261,21 @@ int ort_seidel_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d
                               double h_prime, double lambda, const double *dn /* host */, double *d_out,
                               double *d_per_surface, void *stream);
 
+/* ---- candidate-batched vignetting(system, a) (src/Vignetting.jl:1-30, type src/Types.jl:169-176).
+ *      RtnK[C][4][rows]; a_solve[rows-1] = the apertures solve() picks the stop with; a_vig[rows-1] (NULL = a_solve)
+ *      = the semi-diameters under test.  k = rows - 1.  out[C][6 k + 12]:
+ *        [0 .. 5k)   M, column-major k x 5: a, limited |y|, unvignetted |y| + |ybar|, half |ybar|, full |ybar| - |y|
+ *                    (half / full NaN where < |y|, :12-13)
+ *        [5k .. 6k)  per-surface code: 1 = limit (:27), 2 = partial (:29), 4 = full (:28)
+ *        [6k .. 6k+9) FOV 3 x 3 row-major: rows unvignetted / half / fully vignetted, columns 2 atand(u), u, h' (:20-26)
+ *        6k+9 un (:15), 6k+10 stop, 6k+11 f.
+ *      One thread per candidate, reference operation order; atand is CUDA libm atan * 180/pi (last-ulp, not bit, parity). */
+#define ORT_VIG_TAIL 12
+int ort_vignetting_candidates(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *a_solve,
+                              const double *a_vig, double h_prime, double *out);
+int ort_vignetting_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a_solve /* host */,
+                                  const double *a_vig /* host */, double h_prime, double *d_out, void *stream);
+
 /* ---- multi-GPU combine (host arithmetic): Chan merge of per-shard records recs[n_shards][n_fields], folded in
  *      shard (rank) order so every rank gets bit-identical results, and the reference's sigma of the mirrored spot
  *      (src/PupilSampling.jl:140-146,169-173) from one record. */

@@ -15,7 +15,7 @@ using OpticalRayTracing
 using OpticalRayTracing: Layout, Lens, System, RayBasis, SystemOrRayBasis, RealRay, RealRayError,
                          TransferMatrix, trace_chief_ray, trace_marginal_ray, trace_edge_rays,
                          spot_rays, λ
-import OpticalRayTracing: full_trace, raytrace, transfer, reverse_transfer
+import OpticalRayTracing: full_trace, raytrace, transfer, reverse_transfer, vignetting, aberrations
 
 const LIB = get(ENV, "ORT_B200_LIB", "libort_b200.so")
 
@@ -219,6 +219,53 @@ function reverse_transfer(M::AbstractMatrix, V::Matrix{Float64}, τ′, τ)
     check(ccall((:ort_transfer_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Cint, Int64, Ptr{Float64}, Ptr{Float64}),
                 ctx(), Mc, τ, τ′, 1, size(V, 2), V, out))
+    return out
+end
+
+# --- population methods (additive): one prescription per candidate, shared apertures -----------
+# pack R, t, n, K of every candidate as [C][4][rows] (rows fastest), the layout ort_b200.h documents
+function pack(candidates::Vector{<:Layout})
+    rows = length(first(candidates).R)
+    P = Array{Float64}(undef, rows, 4, length(candidates))
+    for (c, L) in enumerate(candidates)
+        P[:, 1, c] = L.R; P[:, 2, c] = L.t; P[:, 3, c] = L.n; P[:, 4, c] = L.K
+    end
+    return P, rows
+end
+
+# full_trace (src/PupilSampling.jl:85-147) for every candidate: per-candidate solve, ray aiming, pupil grid, spot
+# statistics.  Returns (spot 4 × C = n_kept, mean_x, mean_y, RMS of the half pupil; aim 24 × C prelude records).
+function full_trace(candidates::Vector{<:Layout}, a::AbstractVector, h′, H, k_rays = 64; arith = 1)
+    abs(H) ≤ 1.0 || throw(DomainError(H, "Domain: |H| ≤ 1.0"))
+    P, rows = pack(candidates); C = length(candidates)
+    aim = Matrix{Float64}(undef, 24, C); spot = Matrix{Float64}(undef, 4, C)
+    av = collect(Float64, a)
+    check(ccall((:ort_aim_candidates, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}),
+                ctx(), rows, C, P, av, h′, H, 1, aim))
+    check(ccall((:ort_trace3d_candidates_aimed, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Cint, Ptr{Float64}),
+                ctx(), rows, C, P, aim, k_rays, k_rays ÷ 2, arith, spot))
+    return spot, aim
+end
+
+# vignetting(system, a) (src/Vignetting.jl:1-30) for every candidate; out is (6k + 12) × C, see ort_b200.h
+function vignetting(candidates::Vector{<:Layout}, a::AbstractVector, h′; a_vig = a)
+    P, rows = pack(candidates); C = length(candidates)
+    out = Matrix{Float64}(undef, 6 * (rows - 1) + 12, C)
+    check(ccall((:ort_vignetting_candidates, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                ctx(), rows, C, P, collect(Float64, a), collect(Float64, a_vig), h′, out))
+    return out
+end
+
+# first-order solve + Seidel sums (src/SeidelAberrations.jl:6-53) for every candidate; out is 16 × C
+function aberrations(candidates::Vector{<:Layout}, a::AbstractVector, h′; λ = 587.5618e-6, δn = zeros(length(first(candidates).R)))
+    P, rows = pack(candidates); C = length(candidates)
+    out = Matrix{Float64}(undef, 16, C)
+    check(ccall((:ort_seidel_candidates, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx(), rows, C, P, collect(Float64, a), h′, λ, collect(Float64, δn), out, C_NULL))
     return out
 end
 

@@ -13,11 +13,11 @@ from .host import (LAMBDA, SA, TSA, Aberration, aberrations, seidel_merit, Wavef
                    VectorRealRay, flatten, full_trace, full_trace_candidates, full_trace_fields, make_lens, merge_stats,
                    raytrace, reverse_transfer, rms_from_stats, set_default_backend, solve,
                    trace_chief_ray, trace_edge_rays, trace_marginal_ray, transfer, transfer_matrix,
-                   wavegrad)
+                   vignetting, Vignetting, wavegrad)
 
 __all__ = ["_lib", "distributed", "host", "prescriptions", "Context", "OrtError", "PinnedArray", "STATS_DTYPE", "FAST",
            "STRICT", "FLAG_MISS", "FLAG_TIR", "FLAG_DOMAIN", "FLAG_CLIP", "FLAG_VIGN", "EXT_OPD", "EXT_VIGNETTE", "STATS_BYTES", "LAMBDA", "SA", "TSA", "Aberration", "aberrations", "seidel_merit", "Wavefront", "aim_rays", "wavefront",
            "Layout", "Lens", "RayBasis", "RealRay", "RealRayError", "System", "VectorRealRay",
            "flatten", "full_trace", "full_trace_candidates", "full_trace_fields", "make_lens", "merge_stats", "raytrace",
            "reverse_transfer", "rms_from_stats", "set_default_backend", "solve", "trace_chief_ray",
-           "trace_edge_rays", "trace_marginal_ray", "transfer", "transfer_matrix", "wavegrad"]
+           "trace_edge_rays", "trace_marginal_ray", "transfer", "transfer_matrix", "vignetting", "Vignetting", "wavegrad"]

@@ -17,6 +17,7 @@ FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP, FLAG_VIGN = 1, 2, 4, 8, 16
 EXT_OPD, EXT_VIGNETTE = 1, 2
 STRICT, FAST = 0, 1
 AIM_NOUT = 24
+VIG_TAIL = 12
 
 # every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
@@ -26,7 +27,8 @@ SYMBOLS = [
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev",
-    "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_seidel_candidates",
+    "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_vignetting_candidates",
+    "ort_vignetting_candidates_dev", "ort_seidel_candidates",
     "ort_seidel_candidates_dev", "ort_merge_stats", "ort_rms_from_stats", "ort_fp64_peak",
 ]
 
@@ -130,6 +132,9 @@ def load():
     L.ort_seidel_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
     L.ort_seidel_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, _dp,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ort_vignetting_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, C.c_double, _dp]
+    L.ort_vignetting_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, _dp, C.c_double, C.c_void_p,
+                                                C.c_void_p]
     L.ort_aim_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.ort_aim_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]
@@ -435,6 +440,26 @@ class Context:
         self._ck(self.L.ort_seidel_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(lam), _p(dn_),
                                               _p(out), _p(per)))
         return (out, per) if per_surface else out
+
+    def vignetting_candidates(self, RtnK, a, h_prime, a_vig=None):
+        """vignetting(system, a) per candidate -> dict(M (C, k, 5), code (C, k), FOV (C, 3, 3), un (C,), stop (C,), f (C,))"""
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        k = rows - 1
+        a = _d(a)
+        av = None if a_vig is None else _d(a_vig)
+        assert four == 4 and a.shape == (k,) and (av is None or av.shape == (k,))
+        out = np.empty((Cn, 6 * k + VIG_TAIL), dtype=np.float64)
+        self._ck(self.L.ort_vignetting_candidates(self.h, rows, Cn, _p(RtnK), _p(a), _p(av), float(h_prime), _p(out)))
+        return dict(M=out[:, :5 * k].reshape(Cn, 5, k).transpose(0, 2, 1).copy(), code=np.nan_to_num(out[:, 5 * k:6 * k]).astype(np.int32),
+                    FOV=out[:, 6 * k:6 * k + 9].reshape(Cn, 3, 3).copy(), un=out[:, 6 * k + 9] == 1.0,
+                    stop=np.nan_to_num(out[:, 6 * k + 10]).astype(np.int32), f=out[:, 6 * k + 11].copy())
+
+    def vignetting_candidates_dev(self, rows, Cn, d_RtnK, a, h_prime, d_out, a_vig=None, stream=0):
+        a = _d(a)
+        av = None if a_vig is None else _d(a_vig)
+        self._ck(self.L.ort_vignetting_candidates_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), _p(a), _p(av),
+                                                      float(h_prime), C.c_void_p(d_out), C.c_void_p(stream)))
 
     def aim_candidates(self, RtnK, a, h_prime, H, aspheric=False):
         """per-candidate full_trace prelude -> (C, 24) records (see ort_b200.h: ort_aim_candidates)"""

@@ -61,6 +61,14 @@ struct SeidelArgs {
     double* out; double* per;
 };
 
+struct VigArgs {
+    int rows; long long C;
+    const double* RtnK;
+    double a_solve[ORT_MAX_ROWS], a_vig[ORT_MAX_ROWS];
+    double h_prime;
+    double* out;                            // [C][6 * (rows - 1) + ORT_VIG_TAIL]
+};
+
 struct AimCandArgs {
     int rows; long long C;
     const double* RtnK;
@@ -124,6 +132,7 @@ cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaS
 cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
 cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st);
 cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st);
+cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st);
 cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, cudaStream_t st);
 cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,

@@ -353,6 +353,99 @@ __global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelAr
 }
 
 // ------------------------------------------------------------------------------------------
+// vignetting(system, a) per candidate (src/Vignetting.jl:1-30): semi-diameter table
+// [a, limited = |y|, unvignetted = |y| + |ybar|, half = |ybar|, full = |ybar| - |y|] (the last two NaN where
+// < |y|, :12-13), the three maximum fields of view (:20-26), and the limit / partial / full classification
+// (:27-29) as a per-surface code.  Same two-pass first-order solve as k_seidel (bit-identical rays).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool jl_isapprox(double x, double y)
+{   // isapprox(x, y): x == y || (isfinite(x) && isfinite(y) && |x - y| <= sqrt(eps) * max(|x|, |y|))
+    if (x == y) return true;
+    if (!isfinite(x) || !isfinite(y)) return false;
+    return fabs(SS(x, y)) <= SM(1.4901161193847656e-08, fmax(fabs(x), fabs(y)));
+}
+
+__global__ void __launch_bounds__(128) k_vignetting(const __grid_constant__ VigArgs A)
+{
+    const long long c = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (c >= A.C) return;
+    const int rows = A.rows, k = rows - 1;
+    const double* R = A.RtnK + (size_t)c * 4 * rows;
+    const double* t = R + rows;
+    const double* n = t + rows;
+    double* M = A.out + (size_t)c * (6 * k + ORT_VIG_TAIL);
+    double* tail = M + 6 * k;
+    const double tl = t[rows - 1];
+    if (!(tl == 0.0 || !isfinite(tl))) {
+        for (int j = 0; j < 6 * k + ORT_VIG_TAIL; j++) M[j] = CUDART_NAN;
+        return;
+    }
+    // ---- pass 1: stop, scale, marginal nu[end]
+    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
+    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0, yfirst = 0.0;
+    int stop = 1;
+    for (int i = 0; i < k; i++) {
+        double ti = t[i];
+        if (i == 0 && !isfinite(ti)) ti = 0.0;
+        const double tau = SD(ti, n[i]);
+        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
+        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
+        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        const double v = SD(A.a_solve[i], y1);
+        if (i == 0) yfirst = y1;
+        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }
+    }
+    const double f = -SD(1.0, w1);
+    const double numk = SM(w1, s);
+    const double nub = SD(SM(-numk, A.h_prime), SM(yfirst, s));
+    const double y_stop = SM(ys1, s);
+    // ---- pass 2: the table and the three minima
+    y1 = 1.0; w1 = 0.0; y2 = 0.0; w2 = 1.0;
+    double min_un = CUDART_INF, min_half = CUDART_INF, min_full = CUDART_INF;
+    bool un = true, nan_un = false, nan_half = false, nan_full = false;
+    for (int i = 0; i < k; i++) {
+        double ti = t[i];
+        if (i == 0 && !isfinite(ti)) ti = 0.0;
+        const double tau = SD(ti, n[i]);
+        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
+        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
+        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        const double ym = SM(y1, s);
+        const double yb = fabs(SM(nub, SS(y2, SD(SM(ym, ys2), y_stop))));     // |chief y|  (src/RayTracing.jl:258)
+        const double y = fabs(ym);
+        const double a = A.a_vig[i];
+        const double unv = SA(y, yb);
+        double half = yb, full = SS(yb, y);
+        if (half < y) half = CUDART_NAN;                                       // :12
+        if (full < y) full = CUDART_NAN;                                       // :13
+        const bool a_unvig = a >= unv || jl_isapprox(a, unv);                  // :14
+        un = un && a_unvig;
+        const bool is_limit = a < y && !jl_isapprox(a, unv);                   // :27
+        const bool is_full = a <= full;                                        // :28 (NaN compares false)
+        const bool is_partial = !a_unvig && !is_full;                          // :29
+        M[0 * k + i] = a; M[1 * k + i] = y; M[2 * k + i] = unv; M[3 * k + i] = half; M[4 * k + i] = full;
+        M[5 * k + i] = (double)((is_limit ? 1 : 0) | (is_partial ? 2 : 0) | (is_full ? 4 : 0));
+        // minimum(...) propagates NaN in Julia; fmin would drop it
+        if (i != stop - 1) { const double q = SD(SS(a, y), yb); nan_un |= isnan(q); if (q < min_un) min_un = q; }   // :17
+        { const double q = SD(a, yb); nan_half |= isnan(q); if (q < min_half) min_half = q; }                       // :18
+        { const double q = SD(SA(a, y), yb); nan_full |= isnan(q); if (q < min_full) min_full = q; }                // :19
+    }
+    if (nan_un) min_un = CUDART_NAN;
+    if (nan_half) min_half = CUDART_NAN;
+    if (nan_full) min_full = CUDART_NAN;
+    const double u0 = SD(nub, n[0]);                                           // chief.u[1] = nu_bar / n[1]
+    const double mins[3] = {min_un, min_half, min_full};
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const double ub = fabs(SM(u0, mins[j]));                               // :22
+        tail[3 * j + 0] = SM(2.0, SM(atan(ub), 57.29577951308232));            // 2 atand(u_bar)  :23
+        tail[3 * j + 1] = ub;
+        tail[3 * j + 2] = fabs(SM(A.h_prime, mins[j]));                        // chief.y[end] = h'  :25
+    }
+    tail[9] = un ? 1.0 : 0.0; tail[10] = (double)stop; tail[11] = f;
+}
+
+// ------------------------------------------------------------------------------------------
 // Per-candidate prelude of full_trace (src/PupilSampling.jl:85-108): first-order solve
 // (src/RayTracing.jl:208-221, 246-263), real chief ray traced backwards through the reversed prescription
 // (:265-296), real marginal ray (:223-240), edge rays (src/PupilSampling.jl:67-83; the two roots of the
@@ -565,6 +658,13 @@ cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st)
 {
     if (A.C == 0) return cudaSuccess;
     k_seidel<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st)
+{
+    if (A.C == 0) return cudaSuccess;
+    k_vignetting<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A);
     return cudaGetLastError();
 }
 

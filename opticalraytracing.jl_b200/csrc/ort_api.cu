@@ -774,6 +774,43 @@ int ort_trace3d_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK
     return ORT_OK;
 }
 
+int ort_vignetting_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* a_solve,
+                                  const double* a_vig, double h_prime, double* d_out, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS) return fail(ctx, ORT_EINVAL, "vignetting: rows = %d", rows);
+    if (C < 0 || C >= (1LL << 31) || !d_RtnK || !a_solve || !d_out) return fail(ctx, ORT_EINVAL, "vignetting: bad input");
+    CK(cudaSetDevice(ctx->device));
+    VigArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.h_prime = h_prime; A.out = d_out;
+    for (int i = 0; i + 1 < rows; i++) { A.a_solve[i] = a_solve[i]; A.a_vig[i] = a_vig ? a_vig[i] : a_solve[i]; }
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_vignetting(A, (cudaStream_t)stream));
+    }
+    if (C > 0) ctx->launches++;
+    return ORT_OK;
+}
+
+int ort_vignetting_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, const double* a_solve,
+                              const double* a_vig, double h_prime, double* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (C < 0 || !RtnK || !a_solve || !out || rows < 2) return fail(ctx, ORT_EINVAL, "vignetting: bad input");
+    if (C == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)C * 4 * (size_t)rows * 8, no = (size_t)C * (6 * (size_t)(rows - 1) + ORT_VIG_TAIL) * 8;
+    double *d_p, *d_o;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT0, no, d_o);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
+    int rc = ort_vignetting_candidates_dev(ctx, rows, C, d_p, a_solve, a_vig, h_prime, d_o, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, no, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
 int ort_aim_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_RtnK, const double* a, double h_prime,
                            double H, int aspheric, double* d_out, void* stream)
 {

@@ -799,6 +799,48 @@ def full_trace_candidates(RtnK, a, h_prime, H, k_rays=SPOT_RAYS, aspheric=False,
     return spot, aim
 
 
+@dataclass
+class Vignetting:
+    """Vignetting (src/Types.jl:169-176); limit / partial / full hold 1-based surface indices like the reference"""
+    M: np.ndarray
+    FOV: np.ndarray
+    un: bool
+    limit: np.ndarray
+    partial: np.ndarray
+    full: np.ndarray
+
+
+def _isapprox(x, y):
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        return (x == y) | (np.isfinite(x) & np.isfinite(y) & (np.abs(x - y) <= EPS * np.maximum(np.abs(x), np.abs(y))))
+
+
+def vignetting(system, a=None):
+    """vignetting(system::SystemOrRayBasis, a = system.a) -- src/Vignetting.jl:1-30.  O(k) host algebra on the two
+    paraxial rays the System already holds (like the tail of solve()); the population form, one thread per
+    candidate prescription, is Context.vignetting_candidates."""
+    a = np.asarray(system.a if a is None else a, dtype=np.float64)
+    yb = np.abs(system.chief.y[1:-1])
+    y = np.abs(system.marginal.y[1:-1])
+    M = np.column_stack([a, y, y + yb, yb, yb - y])
+    nanmin = lambda v: np.nan if np.any(np.isnan(v)) else float(np.min(v))       # Julia's minimum propagates NaN
+    with np.errstate(invalid="ignore", divide="ignore"):
+        M[M[:, 3] < y, 3] = np.nan                                               # :12
+        M[M[:, 4] < y, 4] = np.nan                                               # :13
+        a_unvig = (a >= M[:, 2]) | _isapprox(a, M[:, 2])                         # :14
+        others = np.arange(len(a)) != system.stop - 1
+        scales = (nanmin(((a - y) / yb)[others]), nanmin(a / yb), nanmin((a + y) / yb))    # :17-19
+        FOV = np.empty((3, 3))
+        for i, sc in enumerate(scales):
+            ub = abs(system.chief.u[0] * sc)
+            FOV[i] = (2 * (math.atan(ub) * (180.0 / math.pi)), ub, abs(system.chief.y[-1] * sc))
+        limit = np.nonzero((a < M[:, 1]) & ~_isapprox(a, M[:, 2]))[0] + 1        # :27
+        full = np.nonzero(a <= M[:, 4])[0] + 1                                   # :28
+        partial = np.setdiff1d(np.nonzero(~a_unvig)[0] + 1, full)                # :29
+    return Vignetting(M, FOV, bool(np.all(a_unvig)), limit, partial, full)
+
+
 def wavegrad(eps, lam=LAMBDA):
     """wavegrad(eps::RealRayError, lambda) -- src/PupilSampling.jl:165-167"""
     return eps.x * eps.nu / lam, eps.y * eps.nu / lam

@@ -265,3 +265,46 @@ def tsa(surfaces, system, k_rays=22):
         y_XP[i] = ray.y[-1] + math.tan(ray.u[-1]) * XP_t
         eps_[i] = ray.y[-1] + math.tan(ray.u[-1]) * t
     return y_XP, eps_
+
+
+def _isapprox(x, y):
+    """Julia isapprox for Float64: rtol = sqrt(eps), atol = 0, elementwise"""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        return (x == y) | (np.isfinite(x) & np.isfinite(y) & (np.abs(x - y) <= EPS * np.maximum(np.abs(x), np.abs(y))))
+
+
+def _jl_minimum(v):
+    v = np.asarray(v, dtype=np.float64)
+    return np.nan if np.any(np.isnan(v)) else float(np.min(v))
+
+
+def vignetting(system, a=None):
+    """vignetting(system, a) -- src/Vignetting.jl:1-30.  Index lists are 1-based like the reference's findall."""
+    a = np.asarray(system.a if a is None else a, dtype=np.float64)
+    stop = system.stop
+    yb = np.abs(system.chief.y[1:-1])                     # :3
+    y = np.abs(system.marginal.y[1:-1])                   # :4
+    k = len(a)
+    M = np.empty((k, 5))
+    M[:, 0] = a
+    M[:, 1] = y
+    M[:, 2] = y + yb
+    M[:, 3] = yb
+    M[:, 4] = yb - y
+    with np.errstate(invalid="ignore", divide="ignore"):
+        M[M[:, 3] < y, 3] = np.nan                        # :12
+        M[M[:, 4] < y, 4] = np.nan                        # :13
+        a_unvig = (a >= M[:, 2]) | _isapprox(a, M[:, 2])  # :14
+        un = bool(np.all(a_unvig))
+        min_un = _jl_minimum([(a[i] - y[i]) / yb[i] for i in range(k) if i != stop - 1])    # :17
+        min_half = _jl_minimum(a / yb)                    # :18
+        min_full = _jl_minimum((a + y) / yb)              # :19
+        FOV = np.empty((3, 3))
+        for i, sc in enumerate((min_un, min_half, min_full)):
+            ub = abs(system.chief.u[0] * sc)
+            FOV[i] = (2 * (math.atan(ub) * (180.0 / math.pi)), ub, abs(system.chief.y[-1] * sc))   # :22-25
+        limit = np.nonzero((a < M[:, 1]) & ~_isapprox(a, M[:, 2]))[0] + 1                  # :27
+        full = np.nonzero(a <= M[:, 4])[0] + 1                                             # :28
+        partial = np.array([i for i in np.nonzero(~a_unvig)[0] + 1 if i not in set(full)], dtype=np.int64)   # :29
+    return NS(M=M, FOV=FOV, un=un, limit=limit, partial=partial, full=full)

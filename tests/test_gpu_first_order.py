@@ -145,6 +145,33 @@ def test_seidel_candidates(ctx, orc, ort):
     assert np.isnan(o2[1]).all() and not np.isnan(o2[0]).any()
 
 
+def test_vignetting_candidates(ctx, pre, ort):
+    """batched vignetting(system, a) == the CPU restatement per candidate: table and classification bit for bit,
+    FOV angles to the last ulp of atan"""
+    P = ort.prescriptions.COOKE
+    C = 300
+    RtnK = ort.prescriptions.perturbed_triplets(C)
+    RtnK[0] = np.vstack([P["surfaces"].T, np.zeros(8)])
+    a = np.asarray(P["a"])
+    for a_vig in (None, a * 0.93, np.array([14.7, 14.7, 10.8, 3.0, 10.3, 11.6, 30.0])):
+        r = ctx.vignetting_candidates(RtnK, a, P["h"], a_vig=a_vig)
+        for c in list(range(0, C, 37)) + [C - 1]:
+            so = pre.solve(RtnK[c, :3].T.copy(), a, P["h"])
+            o = pre.vignetting(so, a if a_vig is None else a_vig)
+            assert n_bits_differ(r["M"][c], o.M) == 0
+            assert n_bits_differ(r["FOV"][c][:, 1:], o.FOV[:, 1:]) == 0
+            assert np.max(np.abs(r["FOV"][c][:, 0] / o.FOV[:, 0] - 1)) < 1e-15
+            assert bool(r["un"][c]) == o.un and r["stop"][c] == so.stop and r["f"][c] == so.f
+            code = r["code"][c]
+            for bit, name in ((1, "limit"), (2, "partial"), (4, "full")):
+                assert list(np.nonzero(code & bit)[0] + 1) == list(getattr(o, name))
+    r = ctx.vignetting_candidates(RtnK[:1], a, P["h"])
+    assert list(np.nonzero(r["code"][0] & 2)[0] + 1) == [1, 2, 3, 6, 7]          # test/runtests.jl:243
+    bad = RtnK[:2].copy(); bad[1, 1, -1] = 3.0
+    r = ctx.vignetting_candidates(bad, a, P["h"])
+    assert np.isnan(r["M"][1]).all() and not np.isnan(r["M"][0][:, :3]).any()
+
+
 class _NoAim:
     """proxy that hides aim2d so the host runs its own secant loop (one 2-ray batch per step)"""
 

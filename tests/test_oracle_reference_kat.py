@@ -107,6 +107,24 @@ def test_vignetting_clip_threshold(system, orc):
     assert partial == COOKE["vignetting_partial"]
 
 
+def test_vignetting_analysis(system, pre):
+    """test/runtests.jl:241-250 on the restated vignetting(system, a): vig.partial == [1,2,3,6,7]; a system re-solved
+    at each of the three limiting image heights has some non-stop surface whose aperture equals (isapprox) the
+    matching column of its own table."""
+    vig = pre.vignetting(system, A)
+    assert list(vig.partial) == COOKE["vignetting_partial"] == [1, 2, 3, 6, 7]
+    assert list(vig.limit) == [] and list(vig.full) == [] and vig.un is False
+    idx = [i for i in range(len(A)) if i != system.stop - 1]
+    for i, hp in enumerate(vig.FOV[:, 2]):
+        M = pre.vignetting(pre.solve(S, A, hp)).M
+        assert np.any(pre._isapprox(A[idx], M[idx, i + 2]))
+    assert abs(vig.FOV[1, 0] / 2 - math.degrees(math.atan(vig.FOV[1, 1]))) < 1e-13
+    # an aperture stopped down below the marginal ray is "limit"; a wide-open one is unvignetted
+    small = A.copy(); small[0] = 10.0
+    assert list(pre.vignetting(system, small).limit) == [1]
+    assert pre.vignetting(system, A * 3).un is True
+
+
 def test_real_raytracing(system, pre, orc):
     """test/runtests.jl:260-286"""
     rt_par, _ = orc.paraxial_trace(system.tau, system.phi, 1.0, 0.0)
