@@ -197,11 +197,14 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
     }
 }
 
-template <int ARITH, bool EXT>
+// LEAN: the caller wants exactly the spot diagram and the mask (ex, ey, mask -- BASELINE config 2's 17 B per ray):
+// no per-pointer null tests, 32-bit indexing off per-field base pointers.
+template <int ARITH, bool EXT, bool LEAN>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
-                                             bool valid, size_t o, double cx, double cy, double co, RawAcc& acc)
+                                             bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc)
 {
+    const size_t o = fbase + idx;
     const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
     double ri = 0.0, r2 = 0.0;
     bool clip = false;
@@ -221,7 +224,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
         r2 = ri * ri;
-    } else if (A.r) {
+    } else if (!LEAN && A.r) {
         ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
     }
     const bool vig = EXT && (h.flags & ORT_FLAG_VIGN);
@@ -234,7 +237,17 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     const double ey = sv ? SS(h.yf, fld.h_prime) : h.yf - fld.h_prime;  // :134
     double opd = 0.0;
     if (EXT && (A.ext & ORT_EXT_OPD)) opd = sv ? SM(SS(h.opl, fld.opl_ref), A.opd_scale) : (h.opl - fld.opl_ref) * A.opd_scale;
-    if (valid) {
+    if (LEAN) {
+        if (valid) {
+            (A.ex + fbase)[idx] = ex; (A.ey + fbase)[idx] = ey; (A.mask + fbase)[idx] = (uint8_t)kept;
+            if (sv) {
+                acc.nstrict++;
+                acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
+                acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0);
+            }
+            acc.nflag_hi += clip ? 0x10000 : 0;
+        }
+    } else if (valid) {
         if (A.ex) A.ex[o] = ex;
         if (A.ey) A.ey[o] = ey;
         if (A.r) A.r[o] = ri;                                           // :136
@@ -263,7 +276,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     return kept;
 }
 
-template <int ARITH, int RPT, bool EXT>
+template <int ARITH, int RPT, bool EXT, bool LEAN = false>
 __global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? 2 : ORT_BPS2)) : 2)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
@@ -341,8 +354,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
-            const int kept = grid_epilogue<ARITH, EXT>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
-                                                       fbase + idx[j], cx, cy, co, acc);
+            const int kept = grid_epilogue<ARITH, EXT, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
+                                                             fbase, cx, cy, co, acc);
             if (A.tile_counts) {
                 const int c = __syncthreads_count(kept);
                 const unsigned sub = tile * RPT + j;
@@ -750,7 +763,9 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
 {
     const bool ext = A.ext != 0;
     if (arith == ORT_ARITH_FAST) {
+        const bool lean = !ext && A.ex && A.ey && A.mask && !A.r && !A.theta && !A.wx && !A.wy && !A.flags && !A.opd;
         if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false><<<grid, ORT_TILE, 0, st>>>(P, A);
     } else {
         if (ext) k_grid<ORT_ARITH_STRICT, 1, true><<<grid, ORT_TILE, 0, st>>>(P, A);
