@@ -269,7 +269,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         const double dx = ex - cx, dy = ey - cy;
         acc.s1x += dx; acc.s2x = fma(dx, dx, acc.s2x);
         acc.s1y += dy; acc.s2y = fma(dy, dy, acc.s2y);
-        acc.rmax = fmax(acc.rmax, (ARITH == ORT_ARITH_STRICT) ? ri : r2);
+        { const double rv = (ARITH == ORT_ARITH_STRICT) ? ri : r2; if (rv > acc.rmax) acc.rmax = rv; }   // kept rays: never NaN
         if (EXT) { const double dd = opd - co; acc.s1o += dd; acc.s2o = fma(dd, dd, acc.s2o); }
         acc.n++;
     }
@@ -289,6 +289,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     const unsigned ntiles = (nsub + RPT - 1) / RPT;
     const size_t fbase = (size_t)f * NN;
     const double* ysf = A.ys + (size_t)f * A.ys_stride;
+    const unsigned ysoff = (unsigned)f * (unsigned)A.ys_stride;      // n_fields * ny < 2^31
     const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
 
     RawAcc acc;
@@ -340,7 +341,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
             valid[j] = i0 < NN;
             idx[j] = valid[j] ? i0 : NN - 1;     // padded lanes re-trace the last ray: the warp stays convergent
             const unsigned iy = valid[j] ? iyj[j] : (unsigned)A.ny - 1, ix = valid[j] ? ixj[j] : nxu - 1;   // y outer, x inner (:123)
-            y0[j] = __ldg(ysf + iy); x0[j] = __ldg(A.xs + ix);
+            y0[j] = __ldg(A.ys + (ysoff + iy)); x0[j] = __ldg(A.xs + ix);      // 32-bit offsets: one IMAD.WIDE each
             if (collimated) { u[j] = fld.u; v[j] = fld.v; }
             else field_slopes(fld, y0[j], x0[j], u[j], v[j]);
             ixj[j] += dr; iyj[j] += dq;
@@ -579,7 +580,7 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
     S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
     S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
-    S.eq_thr = __double2hiint(isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : CUDART_INF); S.pad2_ = 0;
+    S.eq_thr = __double2hiint(isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : CUDART_INF); S.kcode = S.kind & 7;
     S.a = CUDART_INF; S.a2 = CUDART_INF;
 }
 

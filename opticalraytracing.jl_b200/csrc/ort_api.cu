@@ -105,7 +105,7 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     {
         const double eq = isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : INFINITY;   // |R| (1 - 2^-20)
         int64_t eb; memcpy(&eb, &eq, 8);
-        S.eq_thr = (int32_t)(eb >> 32); S.pad2_ = 0;
+        S.eq_thr = (int32_t)(eb >> 32); S.kcode = S.kind & 7;
     }
     S.a = INFINITY; S.a2 = INFINITY;
 }
