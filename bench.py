@@ -83,6 +83,12 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.002)
 
+    def reset(self):
+        self.samples, self.reasons = [], set()
+
+    def median_mhz(self):
+        return float(np.median(self.samples)) if self.samples else None
+
     def result(self):
         if self.nv is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
@@ -187,18 +193,21 @@ def _main(real_stdout):
     d_ex = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_ey = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_mask = torch.empty((nf, NN), dtype=torch.uint8, device=dev)
-    # statistics records are double-buffered so the all-gather of step k (NCCL's own stream) overlaps the
-    # trace of step k+1 (launching stream); a buffer is reused only after its gather has completed
-    d_stats2 = [torch.zeros((nf, SB), dtype=torch.uint8, device=dev) for _ in range(2)]
-    d_gather2 = [torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) for _ in range(2)] if n > 1 else None
+    # statistics records go through a ring of RING buffers so the all-gather of step k (NCCL's own stream) overlaps
+    # the traces of the following steps (launching stream); a buffer is reused only after its gather has completed.
+    # RING = 4: the persistent k_grid fills every SM, so a gather kernel may only find a free slot at a later kernel
+    # boundary; with four buffers in flight its latency and the inter-rank skew stay off the critical path.
+    RING = 4
+    d_stats2 = [torch.zeros((nf, SB), dtype=torch.uint8, device=dev) for _ in range(RING)]
+    d_gather2 = [torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) for _ in range(RING)] if n > 1 else None
     ptrs2 = [dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats2[b].data_ptr())
-             for b in range(2)]
+             for b in range(RING)]
     stream = torch.cuda.current_stream().cuda_stream
-    works = [None, None]
+    works = [None] * RING
     state = {"k": 0}
 
     def step():
-        b = state["k"] & 1
+        b = state["k"] % RING
         state["k"] += 1
         if works[b] is not None:
             works[b].wait()
@@ -208,7 +217,7 @@ def _main(real_stdout):
             works[b] = dist.all_gather_into_tensor(d_gather2[b].view(-1), d_stats2[b].view(-1), async_op=True)
 
     def drain():
-        for b in range(2):
+        for b in range(RING):
             if works[b] is not None:
                 works[b].wait()
                 works[b] = None
@@ -221,10 +230,13 @@ def _main(real_stdout):
     for _ in range(args.warmup):
         step()
     drain()
-    barrier()
-    ctx.profile_enable(True)
+    # everything with variable host latency (NVML init, thread start) happens BEFORE the barrier: ranks that leave the
+    # barrier skewed pay the skew back inside the timed region, waiting in the last gathers for the slowest one
     sampler = ClockSampler(local_rank)
     sampler.start()
+    ctx.profile_enable(True)
+    barrier()
+    sampler.reset()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -243,12 +255,21 @@ def _main(real_stdout):
     if n > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_step = float(t_ms.item()) / args.steps
+    # per-rank evidence for the scaling number: this rank's mean k_grid time, its own wall time per step and its
+    # median SM clock during the timed region, gathered to rank 0
+    mine = torch.tensor([float(np.mean(kern_ms)) if len(kern_ms) else 0.0, ms_total / args.steps,
+                         float(sampler.median_mhz() or 0.0)], dtype=torch.float64, device=dev)
+    per_rank = [mine]
+    if n > 1:
+        per_rank = [torch.zeros_like(mine) for _ in range(n)]
+        dist.all_gather(per_rank, mine)
+    per_rank = torch.stack(per_rank).cpu().numpy()
     rays_step = nf * NN * n
     inter_ray = ort.prescriptions.DOUBLE_GAUSS_GLASS_SURFACES
     value = rays_step * inter_ray / (ms_step * 1e-3)
 
     # statistics of the last step, merged across ranks in rank order (Chan) -- evidence, not timed
-    last = (state["k"] - 1) & 1
+    last = (state["k"] - 1) % RING
     d_stats = d_stats2[last]
     d_gather = d_gather2[last] if n > 1 else None
     stats = np.frombuffer((d_gather if n > 1 else d_stats.view(1, nf, SB)).cpu().numpy().tobytes(),
@@ -343,6 +364,9 @@ def _main(real_stdout):
                   "coordinates, cache-resident by design",
             "spot_rms_mm": [round(x, 9) for x in rms], "kept_rays": kept,
             "rays_retraced_strict": n_strict,
+            "per_rank": {"kernel_ms": [round(float(x), 4) for x in per_rank[:, 0]],
+                         "ms_per_step": [round(float(x), 4) for x in per_rank[:, 1]],
+                         "sm_mhz": [float(x) for x in per_rank[:, 2]]},
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms,
