@@ -197,9 +197,10 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
     }
 }
 
-// LEAN: the caller wants exactly the spot diagram and the mask (ex, ey, mask -- BASELINE config 2's 17 B per ray):
-// no per-pointer null tests, 32-bit indexing off per-field base pointers.
-template <int ARITH, bool EXT, bool LEAN>
+// LEAN = 1: the caller wants exactly the spot diagram and the mask (ex, ey, mask -- BASELINE config 2's 17 B per
+// ray): no per-pointer null tests, 32-bit indexing off per-field base pointers.  LEAN = 2: statistics only (config 3's
+// 0 B per ray): no stores at all.  LEAN = 0: any combination of outputs.
+template <int ARITH, bool EXT, int LEAN>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
                                              bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc)
@@ -239,7 +240,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     if (EXT && (A.ext & ORT_EXT_OPD)) opd = sv ? SM(SS(h.opl, fld.opl_ref), A.opd_scale) : (h.opl - fld.opl_ref) * A.opd_scale;
     if (LEAN) {
         if (valid) {
-            (A.ex + fbase)[idx] = ex; (A.ey + fbase)[idx] = ey; (A.mask + fbase)[idx] = (uint8_t)kept;
+            if (LEAN == 1) { (A.ex + fbase)[idx] = ex; (A.ey + fbase)[idx] = ey; (A.mask + fbase)[idx] = (uint8_t)kept; }
             if (sv) {
                 acc.nstrict++;
                 acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
@@ -276,7 +277,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     return kept;
 }
 
-template <int ARITH, int RPT, bool EXT, bool LEAN = false>
+template <int ARITH, int RPT, bool EXT, int LEAN = 0>
 __global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? 2 : ORT_BPS2)) : 2)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
@@ -764,9 +765,12 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
 {
     const bool ext = A.ext != 0;
     if (arith == ORT_ARITH_FAST) {
-        const bool lean = !ext && A.ex && A.ey && A.mask && !A.r && !A.theta && !A.wx && !A.wy && !A.flags && !A.opd;
+        const bool others = A.r || A.theta || A.wx || A.wy || A.flags || A.opd;
+        const bool lean = !ext && !others && A.ex && A.ey && A.mask;
+        const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
         if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
         else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false><<<grid, ORT_TILE, 0, st>>>(P, A);
     } else {
         if (ext) k_grid<ORT_ARITH_STRICT, 1, true><<<grid, ORT_TILE, 0, st>>>(P, A);

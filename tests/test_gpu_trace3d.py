@@ -63,6 +63,9 @@ def test_grid_fast_within_tolerance_mask_exact(ctx, orc, pre, ort, name, H):
                           arith=ort.FAST, want=("ex", "ey", "mask", "stats"))
     assert n_bits_differ(rl["ex"], r["ex"]) == 0 and n_bits_differ(rl["ey"], r["ey"]) == 0
     assert np.array_equal(rl["mask"], r["mask"]) and rl["stats"].tobytes() == r["stats"].tobytes()
+    ro = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop,
+                          arith=ort.FAST, want=("stats",))                      # statistics-only instantiation
+    assert ro["stats"].tobytes() == r["stats"].tobytes()
 
 
 def test_grid_multi_field_compact_and_stats(ctx, orc, pre, ort):
