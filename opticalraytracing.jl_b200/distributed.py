@@ -50,3 +50,31 @@ def sharded_sweep(backend, fields, ys_total, xs, stop, a_stop, rank, world, grou
     gathered = allgather_stats(res["stats"], group=group, device=device)
     merged = merged_field_stats(gathered)
     return res, merged, [rms_from_stats(m) for m in merged]
+
+
+def sharded_candidates(backend, RtnK, a, h_prime, H, k_rays=64, rank=0, world=1, group=None, device=None, arith=_lib.FAST,
+                       gather=True):
+    """BASELINE config 5 across ranks: candidates are independent, so every rank takes a contiguous range
+    [lo, hi) of the population (prescriptions replicated by the caller or sliced before the call) and runs the
+    per-candidate prelude + aimed sweep on it -- no data-path collective.  With gather=True the (C, 4) merit table
+    (n_kept, mean_x, mean_y, RMS; 32 B per candidate) is all-gathered so every rank can rank the whole population.
+    Returns (table, (lo, hi)): the full table when gathered, else this rank's rows."""
+    import torch
+    import torch.distributed as dist
+    RtnK = np.asarray(RtnK, dtype=np.float64)
+    C = RtnK.shape[0]
+    lo, hi = shard_rows(C, rank, world)
+    aim = backend.aim_candidates(RtnK[lo:hi], a, h_prime, H)
+    spot = backend.trace3d_candidates_aimed(RtnK[lo:hi], aim, int(k_rays), int(k_rays) // 2, arith=arith)
+    if not gather or world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return spot, (lo, hi)
+    per = -(-C // world)                                     # ranges differ by at most one row: pad to the longest
+    mine = torch.full((per, 4), float("nan"), dtype=torch.float64)
+    mine[:hi - lo] = torch.from_numpy(np.ascontiguousarray(spot))
+    if device is not None:
+        mine = mine.to(device)
+    out = torch.empty((world, per, 4), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
+    out = out.cpu().numpy()
+    table = np.concatenate([out[r, :shard_rows(C, r, world)[1] - shard_rows(C, r, world)[0]] for r in range(world)])
+    return table, (lo, hi)

@@ -71,3 +71,40 @@ def test_two_rank_sharded_sweep_matches_single():
         # concatenating the ranks' compacted outputs in rank order reproduces the reference's push! order
         cat = np.concatenate([out[0][4][f], out[1][4][f]])
         assert np.array_equal(cat, ref.x[:n])
+
+
+def _cand_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, HERE]
+    import torch.distributed as dist
+    import ort_b200 as ort
+    from oracle_backend import OracleBackend
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    P = ort.prescriptions.COOKE
+    RtnK = ort.prescriptions.perturbed_triplets(5)            # 5 candidates over 2 ranks: ragged ranges 3 + 2
+    table, rng = ort.distributed.sharded_candidates(OracleBackend(), RtnK, P["a"], P["h"], 0.7, 32, rank, world)
+    q.put((rank, table, rng))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_candidates():
+    """config 5 over 2 ranks: contiguous candidate ranges, no data-path collective, one all-gather of the merit table;
+    every rank ends with the same table as a single process."""
+    sys.path[:0] = [ROOT, HERE]
+    import ort_b200 as ort
+    from oracle_backend import OracleBackend
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cand_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    P = ort.prescriptions.COOKE
+    single, _ = ort.distributed.sharded_candidates(OracleBackend(), ort.prescriptions.perturbed_triplets(5), P["a"], P["h"],
+                                                   0.7, 32)
+    assert out[0][2] == (0, 3) and out[1][2] == (3, 5)
+    assert out[0][1].tobytes() == out[1][1].tobytes() == single.tobytes()
