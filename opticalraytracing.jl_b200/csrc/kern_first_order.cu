@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelAr
     const double EBFD = SM(y1, f);
     const double numk = SM(w1, s);                                   // marginal.nu[end]
     const double y_stop = SM(ys1, s), y2_stop = ys2;
-    const double ym1 = SM(1.0, s);                                   // marginal.y[1] = y at the first surface?  see below
+    const double ym1 = SM(1.0, s);                                   // marginal.y[begin]: the start height 1.0 scaled by s (:217)
     // ---- pass 2
     y1 = 1.0; w1 = 0.0; y2 = 0.0; w2 = 1.0;
     double W[7] = {0, 0, 0, 0, 0, 0, 0};

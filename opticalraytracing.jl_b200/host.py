@@ -816,11 +816,20 @@ def _isapprox(x, y):
         return (x == y) | (np.isfinite(x) & np.isfinite(y) & (np.abs(x - y) <= EPS * np.maximum(np.abs(x), np.abs(y))))
 
 
-def vignetting(system, a=None):
-    """vignetting(system::SystemOrRayBasis, a = system.a) -- src/Vignetting.jl:1-30.  O(k) host algebra on the two
-    paraxial rays the System already holds (like the tail of solve()); the population form, one thread per
-    candidate prescription, is Context.vignetting_candidates."""
+def vignetting(system, a=None, backend=None):
+    """vignetting(system::SystemOrRayBasis, a = system.a) -- src/Vignetting.jl:1-30.  For a System the table comes from
+    the candidate kernel (Context.vignetting_candidates, one candidate: the same first-order solve, bit for bit);
+    for a RayBasis (whose rays are not a solve() of a prescription) and for injected test backends it is O(k) host
+    algebra on the two paraxial rays the object already holds, like the tail of solve()."""
     a = np.asarray(system.a if a is None else a, dtype=np.float64)
+    be = _be(backend)                              # no GPU and no injected backend: raises, like every other entry
+    if isinstance(system, System) and hasattr(be, "vignetting_candidates"):
+        L = system.layout
+        RtnK = np.stack([L.R, L.t, L.n, L.K])[None]
+        r = be.vignetting_candidates(RtnK, system.a, float(system.chief.y[-1]), a_vig=a)
+        code = r["code"][0]
+        return Vignetting(r["M"][0], r["FOV"][0], bool(r["un"][0]), np.nonzero(code & 1)[0] + 1,
+                          np.nonzero(code & 2)[0] + 1, np.nonzero(code & 4)[0] + 1)
     yb = np.abs(system.chief.y[1:-1])
     y = np.abs(system.marginal.y[1:-1])
     M = np.column_stack([a, y, y + yb, yb, yb - y])

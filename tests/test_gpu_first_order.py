@@ -167,6 +167,11 @@ def test_vignetting_candidates(ctx, pre, ort):
                 assert list(np.nonzero(code & bit)[0] + 1) == list(getattr(o, name))
     r = ctx.vignetting_candidates(RtnK[:1], a, P["h"])
     assert list(np.nonzero(r["code"][0] & 2)[0] + 1) == [1, 2, 3, 6, 7]          # test/runtests.jl:243
+    # the single-system host entry runs the same kernel
+    system = ort.solve(P["surfaces"], a, P["h"], backend=ctx)
+    v = ort.vignetting(system, backend=ctx)
+    o = pre.vignetting(pre.solve(P["surfaces"], a, P["h"]))
+    assert n_bits_differ(v.M, o.M) == 0 and list(v.partial) == [1, 2, 3, 6, 7] and v.un == o.un
     bad = RtnK[:2].copy(); bad[1, 1, -1] = 3.0
     r = ctx.vignetting_candidates(bad, a, P["h"])
     assert np.isnan(r["M"][1]).all() and not np.isnan(r["M"][0][:, :3]).any()

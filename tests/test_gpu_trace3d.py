@@ -274,6 +274,47 @@ def test_candidates_aimed(ctx, orc, pre, ort, H):
     assert abs(math.sqrt(spot[0, 3] ** 2 + spot[0, 1] ** 2) / e.RMS - 1) < 1e-9
 
 
+@pytest.mark.parametrize("name,H,conic", [("DOUBLE_GAUSS", 1.0, False), ("DOUBLE_GAUSS", 0.5, False), ("TESSAR", 0.7, False),
+                                          ("SINGLET", 1.0, False), ("COOKE", 0.7, True), ("DOUBLE_GAUSS", 0.7, True)])
+def test_candidates_aimed_other_systems(ctx, orc, pre, ort, name, H, conic):
+    """the per-candidate prelude + aimed sweep on other prescriptions (12-row double-Gauss, Tessar, a singlet whose
+    stop is its first surface) and with conic surfaces (Layout{Aspheric}: K enters sag and tilt, the reversed chief-ray
+    layout carries reverse(K) shifted by one row, src/RayTracing.jl:272-274)"""
+    P = getattr(ort.prescriptions, name)
+    S = P["surfaces"][:, :3]
+    rows = S.shape[0]
+    rng = np.random.default_rng(11)
+    C = 6
+    RtnK = np.zeros((C, 4, rows))
+    for c in range(C):
+        RtnK[c, 0] = np.where(np.isfinite(S[:, 0]), S[:, 0] * (1 + rng.uniform(-0.01, 0.01, rows)), S[:, 0])
+        RtnK[c, 1] = S[:, 1] * (1 + rng.uniform(-0.005, 0.005, rows))
+        RtnK[c, 2] = S[:, 2]
+        if conic:
+            RtnK[c, 3] = np.where(np.isfinite(S[:, 0]), rng.uniform(-0.6, 0.3, rows), 0.0)
+            RtnK[c, 3, 0] = 0.0
+    aim = ctx.aim_candidates(RtnK, P["a"], P["h"], H, aspheric=conic)
+    assert np.all(aim[:, 11] == 0.0)
+    for c in range(C):
+        Sc, Kc = RtnK[c, :3].T.copy(), RtnK[c, 3].copy()
+        sysm = pre.solve(Sc, P["a"], P["h"])
+        p = pre.full_trace_inputs(sysm, H, 48, K=Kc if conic else None, aspheric=conic)
+        ref = np.array([p.y1, p.y2, p.y_EP, p.u, p.h_prime, p.focus, p.stop, p.a_stop, p.EP_t])
+        got = aim[c, :9]
+        assert got[6] == ref[6] and got[7] == ref[7] and got[5] == ref[5] and aim[c, 10] == sysm.f
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-9
+    for arith in (ort.STRICT, ort.FAST):
+        out = ctx.trace3d_candidates_aimed(RtnK, aim, 48, 24, arith=arith)
+        for c in range(C):
+            y1, y2, y_EP, u, hp, focus, stop, a_stop = aim[c, :8]
+            ext = np.concatenate([RtnK[c], np.array([[np.inf], [0.0], [1.0], [0.0]])], axis=1)
+            ext[1, -2] = focus
+            ref = orc.candidates(ext[None], np.linspace(y1, y2, 48), np.linspace(0.0, y_EP, 24), int(stop), a_stop, hp, u)[0]
+            assert out[c, 0] == ref[0] and ref[0] > 500
+            assert np.max(np.abs(out[c, 1:3] - ref[1:3])) / max(abs(hp), y_EP) < TOL
+            assert abs(out[c, 3] / ref[3] - 1) < 1e-9
+
+
 def test_candidates_aimed_failures(ctx, ort):
     """a candidate whose prelude cannot be completed gives NaN statistics and a status, never an error"""
     P = ort.prescriptions.COOKE
