@@ -84,7 +84,7 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
 // (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
 // (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
-template <int RPT, bool EXT, class SurfArray>
+template <int RPT, bool EXT, class SurfArray, bool MIRROR = true>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
@@ -104,10 +104,10 @@ __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int st
         }
     }
     int i = 0;
-    for (; i < stop; i++) fast_step<RPT, EXT>(S[i], r, vignette);
+    for (; i < stop; i++) fast_step<RPT, EXT, MIRROR>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
-    for (; i < nsurf; i++) fast_step<RPT, EXT>(S[i], r, vignette);
+    for (; i < nsurf; i++) fast_step<RPT, EXT, MIRROR>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         h[j].xf = r.x[j]; h[j].yf = r.y[j];
@@ -277,7 +277,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     return kept;
 }
 
-template <int ARITH, int RPT, bool EXT, int LEAN = 0>
+template <int ARITH, int RPT, bool EXT, int LEAN = 0, bool MIRROR = true>
 __global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? 2 : ORT_BPS2)) : 2)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
@@ -351,8 +351,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         Hit h[RPT];
         int amb[RPT];
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<RPT, EXT>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
-                                 collimated ? K0 : nullptr);
+            trace_fast<RPT, EXT, decltype(P.s), MIRROR>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
+                                                        collimated ? K0 : nullptr);
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
@@ -769,6 +769,9 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool lean = !ext && !others && A.ex && A.ey && A.mask;
         const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
         if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
         else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false><<<grid, ORT_TILE, 0, st>>>(P, A);

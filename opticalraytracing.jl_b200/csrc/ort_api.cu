@@ -266,6 +266,7 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
         if (Ri == 0.0 || isnan(Ri) || !isfinite(Ki) || !isfinite(t[i]) || !isfinite(n[i]) || !isfinite(n[i + 1]) ||
             n[i] == 0.0 || n[i + 1] == 0.0)
             P.fast_ok = 0;
+        if (!(n[i] > 0.0) || !(n[i + 1] > 0.0)) P.has_mirror = 1;      // reflection (n2 = -n1) or anything unusual
     }
     ctx->rows = rows;
     ctx->have_layout = true;
