@@ -598,10 +598,14 @@ k_candidates(CandArgs A)
     const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
     const double* Rc = A.RtnK + (size_t)c * 4 * rows;
     const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
+    __shared__ int s_mirror;
+    if (threadIdx.x == ORT_TILE - 2) s_mirror = 0;
+    __syncthreads();
     if (threadIdx.x < rows - 1) {
         const int i = threadIdx.x;
         derive_surface(s_surf[i], Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i],
                        Rc[2 * rows + i + 1]);
+        if (!(Rc[2 * rows + i] > 0.0) || !(Rc[2 * rows + i + 1] > 0.0)) atomicOr(&s_mirror, 1);   // a reflecting candidate
     } else if (AIMED && threadIdx.x == rows - 1) {
         derive_surface(s_surf[rows - 1], CUDART_INF, 0.0, rec[5], Rc[3 * rows - 1], 1.0);
     }
@@ -625,6 +629,7 @@ k_candidates(CandArgs A)
     }
     __syncthreads();
     const volatile double* par = s_par;
+    const bool mirror = s_mirror != 0;
     const int stop = s_stop;
     const bool ok = stop > 0;
 #define CAND_PAR(i, shared_grid_value) (AIMED ? par[i] : (shared_grid_value))
@@ -670,7 +675,10 @@ k_candidates(CandArgs A)
             uu[j] = 0.0; vv[j] = A.v;                           // the fast path takes the direction from K0
         }
         Hit h[RPT]; int amb[RPT];
-        if (ARITH == ORT_ARITH_FAST) trace_fast<RPT, false>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+        if (ARITH == ORT_ARITH_FAST) {      // CTA-uniform choice between the general and the no-mirror fast path
+            if (mirror) trace_fast<RPT, false, SurfK*, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+            else trace_fast<RPT, false, SurfK*, false>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+        }
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             double ri = 0.0, r2 = 0.0; bool clip = false;
