@@ -581,7 +581,11 @@ __device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, dou
     S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
     S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
     S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
-    S.eq_thr = __double2hiint(isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : CUDART_INF); S.kcode = S.kind & 7;
+    {
+        const int e = __double2hiint(isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : CUDART_INF);    // |R| (1 - 2^-20)
+        S.eq_thr = (R < 0.0) ? (int)(0x80000000u + (unsigned)(e - 1)) : e - 1;
+    }
+    S.kcode = S.kind & 7;
     S.a = CUDART_INF; S.a2 = CUDART_INF;
 }
 

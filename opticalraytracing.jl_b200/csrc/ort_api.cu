@@ -105,7 +105,9 @@ void derive_surface_host(SurfK& S, double R, double K, double t, double n1, doub
     {
         const double eq = isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : INFINITY;   // |R| (1 - 2^-20)
         int64_t eb; memcpy(&eb, &eq, 8);
-        S.eq_thr = (int32_t)(eb >> 32); S.kcode = S.kind & 7;
+        const int32_t e = (int32_t)(eb >> 32);
+        S.eq_thr = (R < 0.0) ? (int32_t)(0x80000000u + (uint32_t)(e - 1)) : e - 1;      // signed form, see SurfK
+        S.kcode = S.kind & 7;
     }
     S.a = INFINITY; S.a2 = INFINITY;
 }
