@@ -567,27 +567,6 @@ __device__ __forceinline__ Part acc_to_part(const Acc& a, bool rmax_is_squared)
 // ------------------------------------------------------------------------------------------
 // K5: candidate prescriptions, one CTA each, prescription staged in shared memory
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void derive_surface(SurfK& S, double R, double K, double t, double n1, double n2)
-{
-    S.R = R; S.K = K; S.t = t; S.n1 = n1; S.n2 = n2;
-    S.sgnR = (R < 0.0) ? -1.0 : ((R > 0.0) ? 1.0 : R);
-    S.c = isfinite(R) ? 1.0 / R : 0.0;
-    S.n1sq = n1 * n1;
-    S.cn1sq = S.c * S.n1sq;
-    S.dn2 = (n2 - n1) * (n2 + n1);
-    S.onepK = 1.0 + K;
-    S.kind = (!isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC)) | (n1 != n2 ? SURF_REFR : 0) |
-             (n2 < 0.0 ? SURF_N2NEG : 0);
-    S.tir_thr = __double2hiint(n2 * n2 * 9.313225746154785e-10);
-    S.gr_thr = __double2hiint(n1 * n1 * 9.313225746154785e-10);
-    S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
-    {
-        const int e = __double2hiint(isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : CUDART_INF);    // |R| (1 - 2^-20)
-        S.eq_thr = (R < 0.0) ? (int)(0x80000000u + (unsigned)(e - 1)) : e - 1;
-    }
-    S.kcode = S.kind & 7;
-    S.a = CUDART_INF; S.a2 = CUDART_INF;
-}
 
 // AIMED: every candidate carries its own prelude record (k_aim_candidates): stop, stop radius, field slope,
 // image height, focus (the image plane [Inf 0 1] is appended here, t[end-1] = focus, src/PupilSampling.jl:111-114)

@@ -84,33 +84,6 @@ int ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
     do { void* p_; int rc_ = ensure(ctx, (id), (bytes), &p_); if (rc_) return rc_; \
          (ptr) = (decltype(ptr))p_; } while (0)
 
-void derive_surface_host(SurfK& S, double R, double K, double t, double n1, double n2)
-{
-    S.R = R; S.K = K; S.t = t; S.n1 = n1; S.n2 = n2;
-    S.sgnR = (R < 0.0) ? -1.0 : ((R > 0.0) ? 1.0 : R);          // Julia sign()
-    S.c = isfinite(R) ? 1.0 / R : 0.0;
-    S.n1sq = n1 * n1;
-    S.cn1sq = S.c * S.n1sq;
-    S.dn2 = (n2 - n1) * (n2 + n1);
-    S.onepK = 1.0 + K;
-    S.kind = (!isfinite(R) ? SURF_PLANE : (K == 0.0 ? SURF_SPHERE : SURF_CONIC)) | (n1 != n2 ? SURF_REFR : 0) |
-             (n2 < 0.0 ? SURF_N2NEG : 0);
-    const double thr = n2 * n2 * 9.313225746154785e-10;         // 2^-30 n2^2
-    int64_t bits; memcpy(&bits, &thr, 8);
-    S.tir_thr = (int32_t)(bits >> 32);
-    const double thr1 = n1 * n1 * 9.313225746154785e-10;        // 2^-30 n1^2
-    memcpy(&bits, &thr1, 8);
-    S.gr_thr = (int32_t)(bits >> 32);
-    S.n2mask = (n2 < 0.0) ? (int32_t)0x80000000 : 0;
-    {
-        const double eq = isfinite(R) ? fabs(R) * (1.0 - 9.5367431640625e-07) : INFINITY;   // |R| (1 - 2^-20)
-        int64_t eb; memcpy(&eb, &eq, 8);
-        const int32_t e = (int32_t)(eb >> 32);
-        S.eq_thr = (R < 0.0) ? (int32_t)(0x80000000u + (uint32_t)(e - 1)) : e - 1;      // signed form, see SurfK
-        S.kcode = S.kind & 7;
-    }
-    S.a = INFINITY; S.a2 = INFINITY;
-}
 
 // bracket the dominant kernel with an event pair (measurement only)
 struct ProfScope {
@@ -160,7 +133,7 @@ int ort_init(ort_ctx** out, int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
-    snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+    snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
 #define CKI(call)                                                                                   \
     do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) {                                        \
              fail(nullptr, ORT_ECUDA, "ort_init: %s -> %s", #call, cudaGetErrorString(e2_));         \
@@ -264,7 +237,7 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
     P.nlast = n[rows - 1];
     for (int i = 0; i + 1 < rows; i++) {
         const double Ri = R[i + 1], Ki = K ? K[i + 1] : 0.0;
-        derive_surface_host(P.s[i], Ri, Ki, t[i], n[i], n[i + 1]);
+        derive_surface(P.s[i], Ri, Ki, t[i], n[i], n[i + 1]);
         if (Ri == 0.0 || isnan(Ri) || !isfinite(Ki) || !isfinite(t[i]) || !isfinite(n[i]) || !isfinite(n[i + 1]) ||
             n[i] == 0.0 || n[i + 1] == 0.0)
             P.fast_ok = 0;
