@@ -1,0 +1,75 @@
+"""Fuzz the FAST path against STRICT on the GPU: seeded random sequential systems (spheres, planes, conics, mirrors,
+cemented groups; tests/test_gpu_random_systems.random_system) and deliberately hostile ray bundles (large heights ->
+misses and near-equator hits, steep slopes -> TIR and grazing incidence).  STRICT is bit-identical to the CPU restatement
+of the reference (tests), so agreement here is agreement with the reference: flags and NaN patterns must be IDENTICAL,
+positions within 1e-12 of the position scale on well-conditioned rays (outliers are re-examined against the 80-bit oracle).
+usage: python tools/fuzz_fast_vs_strict.py [n_systems] [rays_per_system]  -> JSON summary on stdout"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
+
+import ort_b200 as ort
+from test_gpu_random_systems import random_system
+
+
+def main():
+    nsys = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+    ctx = ort.Context(0)
+    try:
+        from oracle import oracle as orc
+    except Exception:
+        orc = None
+    tot = dict(systems=nsys, rays=0, flag_mismatch=0, nan_mismatch=0, miss=0, tir=0, domain=0, finite=0, over_1e12=0,
+               over_1e12_well_conditioned=0, max_err=0.0, max_err_well_conditioned=0.0)
+    worst = []
+    for seed in range(nsys):
+        rng = np.random.default_rng(50000 + seed)
+        S = random_system(rng, mirrors=seed % 3 == 1, conics=seed % 2 == 1)
+        K = S[:, 3].copy()
+        hostile = seed % 4
+        h = (9.0, 25.0, 40.0, 15.0)[hostile]
+        sl = (0.12, 0.3, 0.15, 0.6)[hostile]
+        y0, x0 = rng.uniform(-h, h, N), rng.uniform(-h, h, N)
+        u0, v0 = rng.uniform(-sl, sl, N), rng.uniform(-sl, sl, N)
+        ctx.set_layout(S[:, :3], K)
+        xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+        xf, yf, kf, ff = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
+        tot["rays"] += N
+        tot["flag_mismatch"] += int(np.count_nonzero(fs != ff))
+        tot["nan_mismatch"] += int(np.count_nonzero(np.isnan(xs) != np.isnan(xf)) + np.count_nonzero(np.isnan(ys) != np.isnan(yf)))
+        tot["miss"] += int(np.count_nonzero(fs & ort.FLAG_MISS)); tot["tir"] += int(np.count_nonzero(fs & ort.FLAG_TIR))
+        tot["domain"] += int(np.count_nonzero(fs & ort.FLAG_DOMAIN))
+        with np.errstate(all="ignore"):
+            scale = np.maximum(np.nan_to_num(np.nanmax(np.abs(np.stack([xs, ys])), axis=(0, 1)), nan=1.0), 1.0)
+            e = np.maximum(np.nan_to_num(np.nanmax(np.abs(xf - xs), axis=0), nan=0.0),
+                           np.nan_to_num(np.nanmax(np.abs(yf - ys), axis=0), nan=0.0)) / scale
+        tot["finite"] += int(np.count_nonzero(~np.isnan(xs[-1])))
+        bad = np.nonzero(e > 1e-12)[0]
+        tot["over_1e12"] += len(bad)
+        tot["max_err"] = max(tot["max_err"], float(e.max()))
+        if len(bad) and orc is not None:          # is STRICT itself that far from the 80-bit truth on these rays?
+            xl, yl, _ = orc.trace3d_ld_batch(S[:, :3], y0[bad], x0[bad], u0[bad], v0[bad], K=K)
+            with np.errstate(all="ignore"):
+                cond = np.maximum(np.nan_to_num(np.nanmax(np.abs(xs[:, bad] - xl), axis=0), nan=0.0),
+                                  np.nan_to_num(np.nanmax(np.abs(ys[:, bad] - yl), axis=0), nan=0.0)) / scale[bad]
+                etrue = np.maximum(np.nan_to_num(np.nanmax(np.abs(xf[:, bad] - xl), axis=0), nan=0.0),
+                                   np.nan_to_num(np.nanmax(np.abs(yf[:, bad] - yl), axis=0), nan=0.0)) / scale[bad]
+            well = cond < 1e-13
+            tot["over_1e12_well_conditioned"] += int(np.count_nonzero(well))
+            for j in np.nonzero(etrue > 5e-13 + 2 * cond)[0]:
+                worst.append(dict(seed=seed, ray=int(bad[j]), err_vs_strict=float(e[bad[j]]), strict_vs_truth=float(cond[j]),
+                                  fast_vs_truth=float(etrue[j])))
+        ewell = e.copy(); ewell[bad] = 0.0
+        tot["max_err_well_conditioned"] = max(tot["max_err_well_conditioned"], float(ewell.max()))
+    tot["fast_worse_than_strict_vs_truth"] = worst[:20]
+    tot["n_fast_worse_than_strict_vs_truth"] = len(worst)
+    print(json.dumps(tot, indent=1))
+
+
+if __name__ == "__main__":
+    main()
