@@ -137,7 +137,7 @@ int ort_init(ort_ctx** out, int device)
 #define CKI(call)                                                                                   \
     do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) {                                        \
              fail(nullptr, ORT_ECUDA, "ort_init: %s -> %s", #call, cudaGetErrorString(e2_));         \
-             delete ctx; return ORT_ECUDA; } } while (0)
+             ort_free(ctx); return ORT_ECUDA; } } while (0)
     CKI(cudaSetDevice(device));
     CKI(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKI(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -157,14 +157,18 @@ int ort_init(ort_ctx** out, int device)
 void ort_free(ort_ctx* ctx)
 {
     if (!ctx) return;
+    // also the unwinding path of a failed ort_init: every handle may still be null
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < SL_COUNT; i++) if (ctx->slot[i]) cudaFree(ctx->slot[i]);
-    for (int i = 0; i < ORT_MAX_FIELDS; i++) cudaEventDestroy(ctx->ev_field[i]);
-    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
-    cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < ORT_MAX_FIELDS; i++) if (ctx->ev_field[i]) cudaEventDestroy(ctx->ev_field[i]);
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 2; j++) if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
