@@ -171,6 +171,11 @@ int ort_trace3d_rays(ort_ctx *ctx, int64_t N, const double *y0, const double *x0
 int ort_trace3d_rays_opl(ort_ctx *ctx, int64_t N, const double *y0, const double *x0,
                          const double *u0, const double *v0, int arith,
                          double *xv, double *yv, double *kout, uint8_t *flags, double *opl);
+/* device-pointer form (enqueue only on `stream`): rays and outputs already in HBM, layouts as above; any output
+ * pointer may be NULL */
+int ort_trace3d_rays_dev(ort_ctx *ctx, int64_t N, const double *d_y0, const double *d_x0, const double *d_u0,
+                         const double *d_v0, int arith, double *d_xv, double *d_yv, double *d_kout,
+                         uint8_t *d_flags, double *d_opl, void *stream);
 
 /* ---- 2-D meridional real-ray trace of N rays: replaces raytrace(surfaces, y, U, RealRay)
  *      src/RayTracing.jl:145-173.  aspheric = 1 is the Layout{Aspheric} method (:171-173: K from the

@@ -24,7 +24,7 @@ SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
     "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
     "ort_set_layout", "ort_set_apertures",
-    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace2d_batch", "ort_aim2d",
+    "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace3d_rays_dev", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev",
     "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_vignetting_candidates",
@@ -114,6 +114,7 @@ def load():
     L.ort_trace3d_grid_dev.argtypes = grid_args + [C.c_void_p]
     L.ort_trace3d_rays.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
     L.ort_trace3d_rays_opl.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p, _dp]
+    L.ort_trace3d_rays_dev.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 6
     L.ort_trace2d_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, C.c_int, _dp, _dp, _dp, _u8p]
     L.ort_aim2d.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp, _i32p]
     L.ort_paraxial_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int64,
@@ -355,6 +356,12 @@ class Context:
         self._ck(self.L.ort_trace3d_rays_opl(self.h, N, _p(y0), _p(x0), _p(u0), _p(v0), int(arith), _p(xv),
                                              _p(yv), _p(k), fl.ctypes.data_as(_u8p), _p(ol)))
         return xv, yv, k, fl, ol
+
+    def trace3d_rays_dev(self, N, d_y0, d_x0, d_u0, d_v0, d_xv=0, d_yv=0, d_k=0, d_flags=0, d_opl=0, arith=FAST, stream=0):
+        """device-pointer form of trace3d_rays: xv / yv are [rows-1][N], k is [3][N]; 0 = output not wanted"""
+        vp = lambda a: C.c_void_p(a or 0)
+        self._ck(self.L.ort_trace3d_rays_dev(self.h, int(N), vp(d_y0), vp(d_x0), vp(d_u0), vp(d_v0), int(arith), vp(d_xv),
+                                             vp(d_yv), vp(d_k), vp(d_flags), vp(d_opl), vp(stream)))
 
     def trace2d_batch(self, y0, U0, aspheric=False):
         y0, U0 = _d(y0), _d(U0)

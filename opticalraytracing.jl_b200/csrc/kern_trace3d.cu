@@ -759,7 +759,8 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool others = A.r || A.theta || A.wx || A.wy || A.flags || A.opd;
         const bool lean = !ext && !others && A.ex && A.ey && A.mask;
         const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
-        if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);

@@ -523,6 +523,27 @@ int ort_trace3d_rays_opl(ort_ctx* ctx, int64_t N, const double* y0, const double
     return ORT_OK;
 }
 
+int ort_trace3d_rays_dev(ort_ctx* ctx, int64_t N, const double* d_y0, const double* d_x0, const double* d_u0,
+                         const double* d_v0, int arith, double* d_xv, double* d_yv, double* d_kout, uint8_t* d_flags,
+                         double* d_opl, void* stream)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "trace3d_rays: call ort_set_layout first");
+    if (N < 0 || !d_y0 || !d_x0 || !d_u0 || !d_v0) return fail(ctx, ORT_EINVAL, "trace3d_rays: bad input");
+    if (arith != ORT_ARITH_STRICT && arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "trace3d_rays: arith = %d", arith);
+    if (N == 0) return ORT_OK;
+    CK(cudaSetDevice(ctx->device));
+    RaysArgs A; memset(&A, 0, sizeof A);
+    A.N = N; A.y0 = d_y0; A.x0 = d_x0; A.u0 = d_u0; A.v0 = d_v0;
+    A.xv = d_xv; A.yv = d_yv; A.kout = d_kout; A.flags = d_flags; A.opl = d_opl;
+    {
+        ProfScope prof(ctx, (cudaStream_t)stream);
+        CK(launch_rays(ctx->presc, A, resolve_arith(ctx, arith), (cudaStream_t)stream));
+    }
+    ctx->launches++;
+    return ORT_OK;
+}
+
 int ort_trace3d_rays(ort_ctx* ctx, int64_t N, const double* y0, const double* x0, const double* u0,
                      const double* v0, int arith, double* xv, double* yv, double* kout, uint8_t* flags)
 {

@@ -211,6 +211,28 @@ def test_three_d_equals_two_d(ctx, orc, ort):
         assert np.all(xv == 0.0)
 
 
+def test_rays_device_pointer_form(ctx, ort):
+    """ort_trace3d_rays_dev == ort_trace3d_rays, bit for bit"""
+    import torch
+    P = ort.prescriptions.DOUBLE_GAUSS
+    ctx.set_layout(P["surfaces"])
+    rng = np.random.default_rng(9)
+    N = 5000
+    y0, x0, u0, v0 = rng.uniform(-12, 12, N), rng.uniform(-12, 12, N), rng.uniform(-0.2, 0.2, N), rng.uniform(-0.2, 0.2, N)
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(a).to(dev) for a in (y0, x0, u0, v0)]
+    ns = P["surfaces"].shape[0] - 1
+    xv = torch.empty((ns, N), dtype=torch.float64, device=dev); yv = torch.empty_like(xv)
+    k = torch.empty((3, N), dtype=torch.float64, device=dev); fl = torch.empty(N, dtype=torch.uint8, device=dev)
+    for arith in (ort.STRICT, ort.FAST):
+        ctx.trace3d_rays_dev(N, *[t.data_ptr() for t in d], xv.data_ptr(), yv.data_ptr(), k.data_ptr(), fl.data_ptr(), arith=arith,
+                             stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        hx, hy, hk, hf = ctx.trace3d_rays(y0, x0, u0, v0, arith=arith)
+        assert n_bits_differ(xv.cpu().numpy(), hx) == 0 and n_bits_differ(yv.cpu().numpy(), hy) == 0
+        assert n_bits_differ(k.cpu().numpy(), hk) == 0 and np.array_equal(fl.cpu().numpy(), hf)
+
+
 def test_candidates(ctx, orc, pre, ort):
     P = ort.prescriptions.COOKE
     sysm = pre.solve(P["surfaces"], P["a"], P["h"])

@@ -75,6 +75,26 @@ def main():
     del v, vo, back, y0, w0, y, w, ci
     torch.cuda.empty_cache()
 
+    # ---- k_rays: arbitrary rays, every surface recorded (raytrace(surfaces, y, x, U, V, Vector{RealRay})), device-resident
+    Pg = ort.prescriptions.DOUBLE_GAUSS
+    ctx.set_layout(Pg["surfaces"])
+    NR = 1 << 24
+    gr = torch.Generator(device=dev); gr.manual_seed(3)
+    ry = torch.rand(NR, dtype=torch.float64, device=dev, generator=gr) * 20 - 10
+    rx = torch.rand(NR, dtype=torch.float64, device=dev, generator=gr) * 20 - 10
+    ru = torch.rand(NR, dtype=torch.float64, device=dev, generator=gr) * 0.2 - 0.1
+    rv = torch.rand(NR, dtype=torch.float64, device=dev, generator=gr) * 0.2 - 0.1
+    ns = Pg["surfaces"].shape[0] - 1
+    oxv = torch.empty((ns, NR), dtype=torch.float64, device=dev); oyv = torch.empty_like(oxv)
+    ok_ = torch.empty((3, NR), dtype=torch.float64, device=dev); ofl = torch.empty(NR, dtype=torch.uint8, device=dev)
+    for name, arith in (("fast", ort.FAST), ("strict", ort.STRICT)):
+        ms, best = timed(ctx, lambda: ctx.trace3d_rays_dev(NR, ry.data_ptr(), rx.data_ptr(), ru.data_ptr(), rv.data_ptr(), oxv.data_ptr(),
+                                                          oyv.data_ptr(), ok_.data_ptr(), ofl.data_ptr(), arith=arith, stream=st), reps=5, warm=2)
+        bytes_ray = 32 + ns * 16 + 24 + 1
+        out[f"rays_all_surfaces_{name}"] = {"rays": NR, "ms": ms, "rays_per_s": NR / ms * 1e3, "bytes_per_ray": bytes_ray,
+                                            "GBps": NR * bytes_ray / ms / 1e6, "hbm_frac": NR * bytes_ray / ms / 1e6 / HBM}
+    del ry, rx, ru, rv, oxv, oyv, ok_, ofl
+    torch.cuda.empty_cache()
     # ---- K5: candidates (config 5: C triplet variants x 4096 rays)
     C = int(float(sys.argv[2])) if len(sys.argv) > 2 else 65536
     p = ort.host._full_trace_setup(sysm.layout, sysm, [0.7], 64, None, ctx)
