@@ -278,7 +278,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
 }
 
 template <int ARITH, int RPT, bool EXT, int LEAN = 0, bool MIRROR = true>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? ORT_BPS2E : ORT_BPS2)) : 2)
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? ORT_BPS2E : ORT_BPS2)) : ORT_BPSS)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
     __shared__ RawPart s_part[ORT_TILE / 32];
