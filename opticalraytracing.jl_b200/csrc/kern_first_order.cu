@@ -263,6 +263,55 @@ __global__ void __launch_bounds__(256) k_transfer(TransferArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
+// First-order solve shared by the per-candidate kernels (k_seidel, k_vignetting, k_aim_candidates): Lens(surfaces)
+// src/RayTracing.jl:38-53 and the two fundamental paraxial rays (1, 0) and (0, 1) traced together :55-69, :127-143,
+// stop = argmin a ./ y and the marginal scale s :213-217.  Reference operation order throughout (never contracted),
+// so every kernel that starts from it holds the same bits as the CPU restatement.
+// ------------------------------------------------------------------------------------------
+struct FirstOrder {
+    double y1, w1, y2, w2;      // both rays after the last surface (unscaled)
+    double s;                   // min a[i] / y[i]: scale of the marginal ray
+    double ys1, ys2;            // both rays at the stop (unscaled)
+    double yfirst;              // ray 1 at the first surface (unscaled)
+    double zsum;                // cumsum of the real thicknesses t = tau .* n (Types.jl:41-46)
+    int stop;                   // 1-based
+};
+
+// one Lens row: (tau, phi) of surface i+1 from the candidate's R, t, n
+__device__ __forceinline__ void lens_row(const double* R, const double* t, const double* n, int i, double& tau, double& phi)
+{
+    double ti = t[i];
+    if (i == 0 && !isfinite(ti)) ti = 0.0;                           // :42
+    tau = SD(ti, n[i]);                                              // :43
+    phi = SD(SS(n[i + 1], n[i]), R[i + 1]);                          // :45
+}
+
+// transfer(y, w, tau) then refract(y, w, phi) for both fundamental rays (:55-69)
+__device__ __forceinline__ void lens_step(double tau, double phi, double& y1, double& w1, double& y2, double& w2)
+{
+    if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }     // :62
+    w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));                            // :67
+}
+
+__device__ __forceinline__ FirstOrder first_order(const double* R, const double* t, const double* n, int k, const double* a)
+{
+    FirstOrder o;
+    o.y1 = 1.0; o.w1 = 0.0; o.y2 = 0.0; o.w2 = 1.0;
+    o.s = CUDART_INF; o.ys1 = o.ys2 = o.yfirst = o.zsum = 0.0; o.stop = 1;
+    for (int i = 0; i < k; i++) {
+        double tau, phi;
+        lens_row(R, t, n, i, tau, phi);
+        const double tz = SM(tau, n[i]);
+        o.zsum = (i == 0) ? tz : SA(o.zsum, tz);
+        lens_step(tau, phi, o.y1, o.w1, o.y2, o.w2);
+        const double v = SD(a[i], o.y1);
+        if (i == 0) o.yfirst = o.y1;
+        if (i == 0 || v < o.s) { o.s = v; o.stop = i + 1; o.ys1 = o.y1; o.ys2 = o.y2; }     // findmin :215-216
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
 // K7: first-order solve + Seidel sums, one thread per candidate prescription.
 // Lens(surfaces) src/RayTracing.jl:38-53; trace_marginal_ray(lens, a) :208-221; trace_chief_ray(lens, ...)
 // :246-263; aberrations() src/SeidelAberrations.jl:6-53.  Two passes over the surfaces (the stop --
@@ -284,19 +333,10 @@ __global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelAr
         return;
     }
     // ---- pass 1
-    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
-    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0;
-    int stop = 1;
-    for (int i = 0; i < k; i++) {
-        double ti = t[i];
-        if (i == 0 && !isfinite(ti)) ti = 0.0;                       // :42
-        const double tau = SD(ti, n[i]);                             // :43
-        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);         // :45
-        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }     // :62
-        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));          // :67
-        const double v = SD(A.a[i], y1);
-        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }              // findmin :215-216
-    }
+    const FirstOrder fo = first_order(R, t, n, k, A.a);
+    double y1 = fo.y1, w1 = fo.w1, y2 = fo.y2, w2 = fo.w2;
+    const double s = fo.s, ys1 = fo.ys1, ys2 = fo.ys2;
+    const int stop = fo.stop;
     const double f = -SD(1.0, w1);                                   // :213
     const double EBFD = SM(y1, f);
     const double numk = SM(w1, s);                                   // marginal.nu[end]
@@ -307,13 +347,10 @@ __global__ void __launch_bounds__(128) k_seidel(const __grid_constant__ SeidelAr
     double W[7] = {0, 0, 0, 0, 0, 0, 0};
     double nub = 0.0, H = 0.0;
     for (int i = 0; i < k; i++) {
-        double ti = t[i];
-        if (i == 0 && !isfinite(ti)) ti = 0.0;
-        const double tau = SD(ti, n[i]);
-        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
+        double tau, phi;
+        lens_row(R, t, n, i, tau, phi);
         const double w1_prev = w1;
-        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
-        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        lens_step(tau, phi, y1, w1, y2, w2);
         const double ym = SM(y1, s);                                 // marginal y at surface i+1
         if (i == 0) {
             nub = SD(SM(-numk, A.h_prime), ym);                      // :256  -marginal.nu[end] * h' / y[1]
@@ -381,20 +418,10 @@ __global__ void __launch_bounds__(128) k_vignetting(const __grid_constant__ VigA
         return;
     }
     // ---- pass 1: stop, scale, marginal nu[end]
-    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
-    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0, yfirst = 0.0;
-    int stop = 1;
-    for (int i = 0; i < k; i++) {
-        double ti = t[i];
-        if (i == 0 && !isfinite(ti)) ti = 0.0;
-        const double tau = SD(ti, n[i]);
-        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
-        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
-        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
-        const double v = SD(A.a_solve[i], y1);
-        if (i == 0) yfirst = y1;
-        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }
-    }
+    const FirstOrder fo = first_order(R, t, n, k, A.a_solve);
+    double y1 = fo.y1, w1 = fo.w1, y2 = fo.y2, w2 = fo.w2;
+    const double s = fo.s, ys1 = fo.ys1, ys2 = fo.ys2, yfirst = fo.yfirst;
+    const int stop = fo.stop;
     const double f = -SD(1.0, w1);
     const double numk = SM(w1, s);
     const double nub = SD(SM(-numk, A.h_prime), SM(yfirst, s));
@@ -404,12 +431,9 @@ __global__ void __launch_bounds__(128) k_vignetting(const __grid_constant__ VigA
     double min_un = CUDART_INF, min_half = CUDART_INF, min_full = CUDART_INF;
     bool un = true, nan_un = false, nan_half = false, nan_full = false;
     for (int i = 0; i < k; i++) {
-        double ti = t[i];
-        if (i == 0 && !isfinite(ti)) ti = 0.0;
-        const double tau = SD(ti, n[i]);
-        const double phi = SD(SS(n[i + 1], n[i]), R[i + 1]);
-        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
-        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
+        double tau, phi;
+        lens_row(R, t, n, i, tau, phi);
+        lens_step(tau, phi, y1, w1, y2, w2);
         const double ym = SM(y1, s);
         const double yb = fabs(SM(nub, SS(y2, SD(SM(ym, ys2), y_stop))));     // |chief y|  (src/RayTracing.jl:258)
         const double y = fabs(ym);
@@ -526,22 +550,9 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     const double tl = V.t[rows - 1];
     if (!(tl == 0.0 || !isfinite(tl))) { out[11] = 8.0; return; }     // Lens() would keep the last row
     // ---- first-order solve: both fundamental rays (:209, :252), stop = argmin a ./ y (:215-216)
-    double y1 = 1.0, w1 = 0.0, y2 = 0.0, w2 = 1.0;
-    double s = CUDART_INF, ys1 = 0.0, ys2 = 0.0, yfirst = 0.0, zsum = 0.0;
-    int stop = 1;
-    for (int i = 0; i < k; i++) {
-        double ti = V.t[i];
-        if (i == 0 && !isfinite(ti)) ti = 0.0;
-        const double tau = SD(ti, V.n[i]);
-        const double phi = SD(SS(V.n[i + 1], V.n[i]), V.R[i + 1]);
-        const double tz = SM(tau, V.n[i]);                            // t = tau .* n, z = cumsum(t)  (Types.jl:41-46)
-        zsum = (i == 0) ? tz : SA(zsum, tz);
-        if (isfinite(tau)) { y1 = SA(y1, SM(w1, tau)); y2 = SA(y2, SM(w2, tau)); }
-        w1 = SS(w1, SM(y1, phi)); w2 = SS(w2, SM(y2, phi));
-        const double v = SD(A.a[i], y1);
-        if (i == 0) yfirst = y1;
-        if (i == 0 || v < s) { s = v; stop = i + 1; ys1 = y1; ys2 = y2; }
-    }
+    const FirstOrder fo = first_order(V.R, V.t, V.n, k, A.a);
+    const double y1 = fo.y1, w1 = fo.w1, w2 = fo.w2, s = fo.s, ys1 = fo.ys1, ys2 = fo.ys2, yfirst = fo.yfirst, zsum = fo.zsum;
+    const int stop = fo.stop;
     const double f = -SD(1.0, w1);
     const double nlast = V.n[rows - 1];
     const double ymk = SM(y1, s), numk = SM(w1, s);                   // marginal (y, nu) after the last surface
