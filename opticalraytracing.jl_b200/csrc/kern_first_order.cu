@@ -71,6 +71,49 @@ k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
 // (src/RayTracing.jl:223-240, 265-296; stop_loss :117-125) and of the edge-ray search
 // (src/PupilSampling.jl:67-83), one thread per solve, every function evaluation = a 2-D trace to the stop.
 // ------------------------------------------------------------------------------------------
+// The two root finders of the prelude, generic over the function evaluation `f(x)` = height at the stop surface of the
+// meridional ray parametrised by x (a functor: prescription in the constant bank for k_aim2d, in the candidate's RtnK
+// block for k_aim_candidates).  Returns the iteration count, negative when the iteration left the domain.
+//   secant_reference: x <- x - f eps / (f(x + eps) - f) until |f| <= tol, eps = sqrt(eps())   (src/RayTracing.jl:229-233, 282-286)
+//   secant_polish:    same step with a relative eps, run to the rounding floor (the roots of the reference's BFGS-on-abs,
+//                     src/PupilSampling.jl:67-83)
+template <class F>
+__device__ __forceinline__ int secant_reference(F f, double& x, double tgt, double tol, bool* finite = nullptr)
+{
+    const double eps = 1.4901161193847656e-08;                 // sqrt(eps())  src/RayTracing.jl:1
+    int it = 0;
+    double v = SS(f(x), tgt);
+    while (fabs(v) > tol) {                                     // :229, :282
+        if (++it > 100 || !isfinite(v)) return -(it + 1);
+        const double ve = SS(f(SA(x, eps)), tgt);
+        x = SS(x, SD(SM(v, eps), SS(ve, v)));                   // :231, :284
+        v = SS(f(x), tgt);
+    }
+    if (finite) *finite = isfinite(v);      // a NaN height ends the reference's `while abs(f) > atol` too (no error there)
+    return it;
+}
+
+template <class F>
+__device__ __forceinline__ int secant_polish(F f, double& x, double tgt, double scale)
+{
+    const double eps = 1.4901161193847656e-08;
+    double v_prev = 0.0;
+    int it = 0;
+    for (;; it++) {
+        if (it >= 60) break;
+        const double h = SM(eps, fmax(1.0, fabs(x)));
+        const double v = SS(f(x), tgt);
+        const double vh = SS(f(SA(x, h)), tgt);
+        if (!isfinite(v)) return -(it + 1);
+        bool done = fabs(v) <= SM(4e-16, scale);
+        if (it > 0) done = done || (fabs(v) >= fabs(v_prev) && fabs(v_prev) <= SM(1e-13, scale));
+        if (done) break;
+        x = SS(x, SD(SM(v, h), SS(vh, v)));
+        v_prev = v;
+    }
+    return it;
+}
+
 __device__ __forceinline__ double aim_eval(const Presc& P, const AimArgs& A, double x, double other)
 {
     double y = A.vary_u ? other : x, U = A.vary_u ? x : other, sprev = 0.0;
@@ -86,33 +129,10 @@ k_aim2d(const __grid_constant__ Presc P, AimArgs A)
     if (j >= A.N) return;
     double x = A.x0[j];
     const double other = A.other[j], tgt = A.target[j];
-    const double eps = 1.4901161193847656e-08;                 // sqrt(eps())  src/RayTracing.jl:1
-    int it = 0, status = 0;
-    if (A.mode == 0) {
-        double f = SS(aim_eval(P, A, x, other), tgt);
-        while (fabs(f) > A.tol) {                               // :229, :282
-            if (++it > 100 || !isfinite(f)) { status = -1; break; }
-            const double fe = SS(aim_eval(P, A, SA(x, eps), other), tgt);
-            x = SS(x, SD(SM(f, eps), SS(fe, f)));               // :231, :284
-            f = SS(aim_eval(P, A, x, other), tgt);
-        }
-    } else {
-        double f_prev = 0.0;
-        for (;; it++) {
-            if (it >= 60) break;
-            const double h = SM(eps, fmax(1.0, fabs(x)));
-            const double f = SS(aim_eval(P, A, x, other), tgt);
-            const double fh = SS(aim_eval(P, A, SA(x, h), other), tgt);
-            if (!isfinite(f)) { status = -1; break; }
-            bool done = fabs(f) <= SM(4e-16, A.tol);
-            if (it > 0) done = done || (fabs(f) >= fabs(f_prev) && fabs(f_prev) <= SM(1e-13, A.tol));
-            if (done) break;
-            x = SS(x, SD(SM(f, h), SS(fh, f)));
-            f_prev = f;
-        }
-    }
+    auto f = [&](double xx) { return aim_eval(P, A, xx, other); };
+    const int it = (A.mode == 0) ? secant_reference(f, x, tgt, A.tol) : secant_polish(f, x, tgt, A.tol);
     A.x_out[j] = x;
-    if (A.iters) A.iters[j] = status < 0 ? -(it + 1) : it;
+    if (A.iters) A.iters[j] = it;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -500,44 +520,6 @@ __device__ __noinline__ double cand_height(const CandView& V, int upto, int asph
     return y;
 }
 
-// the reference's secant loop (:229-233, :282-286): x <- x - f eps / (f(x + eps) - f), until |f| <= tol
-template <bool REV, bool VARY_U>
-__device__ __forceinline__ bool cand_secant0(const CandView& V, int upto, int aspheric, double& x, double other,
-                                             double tgt, double tol)
-{
-    const double eps = 1.4901161193847656e-08;
-    double f = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, x) : cand_height<REV>(V, upto, aspheric, x, other), tgt);
-    int it = 0;
-    while (fabs(f) > tol) {
-        if (++it > 100 || !isfinite(f)) return false;
-        const double xe = SA(x, eps);
-        const double fe = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, xe) : cand_height<REV>(V, upto, aspheric, xe, other), tgt);
-        x = SS(x, SD(SM(f, eps), SS(fe, f)));
-        f = SS(VARY_U ? cand_height<REV>(V, upto, aspheric, other, x) : cand_height<REV>(V, upto, aspheric, x, other), tgt);
-    }
-    return isfinite(f);
-}
-
-// root polish of the edge rays (same iteration as k_aim2d mode 1)
-__device__ __forceinline__ bool cand_polish(const CandView& V, int upto, int aspheric, double& x, double U, double tgt,
-                                            double scale)
-{
-    const double eps = 1.4901161193847656e-08;
-    double f_prev = 0.0;
-    for (int it = 0; it < 60; it++) {
-        const double h = SM(eps, fmax(1.0, fabs(x)));
-        const double f = SS(cand_height<false>(V, upto, aspheric, x, U), tgt);
-        const double fh = SS(cand_height<false>(V, upto, aspheric, SA(x, h), U), tgt);
-        if (!isfinite(f)) return false;
-        bool done = fabs(f) <= SM(4e-16, scale);
-        if (it > 0) done = done || (fabs(f) >= fabs(f_prev) && fabs(f_prev) <= SM(1e-13, scale));
-        if (done) break;
-        x = SS(x, SD(SM(f, h), SS(fh, f)));
-        f_prev = f;
-    }
-    return true;
-}
-
 __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ AimCandArgs A)
 {
     const long long c = (long long)blockIdx.x * 64 + threadIdx.x;
@@ -568,7 +550,8 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     const double ybp = A.h_prime;
     double ubp = -SD(nuck, nlast);
     const int rstop = rows - stop;
-    if (!cand_secant0<true, true>(V, rstop, 1, ubp, ybp, 0.0, tol)) status |= 1;
+    bool fin = true;
+    if (secant_reference([&](double uu) { return cand_height<true>(V, rstop, 1, ybp, uu); }, ubp, 0.0, tol, &fin) < 0 || !fin) status |= 1;
     double EP_t, Ubar;
     {
         double y = ybp, U = ubp, sprev = 0.0, csum = 0.0; unsigned fl = 0;
@@ -584,14 +567,15 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     }
     // ---- real marginal ray (:223-240)
     double ym = SM(1.0, s);
-    if (!cand_secant0<false, false>(V, stop, A.aspheric, ym, 0.0, a_stop_signed, tol)) status |= 2;
+    if (secant_reference([&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, 0.0); }, ym, a_stop_signed, tol, &fin) < 0 || !fin) status |= 2;
     const double y_EP = fabs(ym);
     // ---- field point and edge rays (src/PupilSampling.jl:92-100)
     const double U = SM(fabs(A.H), Ubar);
     const double u = tan(U);
     double e1 = SS(y_EP, SM(u, EP_t)), e2 = SS(-y_EP, SM(u, EP_t));
-    if (!cand_polish(V, stop, A.aspheric, e1, U, a_stop, a_stop)) status |= 4;
-    if (!cand_polish(V, stop, A.aspheric, e2, U, -a_stop, a_stop)) status |= 4;
+    auto edge = [&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, U); };
+    if (secant_polish(edge, e1, a_stop, a_stop) < 0) status |= 4;
+    if (secant_polish(edge, e2, -a_stop, a_stop) < 0) status |= 4;
     out[0] = e1; out[1] = e2; out[2] = y_EP; out[3] = u; out[4] = SM(u, f); out[5] = bfd;
     out[6] = (double)stop; out[7] = a_stop; out[8] = EP_t; out[9] = Ubar; out[10] = f; out[11] = (double)status;
     out[12] = numk; out[13] = U; out[14] = 0.0; out[15] = 0.0;     // 14..23: k_aim_edges
