@@ -16,7 +16,50 @@ import ort_b200 as ort
 from test_gpu_random_systems import random_system
 
 
+def grid_mode(nsys):
+    """FAST vs STRICT through the grid kernel: random systems, random stop surface and radius, collimated and finite-object
+    fields, every output-set instantiation (generic / spot + mask / statistics only): masks, flags and counts identical."""
+    ctx = ort.Context(0)
+    tot = dict(mode="grid", systems=nsys, rays=0, mask_mismatch=0, flag_mismatch=0, count_mismatch=0, lean_mismatch=0,
+               stats_only_mismatch=0, max_err=0.0, kept=0, strict_retraced=0)
+    for seed in range(nsys):
+        rng = np.random.default_rng(70000 + seed)
+        S = random_system(rng, mirrors=seed % 3 == 1, conics=seed % 2 == 1)
+        K = np.append(S[:, 3], 0.0)
+        ext = np.vstack([S[:, :3], [np.inf, 0.0, S[-1, 2]]])
+        ext[-2, 1] = rng.uniform(20.0, 80.0) * np.sign(S[-1, 2])
+        stop = int(rng.integers(1, ext.shape[0] - 1))
+        a_stop = rng.uniform(3.0, 12.0)
+        ny, nx = int(rng.integers(40, 90)), int(rng.integers(20, 50))
+        ys, xs = np.linspace(-14, 14, ny), np.linspace(0, 14, nx)
+        if seed % 4 == 3:
+            fld = dict(mode=1, ybar=float(rng.uniform(-20, 20)), z0=float(-rng.uniform(150, 600)), h_prime=0.3)
+        else:
+            fld = dict(u=float(rng.uniform(-0.2, 0.2)), v=float(rng.uniform(-0.05, 0.05)), h_prime=0.3)
+        ctx.set_layout(ext, K)
+        want = ("ex", "ey", "r", "theta", "mask", "flags", "stats")
+        rs = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.STRICT, want=want)
+        rf = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.FAST, want=want)
+        rl = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.FAST, want=("ex", "ey", "mask", "stats"))
+        ro = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.FAST, want=("stats",))
+        tot["rays"] += ny * nx
+        tot["mask_mismatch"] += int(np.count_nonzero(rs["mask"] != rf["mask"]))
+        tot["flag_mismatch"] += int(np.count_nonzero(rs["flags"] != rf["flags"]))
+        tot["count_mismatch"] += int(rs["stats"]["n_kept"][0] != rf["stats"]["n_kept"][0])
+        tot["lean_mismatch"] += int(np.count_nonzero(rl["mask"] != rf["mask"])) + int(rl["stats"].tobytes() != rf["stats"].tobytes())
+        tot["stats_only_mismatch"] += int(ro["stats"].tobytes() != rf["stats"].tobytes())
+        tot["kept"] += int(rs["stats"]["n_kept"][0]); tot["strict_retraced"] += int(rf["stats"]["n_strict"][0])
+        m = rs["mask"][0].astype(bool)
+        if m.any():
+            sc = max(np.abs(rs["ex"][0][m]).max(), np.abs(rs["ey"][0][m]).max(), 10.0)
+            tot["max_err"] = max(tot["max_err"], float(np.abs(rf["ex"][0][m] - rs["ex"][0][m]).max() / sc),
+                                 float(np.abs(rf["ey"][0][m] - rs["ey"][0][m]).max() / sc))
+    print(json.dumps(tot, indent=1))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "grid":
+        return grid_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 300)
     nsys = int(sys.argv[1]) if len(sys.argv) > 1 else 400
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     ctx = ort.Context(0)
