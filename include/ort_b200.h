@@ -247,6 +247,10 @@ int ort_aim_candidates(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, co
                        double H, int aspheric, double *out);
 int ort_aim_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a /* host */,
                            double h_prime, double H, int aspheric, double *d_out, void *stream);
+/* The same prelude for ONE system at n_fields relative fields Hs[] (<= ORT_MAX_FIELDS), i.e. src/PupilSampling.jl:85-108 of
+ * a field sweep in one call (two launches): R, t, n, K are the rows of the Layout (K may be NULL), out[n_fields][24]. */
+int ort_aim_fields(ort_ctx *ctx, int rows, const double *R, const double *t, const double *n, const double *K,
+                   const double *a, double h_prime, const double *Hs, int n_fields, int aspheric, double *out);
 int ort_trace3d_candidates_aimed(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *aim, int ny,
                                  int nx, int arith, double *out);
 int ort_trace3d_candidates_aimed_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *d_aim,

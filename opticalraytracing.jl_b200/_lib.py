@@ -26,7 +26,7 @@ SYMBOLS = [
     "ort_set_layout", "ort_set_apertures",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace3d_rays_dev", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
-    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev",
+    "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev", "ort_aim_fields",
     "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_vignetting_candidates",
     "ort_vignetting_candidates_dev", "ort_seidel_candidates",
     "ort_seidel_candidates_dev", "ort_merge_stats", "ort_rms_from_stats", "ort_fp64_peak",
@@ -137,6 +137,7 @@ def load():
     L.ort_vignetting_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, _dp, C.c_double, C.c_void_p,
                                                 C.c_void_p]
     L.ort_aim_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
+    L.ort_aim_fields.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_int, C.c_int, _dp]
     L.ort_aim_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]
     L.ort_trace3d_candidates_aimed.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]
@@ -478,6 +479,17 @@ class Context:
         out = np.empty((Cn, AIM_NOUT), dtype=np.float64)
         self._ck(self.L.ort_aim_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(H), int(bool(aspheric)),
                                            _p(out)))
+        return out
+
+    def aim_fields(self, surfaces, K, a, h_prime, Hs, aspheric=False):
+        """full_trace prelude of ONE system at the relative fields Hs -> (n_fields, 24) records (ort_aim_fields)"""
+        S = _d(surfaces)
+        R, t, n = _d(S[:, 0]), _d(S[:, 1]), _d(S[:, 2])
+        Kc = None if K is None else _d(K)
+        a, Hs = _d(a), _d(np.atleast_1d(Hs))
+        out = np.empty((len(Hs), AIM_NOUT), dtype=np.float64)
+        self._ck(self.L.ort_aim_fields(self.h, len(R), _p(R), _p(t), _p(n), _p(Kc), _p(a), float(h_prime), _p(Hs), len(Hs),
+                                       int(bool(aspheric)), _p(out)))
         return out
 
     def aim_candidates_dev(self, rows, Cn, d_RtnK, a, h_prime, H, d_out, aspheric=False, stream=0):

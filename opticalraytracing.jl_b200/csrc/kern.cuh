@@ -75,6 +75,8 @@ struct AimCandArgs {
     double a[ORT_MAX_ROWS];
     double h_prime, H;
     int aspheric;
+    int n_fields;                           // > 0: ONE prescription (RtnK[0]) at n_fields relative fields Hs[] (C == n_fields)
+    double Hs[ORT_MAX_FIELDS];
     double* out;                            // [C][ORT_AIM_NOUT]
 };
 
@@ -139,7 +141,7 @@ cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);
 cudaError_t launch_seidel(const SeidelArgs& A, cudaStream_t st);
 cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st);
 cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st);
-cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, cudaStream_t st);
+cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, int shared_prescription, cudaStream_t st);
 cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
                              long long* dfma_per_launch);

@@ -526,7 +526,9 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     if (c >= A.C) return;
     const int rows = A.rows, k = rows - 1;
     CandView V;
-    V.R = A.RtnK + (size_t)c * 4 * rows; V.t = V.R + rows; V.n = V.t + rows; V.K = V.n + rows; V.rows = rows; V.bfd = 0.0;
+    V.R = A.RtnK + (A.n_fields > 0 ? 0 : (size_t)c * 4 * rows);       // fields of one system share its prescription
+    V.t = V.R + rows; V.n = V.t + rows; V.K = V.n + rows; V.rows = rows; V.bfd = 0.0;
+    const double Hrel = A.n_fields > 0 ? A.Hs[c] : A.H;
     double* out = A.out + (size_t)c * ORT_AIM_NOUT;
     for (int j = 0; j < ORT_AIM_NOUT; j++) out[j] = CUDART_NAN;
     const double tl = V.t[rows - 1];
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     if (secant_reference([&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, 0.0); }, ym, a_stop_signed, tol, &fin) < 0 || !fin) status |= 2;
     const double y_EP = fabs(ym);
     // ---- field point and edge rays (src/PupilSampling.jl:92-100)
-    const double U = SM(fabs(A.H), Ubar);
+    const double U = SM(fabs(Hrel), Ubar);
     const double u = tan(U);
     double e1 = SS(y_EP, SM(u, EP_t)), e2 = SS(-y_EP, SM(u, EP_t));
     auto edge = [&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, U); };

@@ -707,7 +707,7 @@ struct CandSurfGen {
     }
 };
 
-__global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const double* RtnK, double* aim)
+__global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const double* RtnK, double* aim, int shared)
 {
     const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
     const long long c = t >> 1;
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const 
     const bool good = rec[11] == 0.0 && stop >= 1 && stop <= rows - 1;
     double* o = rec + 16 + 4 * e;
     if (!good) { if (e == 0) { rec[14] = 0.0; rec[15] = 0.0; } o[0] = o[1] = o[2] = o[3] = CUDART_NAN; return; }
-    CandSurfGen gen; gen.Rc = RtnK + (size_t)c * 4 * rows; gen.rows = rows; gen.focus = rec[5];
+    CandSurfGen gen; gen.Rc = RtnK + (shared ? 0 : (size_t)c * 4 * rows); gen.rows = rows; gen.focus = rec[5];
     const Hit h = trace_strict<false>(gen, rows, stop, rec[e], 0.0, rec[3], 0.0);
     const double ri = jl_hypot(h.xs, h.ys);
     const bool drop = ri > rec[7] || is_nan_bits(h.xf) || is_nan_bits(h.yf);
@@ -726,10 +726,10 @@ __global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const 
     if (e == 0) { rec[14] = 1.0; rec[15] = 0.0; }
 }
 
-cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, cudaStream_t st)
+cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, int shared_prescription, cudaStream_t st)
 {
     if (C == 0) return cudaSuccess;
-    k_aim_edges<<<(unsigned)((2 * C + 127) / 128), 128, 0, st>>>(rows, C, RtnK, aim);
+    k_aim_edges<<<(unsigned)((2 * C + 127) / 128), 128, 0, st>>>(rows, C, RtnK, aim, shared_prescription);
     return cudaGetLastError();
 }
 

@@ -826,7 +826,7 @@ int ort_aim_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* d_Rt
     {
         ProfScope prof(ctx, (cudaStream_t)stream);
         CK(launch_aim_candidates(A, (cudaStream_t)stream));
-        CK(launch_aim_edges(rows, C, d_RtnK, d_out, (cudaStream_t)stream));
+        CK(launch_aim_edges(rows, C, d_RtnK, d_out, 0, (cudaStream_t)stream));
     }
     if (C > 0) ctx->launches += 2;
     return ORT_OK;
@@ -846,6 +846,37 @@ int ort_aim_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, co
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     int rc = ort_aim_candidates_dev(ctx, rows, C, d_p, a, h_prime, H, aspheric, d_o, st);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_o, no, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
+int ort_aim_fields(ort_ctx* ctx, int rows, const double* R, const double* t, const double* n, const double* K,
+                   const double* a, double h_prime, const double* Hs, int n_fields, int aspheric, double* out)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (rows < 2 || rows > ORT_MAX_ROWS - 1) return fail(ctx, ORT_EINVAL, "aim_fields: rows = %d", rows);
+    if (!R || !t || !n || !a || !Hs || !out) return fail(ctx, ORT_EINVAL, "aim_fields: bad input");
+    if (n_fields < 1 || n_fields > ORT_MAX_FIELDS) return fail(ctx, ORT_EINVAL, "aim_fields: n_fields = %d not in [1, %d]", n_fields, ORT_MAX_FIELDS);
+    for (int f = 0; f < n_fields; f++)
+        if (!(fabs(Hs[f]) <= 1.0)) return fail(ctx, ORT_EINVAL, "aim_fields: DomainError |H| <= 1");       // src/PupilSampling.jl:88-89
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)4 * rows * 8, no = (size_t)n_fields * ORT_AIM_NOUT * 8;
+    double *d_p, *d_o;
+    ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT1, no, d_o);
+    double h_p[4 * ORT_MAX_ROWS];
+    for (int i = 0; i < rows; i++) { h_p[i] = R[i]; h_p[rows + i] = t[i]; h_p[2 * rows + i] = n[i]; h_p[3 * rows + i] = K ? K[i] : 0.0; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_p, h_p, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                  // h_p is a stack buffer
+    AimCandArgs A; memset(&A, 0, sizeof A);
+    A.rows = rows; A.C = n_fields; A.RtnK = d_p; A.h_prime = h_prime; A.aspheric = aspheric; A.out = d_o;
+    A.n_fields = n_fields;
+    for (int f = 0; f < n_fields; f++) A.Hs[f] = Hs[f];
+    for (int i = 0; i + 1 < rows; i++) A.a[i] = a[i];
+    CK(launch_aim_candidates(A, st));
+    CK(launch_aim_edges(rows, n_fields, d_p, d_o, 1, st));
+    ctx->launches += 2;
     CK(cudaMemcpyAsync(out, d_o, no, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORT_OK;

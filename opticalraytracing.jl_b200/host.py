@@ -511,6 +511,21 @@ def _full_trace_setup(surfaces, system, H, k_rays, focus, backend):
         focus = system.marginal.z[-1] - system.marginal.z[-2]                    # :87
     stop = system.stop
     a_stop = abs(system.a[stop - 1])
+    be = _be(backend)
+    if isinstance(system, System) and hasattr(be, "aim_fields"):
+        # the whole prelude (:90-108) for all fields in one call: first-order solve, reversed real chief ray, real
+        # marginal ray and both edge rays per field on the device (k_aim_candidates, one thread per field).  Used only
+        # when it reproduces the System it was handed (same stop, focal length and marginal nu, bit for bit).
+        rec = be.aim_fields(layout.M3, layout.K, system.a, float(system.chief.y[-1]), Hs, aspheric=layout.aspheric)
+        if (np.all(rec[:, 11] == 0.0) and int(rec[0, 6]) == stop and rec[0, 10] == system.f
+                and rec[0, 12] == system.marginal.nu[-1]):
+            ext = np.vstack([layout.M3, [np.inf, 0.0, 1.0]])                     # :111
+            Kx = np.append(layout.K, 0.0)                                        # :112
+            ext[-2, 1] = focus                                                   # :114
+            return dict(ext=ext, K=Kx, Hs=Hs, U=rec[:, 13].copy(), u=rec[:, 3].copy(), y1=rec[:, 0].copy(),
+                        y2=rec[:, 1].copy(), y_EP=float(rec[0, 2]), EP_t=float(rec[0, 8]), h_prime=rec[:, 4].copy(),
+                        stop=stop, a_stop=a_stop, focus=focus, z0=None, ybar=None, k_rays=k_rays,
+                        nu=system.marginal.nu[-1])
     # full_trace is reached with surfaces::Layout (:85), so trace_chief_ray takes its Layout branch
     real_chief = trace_chief_ray(layout, system, backend=backend)
     real_marginal = trace_marginal_ray(layout, system, backend=backend)

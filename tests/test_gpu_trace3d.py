@@ -211,6 +211,40 @@ def test_three_d_equals_two_d(ctx, orc, ort):
         assert np.all(xv == 0.0)
 
 
+class _NoAimFields:
+    """proxy that hides aim_fields so the host runs its own prelude (solve-consistent secant loops, several launches)"""
+
+    def __init__(self, ctx):
+        self._c = ctx
+
+    def __getattr__(self, name):
+        if name == "aim_fields":
+            raise AttributeError(name)
+        return getattr(self._c, name)
+
+
+@pytest.mark.parametrize("name", ["COOKE", "DOUBLE_GAUSS", "TESSAR", "SINGLET"])
+def test_one_call_prelude_equals_host_prelude(ctx, ort, name):
+    """ort_aim_fields (the whole full_trace prelude of a field sweep in one call) against the host prelude that drives
+    k_paraxial / k_aim2d / k_trace2d step by step: the same device arithmetic, so the aimed quantities agree to the last
+    bits, and the spot they lead to is the same"""
+    P = getattr(ort.prescriptions, name)
+    system = ort.solve(P["surfaces"], P["a"], P["h"], backend=ctx)
+    Hs = [0.0, 0.5, 1.0]
+    pa = ort.host._full_trace_setup(system.layout, system, Hs, 64, None, ctx)
+    pb = ort.host._full_trace_setup(system.layout, system, Hs, 64, None, _NoAimFields(ctx))
+    for k in ("y1", "y2", "u", "U", "h_prime"):
+        assert np.max(np.abs(pa[k] - pb[k]) / np.maximum(np.abs(pb[k]), 1.0)) < 1e-14, k
+    for k in ("y_EP", "EP_t", "focus", "a_stop", "nu"):
+        assert abs(pa[k] - pb[k]) <= 1e-14 * max(abs(pb[k]), 1.0), k
+    assert pa["stop"] == pb["stop"] and np.array_equal(pa["ext"], pb["ext"])
+    ea = ort.full_trace_fields(system.layout, system, Hs, 64, backend=ctx)
+    eb = ort.full_trace_fields(system.layout, system, Hs, 64, backend=_NoAimFields(ctx))
+    for a, b in zip(ea, eb):
+        assert abs(len(a.x) - len(b.x)) <= 4                      # the two rim rays of a field may flip with the last bit
+        assert abs(a.RMS / b.RMS - 1) < 1e-3
+
+
 def test_rays_device_pointer_form(ctx, ort):
     """ort_trace3d_rays_dev == ort_trace3d_rays, bit for bit"""
     import torch
