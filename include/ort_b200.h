@@ -143,6 +143,18 @@ int         ort_profile_read(ort_ctx *ctx, double *ms_out, int max_n);
 int ort_set_layout(ort_ctx *ctx, int rows, const double *R, const double *t, const double *n,
                    const double *K);
 
+/* ---- EXTENSION: aspheric polynomial terms in COEFFICIENT form.  The reference's Layout carries p::Vector{Polynomial} of Julia
+ *      closures (src/Types.jl:21-27, 88-92), which cannot cross a C ABI; here p_i(y) = sum_k coef[i][k] y^k for Layout row
+ *      i (row 0 = object space, ignored), k < ncoef <= ORT_MAX_POLY.  Used exactly where the reference uses p: sag + p(y)
+ *      (src/PupilSampling.jl:7, src/RayTracing.jl:82 -- of the vertex-plane y only, and ignored on a plane) and tilt +
+ *      dp_dy(p, .) with the reference's complex-step derivative (src/RayTracing.jl:103), in the 3-D tracers and -- with
+ *      aspheric = 1 -- the 2-D tracer / ray aiming.  Call after ort_set_layout (which clears them); coef = NULL clears.
+ *      Prescriptions with polynomial terms run in reference arithmetic (ORT_ARITH_FAST requests resolve to STRICT).
+ *      Parity unpinned: the evaluation order of a user's closure is unknowable (Horner here), and the reference has no
+ *      test with p != zero. */
+#define ORT_MAX_POLY 18
+int ort_set_polynomials(ort_ctx *ctx, int rows, int ncoef, const double *coef);
+
 /* EXTENSION: clear semi-apertures a[rows-1] of the surfaces of the current layout (row i+1 <-> a[i]); NULL or
  * +Inf entries = unlimited.  Used iff opts.ext & ORT_EXT_VIGNETTE.  Must follow ort_set_layout. */
 int ort_set_apertures(ort_ctx *ctx, int n, const double *a);

@@ -23,7 +23,7 @@ VIG_TAIL = 12
 SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
     "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
-    "ort_set_layout", "ort_set_apertures",
+    "ort_set_layout", "ort_set_apertures", "ort_set_polynomials",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace3d_rays_dev", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev", "ort_aim_fields",
@@ -137,6 +137,7 @@ def load():
     L.ort_vignetting_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, _dp, C.c_double, C.c_void_p,
                                                 C.c_void_p]
     L.ort_aim_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
+    L.ort_set_polynomials.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
     L.ort_aim_fields.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_int, C.c_int, _dp]
     L.ort_aim_candidates_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]
@@ -480,6 +481,16 @@ class Context:
         self._ck(self.L.ort_aim_candidates(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(H), int(bool(aspheric)),
                                            _p(out)))
         return out
+
+    def set_polynomials(self, coef=None):
+        """EXTENSION: polynomial aspheric terms, coef[row][k] multiplies y^k (row 0 = object space); None clears.
+        Call after set_layout (which clears them)."""
+        if coef is None:
+            self._ck(self.L.ort_set_polynomials(self.h, 0, 0, None))
+            return
+        c = _d(coef)
+        assert c.ndim == 2 and c.shape[0] == self.rows
+        self._ck(self.L.ort_set_polynomials(self.h, c.shape[0], c.shape[1], _p(c)))
 
     def aim_fields(self, surfaces, K, a, h_prime, Hs, aspheric=False):
         """full_trace prelude of ONE system at the relative fields Hs -> (n_fields, 24) records (ort_aim_fields)"""

@@ -11,7 +11,7 @@
 // one iteration of the surface loop of src/RayTracing.jl:151-167; returns ts[i] (:160)
 template <class SurfT>
 __device__ __forceinline__ double trace2d_step(const SurfT& S, int aspheric, double& y, double& U, double& sprev,
-                                               unsigned& flags)
+                                               unsigned& flags, const double* pc = nullptr, int npoly = 0)
 {
     const double tU = tan(U);
     const double ti = SS(S.t, sprev);                        // ts[i] (:148, :161)
@@ -23,20 +23,20 @@ __device__ __forceinline__ double trace2d_step(const SurfT& S, int aspheric, dou
         double y2 = SM(y, y);
         double sec = SD(1.0, cos(U));
         double D = SS(SM(beta, beta), SM(y2, SA(SM(sec, sec), Ks)));
-        if (D >= 0.0) sg = SA(SD(y2, SA(beta, SM(S.sgnR, SQ(D)))), 0.0);
+        if (D >= 0.0) sg = SA(SD(y2, SA(beta, SM(S.sgnR, SQ(D)))), pc ? poly_eval(pc, npoly, y) : 0.0);       // + p(y) :82
         else { if (D < 0.0) flags |= ORT_FLAG_MISS; sg = CUDART_NAN; }
     } else sg = 0.0;
     y = SA(y, SM(sg, tU));                                   // :158
     sprev = sg;                                              // ts[i+1] -= s :161
     double theta;
-    if (Ks == 0.0) {                                         // iszero(Ks) && p === zero, per surface: asin(tilt(y, R))  :162, :101
+    if (Ks == 0.0 && !pc) {                                  // iszero(Ks) && p === zero, per surface: asin(tilt(y, R))  :162, :101
         double q = SD(y, S.R);
         if (fabs(q) > 1.0) flags |= ORT_FLAG_DOMAIN;
         theta = asin(q);
     } else {                                                 // atan(tilt(y, R, K, p))  :98
         double D2 = SS(SM(S.R, S.R), SM(SM(y, y), SA(1.0, Ks)));
         if (D2 < 0.0) flags |= ORT_FLAG_DOMAIN;
-        theta = atan(SA(SD(SM(S.sgnR, y), SQ(D2)), 0.0));
+        theta = atan(SA(SD(SM(S.sgnR, y), SQ(D2)), pc ? poly_dpdy(pc, npoly, y) : 0.0));                     // + dp_dy(p, y) :98
     }
     const double sin_ip = SD(SM(S.n1, sin(SA(U, theta))), S.n2);   // :163
     if (fabs(sin_ip) <= 1.0) U = SS(asin(sin_ip), theta);          // :164
@@ -57,7 +57,8 @@ k_trace2d(const __grid_constant__ Presc P, Trace2dArgs A)
     if (A.U_out) A.U_out[i] = U;
     const int nsurf = P.nsurf;
     for (int s = 0; s < nsurf; s++) {
-        const double ts = trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags);
+        const double ts = trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags,
+                                       (A.aspheric && P.poly) ? P.poly + (size_t)s * P.npoly : nullptr, P.npoly);
         if (A.ts_out) A.ts_out[(size_t)s * N + i] = ts;
         if (A.y_out) A.y_out[(size_t)(s + 1) * N + i] = y;
         if (A.U_out) A.U_out[(size_t)(s + 1) * N + i] = U;
@@ -118,7 +119,8 @@ __device__ __forceinline__ double aim_eval(const Presc& P, const AimArgs& A, dou
 {
     double y = A.vary_u ? other : x, U = A.vary_u ? x : other, sprev = 0.0;
     unsigned flags = 0;
-    for (int s = 0; s < A.stop; s++) trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags);
+    for (int s = 0; s < A.stop; s++)
+        trace2d_step(P.s[s], A.aspheric, y, U, sprev, flags, (A.aspheric && P.poly) ? P.poly + (size_t)s * P.npoly : nullptr, P.npoly);
     return y;
 }
 

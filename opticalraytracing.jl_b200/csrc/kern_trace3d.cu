@@ -43,18 +43,18 @@ __device__ __forceinline__ double strict_opl_close(const RayS& r, const ort_fiel
     return SA(r.opl, SM(nlast, tau));
 }
 
-template <bool EXT, class SurfArray>
+template <bool EXT, class SurfArray, bool POLY = false>
 __device__ __forceinline__ Hit trace_strict(const SurfArray& S, int nsurf, int stop,
                                             double y, double x, double u, double v,
                                             const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
-                                            bool vignette = false)
+                                            bool vignette = false, const double* poly = nullptr, int npoly = 0)
 {
     RayS r;
     strict_init(r, y, x, u, v);
     if (EXT) r.opl = strict_opl_start(r, fld->mode, n0, y, x, fld->z0);
     Hit h; h.xs = h.ys = CUDART_NAN; h.opl = 0.0;
     for (int i = 0; i < nsurf; i++) {
-        strict_step<EXT>(S[i], r, vignette);
+        strict_step<EXT, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly);
         if (i == stop - 1) { h.xs = r.x; h.ys = r.y; }
     }
     h.xf = r.x; h.yf = r.y; h.flags = r.flags;
@@ -63,13 +63,13 @@ __device__ __forceinline__ Hit trace_strict(const SurfArray& S, int nsurf, int s
 }
 
 // the strict re-trace of guard-band rays lives out of line so it does not bloat the hot loop
-template <bool EXT, class SurfArray>
+template <bool EXT, class SurfArray, bool POLY = false>
 __device__ __noinline__ Hit trace_strict_cold(const SurfArray& S, int nsurf, int stop,
                                               double y, double x, double u, double v,
                                               const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
-                                              bool vignette = false)
+                                              bool vignette = false, const double* poly = nullptr, int npoly = 0)
 {
-    return trace_strict<EXT>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette);
+    return trace_strict<EXT, SurfArray, POLY>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette, poly, npoly);
 }
 
 // sign bit set iff a is NaN or +-Inf (exponent field all ones)
@@ -220,7 +220,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
         double u, v; field_slopes(fld, y0, x0, u, v);
         h = (ARITH == ORT_ARITH_STRICT)
-                ? trace_strict<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette)
+                ? trace_strict<EXT, decltype(P.s), EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette, P.poly, P.npoly)
                 : trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
@@ -303,7 +303,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         Hit h; int amb = 0;
         if (ARITH == ORT_ARITH_FAST) trace_fast<1, EXT>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
         if (ARITH == ORT_ARITH_STRICT || amb < 0)
-            h = trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
+            h = trace_strict_cold<EXT, decltype(P.s), EXT && ARITH == ORT_ARITH_STRICT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0,
+                                                                                       P.nlast, vignette, P.poly, P.npoly);
         const double ey = h.yf - fld.h_prime;
         const bool bad = nonfinite_bit(h.xf) < 0 || nonfinite_bit(ey) < 0;
         s_shift[0] = bad ? 0.0 : h.xf;
@@ -520,7 +521,7 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
         RayS r;
         strict_init(r, y0, x0, u0, v0);
         for (int s = 0; s < nsurf; s++) {
-            strict_step<EXT>(P.s[s], r, vignette);
+            strict_step<EXT, EXT && ARITH == ORT_ARITH_STRICT>(P.s[s], r, vignette, (EXT && P.poly) ? P.poly + (size_t)s * P.npoly : nullptr, P.npoly);
             if (A.xv) A.xv[(size_t)s * A.N + i] = r.x;
             if (A.yv) A.yv[(size_t)s * A.N + i] = r.y;
         }
@@ -754,7 +755,7 @@ int grid_blocks_per_sm(int arith, int ext)
 
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st)
 {
-    const bool ext = A.ext != 0;
+    const bool ext = A.ext != 0 || P.poly != nullptr;          // polynomial terms live in the EXT instantiations
     if (arith == ORT_ARITH_FAST) {
         const bool others = A.r || A.theta || A.wx || A.wy || A.flags || A.opd;
         const bool lean = !ext && !others && A.ex && A.ey && A.mask;
@@ -798,7 +799,7 @@ cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream
 {
     const unsigned nb = (unsigned)((A.N + 255) / 256);
     if (nb == 0) return cudaSuccess;
-    const bool ext = A.opl != nullptr || P.has_apertures;
+    const bool ext = A.opl != nullptr || P.has_apertures || P.poly != nullptr;
     if (arith == ORT_ARITH_FAST) {
         if (ext) k_rays<ORT_ARITH_FAST, true><<<nb, 256, 0, st>>>(P, A);
         else k_rays<ORT_ARITH_FAST, false><<<nb, 256, 0, st>>>(P, A);

@@ -16,7 +16,7 @@ enum Slot {
     SL_YS, SL_XS, SL_PARTIALS, SL_TILES, SL_STATS,
     SL_EX, SL_EY, SL_R, SL_TH, SL_WX, SL_WY, SL_OPD, SL_MASK, SL_FLAGS,     // trace outputs (full grid)
     SL_CEX, SL_CEY, SL_CR, SL_CTH, SL_CWX, SL_CWY, SL_COPD,                 // compacted outputs
-    SL_IN0, SL_IN1, SL_IN2, SL_IN3, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3, SL_OUT4, SL_SINK,
+    SL_IN0, SL_IN1, SL_IN2, SL_IN3, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3, SL_OUT4, SL_SINK, SL_POLY,
     SL_COUNT
 };
 
@@ -252,6 +252,30 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
     return ORT_OK;
 }
 
+int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: call ort_set_layout first");
+    Presc& P = ctx->presc;
+    if (!coef || ncoef <= 0) { P.poly = nullptr; P.npoly = 0; return ORT_OK; }     // cleared; fast_ok is re-derived by ort_set_layout
+    if (rows != ctx->rows) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: rows = %d, layout has %d", rows, ctx->rows);
+    if (ncoef > ORT_MAX_POLY) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: ncoef = %d > %d", ncoef, ORT_MAX_POLY);
+    bool any = false;
+    for (int i = 0; i < rows * ncoef; i++) {
+        if (isnan(coef[i])) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: NaN coefficient");
+        any = any || coef[i] != 0.0;
+    }
+    if (!any) { P.poly = nullptr; P.npoly = 0; return ORT_OK; }                       // all zero == Polynomial(zero)
+    CK(cudaSetDevice(ctx->device));
+    double* d_c; ENSURE(SL_POLY, (size_t)(rows - 1) * ncoef * 8, d_c);
+    // surface step i uses Layout row i + 1 (row 0 is object space)
+    CK(cudaMemcpyAsync(d_c, coef + ncoef, (size_t)(rows - 1) * ncoef * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    P.poly = d_c; P.npoly = ncoef;
+    P.fast_ok = 0;                                   // the K-form has no polynomial terms: reference arithmetic only
+    return ORT_OK;
+}
+
 int ort_set_apertures(ort_ctx* ctx, int n, const double* a)
 {
     if (!ctx) return ORT_EINVAL;
@@ -353,7 +377,7 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned NN = (unsigned)((long long)ny * nx);
     const int arith = resolve_arith(ctx, opts->arith);
-    const int gx = grid_dims(ctx, arith, opts->ext & 3, n_fields, NN);
+    const int gx = grid_dims(ctx, arith, (opts->ext & 3) || ctx->presc.poly, n_fields, NN);
     RawPart* d_partials; ENSURE(SL_PARTIALS, sizeof(RawPart) * (size_t)gx * n_fields, d_partials);
     ort_stats* d_stats = d_out->stats;
     if (!d_stats) ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
@@ -388,7 +412,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     const size_t tot = (size_t)NN * n_fields;
     const int arith = resolve_arith(ctx, opts->arith);
     // one launch per field so the D2H of field f overlaps the trace of field f+1
-    const int gx = grid_dims(ctx, arith, opts->ext & 3, 1, NN);
+    const int gx = grid_dims(ctx, arith, (opts->ext & 3) || ctx->presc.poly, 1, NN);
     double *d_ys, *d_xs;
     const size_t nys = (size_t)ny * (opts->ys_per_field ? n_fields : 1);
     ENSURE(SL_YS, sizeof(double) * nys, d_ys);
@@ -426,7 +450,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     // Small sweeps are launch-latency bound: all fields in ONE launch sequence (fields = grid dimension y).
     const bool per_field = n_fields > 1 && tot > ((size_t)1 << 21);
     if (!per_field) {
-        const int gxa = grid_dims(ctx, arith, opts->ext & 3, n_fields, NN);     // <= gx: partials slot is large enough
+        const int gxa = grid_dims(ctx, arith, (opts->ext & 3) || ctx->presc.poly, n_fields, NN);     // <= gx: partials slot is large enough
         rc = grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full,
                           opts->compact ? &comp : nullptr, d_stats, d_partials, d_tiles, gxa, st);
         if (rc) return rc;

@@ -59,12 +59,26 @@ def _be(backend):
 # types (src/Types.jl)
 # ------------------------------------------------------------------------------------------------
 class Layout:
-    """Layout{Spherical|Aspheric} (src/Types.jl:82-112): columns R, t, n, K.  Polynomial terms `p`
-    are arbitrary Julia closures in the reference and cannot cross the C ABI: only p == zero."""
+    """Layout{Spherical|Aspheric} (src/Types.jl:82-112): columns R, t, n, K.  Polynomial terms `p` are arbitrary Julia
+    closures in the reference and cannot cross the C ABI; here they are accepted in COEFFICIENT form (an extension):
+    p[i] = (c0, c1, c2, ...) means p_i(y) = c0 + c1 y + c2 y^2 + ... for row i (None or empty = zero); callables are
+    rejected.  Layouts with polynomial terms are traced in the reference arithmetic (STRICT)."""
 
     def __init__(self, M, K=None, aspheric=None, p=None):
-        if p is not None and any(pi is not None for pi in np.atleast_1d(p)):
-            raise ValueError("ort_b200: aspheric polynomial terms p != zero are not supported on the GPU path")
+        P = None
+        if p is not None:
+            rows_p = list(p)
+            if any(callable(pi) for pi in rows_p):
+                raise ValueError("ort_b200: aspheric polynomial terms must be given as coefficient sequences "
+                                 "(closures cannot cross the C ABI)")
+            coefs = [np.atleast_1d(np.asarray([] if pi is None else pi, dtype=np.float64)) for pi in rows_p]
+            ncoef = max((len(c) for c in coefs), default=0)
+            if ncoef > 0 and any(np.any(c != 0.0) for c in coefs):
+                P = np.zeros((len(coefs), ncoef))
+                for i, c in enumerate(coefs):
+                    P[i, :len(c)] = c
+                if aspheric is None:
+                    aspheric = True
         M = np.array(M, dtype=np.float64)
         if M.ndim != 2 or M.shape[1] < 3:
             raise ValueError("Layout needs rows of [R t n] or [R t n K]")
@@ -75,6 +89,15 @@ class Layout:
         self.R, self.t, self.n = M[:, 0].copy(), M[:, 1].copy(), M[:, 2].copy()
         self.K = np.zeros(len(self.R)) if K is None else np.array(K, dtype=np.float64)
         self.aspheric = bool(aspheric)
+        if P is not None and P.shape[0] != len(self.R):
+            raise ValueError("Layout: one polynomial (coefficient sequence) per row")
+        self.P = P                                   # (rows, ncoef) or None
+
+    def upload(self, be):
+        """prescription (+ polynomial terms) to the backend"""
+        be.set_layout(self.M3, self.K)
+        if self.P is not None:
+            be.set_polynomials(self.P)
 
     @property
     def M3(self):
@@ -341,7 +364,7 @@ def raybasis(system, ybar, s):
 # ------------------------------------------------------------------------------------------------
 def _trace2d(layout, y, U, aspheric, backend):
     be = _be(backend)
-    be.set_layout(layout.M3, layout.K)
+    layout.upload(be)
     return be.trace2d_batch(np.atleast_1d(y), np.atleast_1d(U), aspheric=aspheric)
 
 
@@ -371,7 +394,7 @@ def raytrace(surfaces, *args, a=None, clip=False, backend=None):
         y, x, U, V = args[:4]
         layout = _as_layout(surfaces)
         be = _be(backend)
-        be.set_layout(layout.M3, layout.K)
+        layout.upload(be)
         y0, x0, U0, V0 = np.broadcast_arrays(*(np.atleast_1d(np.asarray(q, dtype=np.float64)) for q in (y, x, U, V)))
         xv, yv, k, fl = be.trace3d_rays(y0, x0, np.tan(U0), np.tan(V0), arith=_lib.STRICT)   # tan: :38-39
         if all(np.isscalar(q) for q in (y, x, U, V)):
@@ -392,7 +415,7 @@ def trace_marginal_ray(surfaces, system, atol=EPS, backend=None):
     a_stop = system.a[stop - 1]
     be = _be(backend)
     if hasattr(be, "aim2d"):                       # the reference's secant loop (:229-233) in one launch
-        be.set_layout(layout.M3, layout.K)
+        layout.upload(be)
         out, it = be.aim2d([y], [0.0], [a_stop], stop, vary_u=False, mode=0, tol=atol, aspheric=layout.aspheric)
         if it[0] < 0:
             raise RuntimeError("trace_marginal_ray did not converge")
@@ -427,13 +450,13 @@ def trace_chief_ray(surfaces, system, atol=EPS, backend=None):
     m = system.marginal
     rev_t[0] = m.z[-1] - m.z[-2]
     rev = Layout(np.column_stack([rev_R, rev_t, rev_n]), K=L.K[::-1].copy() if is_layout else None,
-                 aspheric=is_layout)
+                 aspheric=is_layout, p=None if (L.P is None or not is_layout) else list(L.P[::-1]))   # reverse(p) :274
     stop = rows - system.stop
     ybp = system.chief.y[-1]
     ubp = -system.chief.u[-1]
     be = _be(backend)
     if hasattr(be, "aim2d"):                       # the reference's secant loop on U (:282-286) in one launch
-        be.set_layout(rev.M3, rev.K)
+        rev.upload(be)
         out, it = be.aim2d([ubp], [ybp], [0.0], stop, vary_u=True, mode=0, tol=atol, aspheric=rev.aspheric)
         if it[0] < 0:
             raise RuntimeError("trace_chief_ray did not converge")
@@ -466,7 +489,7 @@ def aim_rays(surfaces, y_start, U, target, stop, scale, backend=None):
     m = len(y)
     be = _be(backend)
     if hasattr(be, "aim2d"):                       # the whole secant loop runs on the device: one launch
-        be.set_layout(layout.M3, layout.K)
+        layout.upload(be)
         out, it = be.aim2d(y, UU, tgt, stop, vary_u=False, mode=1, tol=scale, aspheric=layout.aspheric)
         if np.any(it < 0):
             raise RuntimeError("ray aiming left the domain")
@@ -512,7 +535,8 @@ def _full_trace_setup(surfaces, system, H, k_rays, focus, backend):
     stop = system.stop
     a_stop = abs(system.a[stop - 1])
     be = _be(backend)
-    if isinstance(system, System) and hasattr(be, "aim_fields"):
+    P_ext = None if layout.P is None else np.vstack([layout.P, np.zeros((1, layout.P.shape[1]))])   # fill_poly row of the image plane
+    if isinstance(system, System) and hasattr(be, "aim_fields") and layout.P is None:
         # the whole prelude (:90-108) for all fields in one call: first-order solve, reversed real chief ray, real
         # marginal ray and both edge rays per field on the device (k_aim_candidates, one thread per field).  Used only
         # when it reproduces the System it was handed (same stop, focal length and marginal nu, bit for bit).
@@ -525,7 +549,7 @@ def _full_trace_setup(surfaces, system, H, k_rays, focus, backend):
             return dict(ext=ext, K=Kx, Hs=Hs, U=rec[:, 13].copy(), u=rec[:, 3].copy(), y1=rec[:, 0].copy(),
                         y2=rec[:, 1].copy(), y_EP=float(rec[0, 2]), EP_t=float(rec[0, 8]), h_prime=rec[:, 4].copy(),
                         stop=stop, a_stop=a_stop, focus=focus, z0=None, ybar=None, k_rays=k_rays,
-                        nu=system.marginal.nu[-1])
+                        nu=system.marginal.nu[-1], P=None)
     # full_trace is reached with surfaces::Layout (:85), so trace_chief_ray takes its Layout branch
     real_chief = trace_chief_ray(layout, system, backend=backend)
     real_marginal = trace_marginal_ray(layout, system, backend=backend)
@@ -549,7 +573,7 @@ def _full_trace_setup(surfaces, system, H, k_rays, focus, backend):
     ext[-2, 1] = focus                                                           # :114
     return dict(ext=ext, K=Kx, Hs=Hs, U=U, u=u, y1=y1, y2=y2, y_EP=y_EP, EP_t=EP_t, h_prime=h_prime,
                 stop=stop, a_stop=a_stop, focus=focus, z0=z0, ybar=ybar, k_rays=k_rays,
-                nu=system.marginal.nu[-1])
+                nu=system.marginal.nu[-1], P=P_ext)
 
 
 def full_trace(*args, backend=None, arith=_lib.FAST):
@@ -579,6 +603,8 @@ def full_trace_fields(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, backen
     be = _be(backend)
     p = _full_trace_setup(surfaces, system, Hs, k_rays, focus, backend)
     be.set_layout(p["ext"], p["K"])
+    if p["P"] is not None:
+        be.set_polynomials(p["P"])
     k2 = k_rays // 2                                                             # :116
     xs = np.linspace(0.0, p["y_EP"], k2)                                         # :122
     ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], k_rays) for j in range(len(p["Hs"]))])   # :121
@@ -680,6 +706,8 @@ def wavefront(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, lam=LAMBDA, vi
     # chief ray of every field: through the centre of the stop (aiming uses the 2-D kernel on the bare layout)
     y_c = aim_rays(layout, -p["u"] * p["EP_t"], p["U"], np.zeros(nf), p["stop"], p["a_stop"], backend=backend)
     be.set_layout(ext, p["K"])
+    if p["P"] is not None:
+        be.set_polynomials(p["P"])
     be.set_apertures(system.a if vignette else None)
     xv, yv, k, fl, opl = be.trace3d_rays(y_c, np.zeros(nf), p["u"], np.zeros(nf), arith=_lib.STRICT, opl=True)
     n0, nl = layout.n[0], layout.n[-1]

@@ -58,6 +58,19 @@ def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def set_poly(coef=None):
+    """EXTENSION: aspheric polynomial terms in coefficient form, coef[row][k] multiplies y^k (row 0 = object space,
+    ignored); None clears them.  Process-global state read by the 2-D and 3-D tracers."""
+    if coef is None:
+        lib().orc_set_poly(C.c_int(0), C.c_int(0), None)
+        return
+    c = _d(coef)
+    assert c.ndim == 2
+    rc = lib().orc_set_poly(C.c_int(c.shape[0]), C.c_int(c.shape[1]), c.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise ValueError("orc_set_poly: too many rows / coefficients")
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 

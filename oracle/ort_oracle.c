@@ -39,6 +39,57 @@
 /* Julia Base sign(): sign(0)=0, sign(NaN)=NaN, sign(+-Inf)=+-1 */
 static inline double jl_sign(double x) { return x < 0.0 ? -1.0 : (x > 0.0 ? 1.0 : x); }
 
+/* ------------------------------------------------------------------------------------
+ * EXTENSION: aspheric polynomial terms in COEFFICIENT form.  The reference's Layout carries
+ * p::Vector{Polynomial} of Julia closures (src/Types.jl:21-27, 88-92), which cannot cross a C ABI;
+ * here p_i(y) = sum_k coef[i][k] y^k (Horner, highest power first).  Where the reference uses p:
+ * sag + p(y) (src/PupilSampling.jl:7, src/RayTracing.jl:82 -- p of the vertex-plane y only, and
+ * ignored on a plane, :12 / :87) and tilt + dp_dy(p, .) with the complex-step derivative
+ * dp_dy(p, y) = imag(p(complex(y, eps))) / eps, eps = sqrt(eps()) (src/RayTracing.jl:103).
+ * The evaluation order of a user's closure is unknowable: parity unpinned.  State is process-
+ * global (set before a batch, read-only during it).
+ * ---------------------------------------------------------------------------------- */
+#define ORC_MAX_POLY 18
+static int g_poly_rows = 0, g_poly_n = 0;
+static double g_poly[64 * ORC_MAX_POLY];
+
+ORC_API int orc_set_poly(int rows, int ncoef, const double *coef)
+{
+    if (!coef || rows <= 0 || ncoef <= 0) { g_poly_rows = g_poly_n = 0; return 0; }
+    if (rows > 64 || ncoef > ORC_MAX_POLY) return -1;
+    g_poly_rows = rows; g_poly_n = ncoef;
+    for (int i = 0; i < rows * ncoef; i++) g_poly[i] = coef[i];
+    return 0;
+}
+
+static inline int poly_on(int row) { return g_poly_n > 0 && row < g_poly_rows; }
+
+/* p_row(y); 0.0 (Julia's zero) without polynomials */
+static inline double poly_eval(int row, double y)
+{
+    if (!poly_on(row)) return 0.0;
+    const double *c = g_poly + (size_t)row * g_poly_n;
+    double acc = c[g_poly_n - 1];
+    for (int k = g_poly_n - 2; k >= 0; k--) acc = acc * y + c[k];
+    return acc;
+}
+
+/* dp_dy(p_row, y) = imag(p(complex(y, eps))) / eps -- complex Horner with Julia's complex product
+ * (a + bi)(c + di) = (ac - bd) + (ad + bc)i; 0.0 without polynomials */
+static inline double poly_dpdy(int row, double y)
+{
+    if (!poly_on(row)) return 0.0;
+    const double eps = 1.4901161193847656e-08;
+    const double *c = g_poly + (size_t)row * g_poly_n;
+    double re = c[g_poly_n - 1], im = 0.0;
+    for (int k = g_poly_n - 2; k >= 0; k--) {
+        double nre = re * y - im * eps + c[k];
+        double nim = re * eps + im * y;
+        re = nre; im = nim;
+    }
+    return im / eps;
+}
+
 /* Julia Base.Math._hypot for Float64 on an FMA-capable host (base/math.jl, not under
  * /root/reference).  Used by full_trace for the stop-radius mask, PupilSampling.jl:131.
  * The fma branch is correctly rounded, so the value equals any correctly rounded hypot. */
@@ -227,14 +278,14 @@ ORC_API void orc_transfer_batch(const double *M, double tau, double taup, int re
  * ---------------------------------------------------------------------------------- */
 
 /* sag(y,U,R,K,p) with p == zero -- :75-88 */
-static double sag2d(double y, double U, double R, double K, unsigned *flags)
+static double sag2d(int row, double y, double U, double R, double K, unsigned *flags)
 {
     if (isfinite(R)) {
         double beta = R - y * tan(U);
         double y2 = y * y;
         double sec = 1.0 / cos(U);
         double D = beta * beta - y2 * (sec * sec + K);
-        if (D >= 0.0) return y2 / (beta + jl_sign(R) * sqrt(D)) + 0.0;   /* + p(y), p = zero */
+        if (D >= 0.0) return y2 / (beta + jl_sign(R) * sqrt(D)) + poly_eval(row, y);   /* + p(y) :82 */
         if (D < 0.0) *flags |= F_MISS;
         return NAN;
     }
@@ -258,18 +309,18 @@ ORC_API unsigned orc_trace2d(int rows, const double *R, const double *t, const d
         y += tan(U) * ts[i];                                   /* :152 */
         double Rs = R[i + 1];
         double Ks = aspheric ? K[i + 1] : 0.0;
-        double s = sag2d(y, U, Rs, Ks, &flags);                /* :156 */
+        double s = sag2d(i + 1, y, U, Rs, Ks, &flags);         /* :156 */
         y += s * tan(U);                                       /* :158 */
         ts[i] += s; ts[i + 1] -= s;                            /* :160-161 */
         double theta;
-        if (Ks == 0.0) {                                       /* iszero(Ks) && ps === zero, per surface  :162 */
+        if (Ks == 0.0 && !poly_on(i + 1)) {                    /* iszero(Ks) && ps === zero, per surface  :162 */
             double q = y / Rs;                                 /* tilt(y,R) :101 */
             if (fabs(q) > 1.0) flags |= F_DOMAIN;              /* Julia asin throws */
             theta = asin(q);
         } else {
             double D = Rs * Rs - y * y * (1.0 + Ks);           /* tilt(y,R,K,p) :98 */
             if (D < 0.0) flags |= F_DOMAIN;                    /* Julia sqrt throws */
-            theta = atan(jl_sign(Rs) * y / sqrt(D) + 0.0);     /* + dp_dy(zero) = 0 */
+            theta = atan(jl_sign(Rs) * y / sqrt(D) + poly_dpdy(i + 1, y));   /* + dp_dy(p, y) :98 */
         }
         double sin_ip = n[i] * sin(U + theta) / n[i + 1];      /* :163 */
         if (fabs(sin_ip) <= 1.0) U = asin(sin_ip) - theta;     /* :164 */
@@ -315,14 +366,14 @@ ORC_API void orc_trace2d_batch(int rows, const double *R, const double *t, const
  * ---------------------------------------------------------------------------------- */
 
 /* sag(y,x,u,v,R,K,p), p == zero -- :1-14 */
-static inline double sag3d(double y, double x, double u, double v, double R, double K,
+static inline double sag3d(int row, double y, double x, double u, double v, double R, double K,
                            unsigned *flags)
 {
     if (isfinite(R)) {
         double beta = R - y * u - x * v;                        /* :3 */
         double r2 = x * x + y * y;                              /* :4 */
         double D = beta * beta - r2 * (1.0 + K + u * u + v * v);/* :5 */
-        if (D >= 0.0) return r2 / (beta + jl_sign(R) * sqrt(D)) + 0.0;   /* :7 (+ p(y)) */
+        if (D >= 0.0) return r2 / (beta + jl_sign(R) * sqrt(D)) + poly_eval(row, y);   /* :7 (+ p(y)) */
         if (D < 0.0) *flags |= F_MISS;
         return NAN;                                             /* :9 */
     }
@@ -353,7 +404,7 @@ ORC_API unsigned orc_trace3d(int rows, const double *R, const double *t, const d
         y += u * ti;                                            /* :46 */
         x += v * ti;                                            /* :47 */
         double Rs = R[i + 1], Ks = K ? K[i + 1] : 0.0;
-        double s = sag3d(y, x, u, v, Rs, Ks, &flags);           /* :51 */
+        double s = sag3d(i + 1, y, x, u, v, Rs, Ks, &flags);    /* :51 */
         y += s * u;                                             /* :52 */
         x += s * v;                                             /* :53 */
         s_prev = s; have_prev = 1;                              /* :54-55 */
@@ -361,8 +412,8 @@ ORC_API unsigned orc_trace3d(int rows, const double *R, const double *t, const d
         double D = Rs * Rs - (x * x + y * y) * (1.0 + Ks);      /* :17 */
         if (D < 0.0) flags |= F_DOMAIN;                         /* Julia sqrt would throw */
         double sq = sqrt(D);
-        double m1 = jl_sign(Rs) * x / sq + 0.0;                 /* :18, + dp_dy(zero, x) = 0.0 */
-        double m2 = jl_sign(Rs) * y / sq + 0.0;
+        double m1 = jl_sign(Rs) * x / sq + poly_dpdy(i + 1, x);  /* :18, + dp_dy(p, x) */
+        double m2 = jl_sign(Rs) * y / sq + poly_dpdy(i + 1, y);
         double m3 = -1.0;
         {
             double nrm = sqrt(m1 * m1 + m2 * m2 + m3 * m3);
@@ -580,7 +631,7 @@ ORC_API unsigned orc_trace3d_ext(int rows, const double *R, const double *t, con
         y += u * ti;
         x += v * ti;
         double Rs = R[i + 1], Ks = K ? K[i + 1] : 0.0;
-        double s = sag3d(y, x, u, v, Rs, Ks, &flags);
+        double s = sag3d(i + 1, y, x, u, v, Rs, Ks, &flags);
         y += s * u;
         x += s * v;
         s_prev = s; have_prev = 1;
@@ -589,8 +640,8 @@ ORC_API unsigned orc_trace3d_ext(int rows, const double *R, const double *t, con
         double D = Rs * Rs - (x * x + y * y) * (1.0 + Ks);
         if (D < 0.0) flags |= F_DOMAIN;
         double sq = sqrt(D);
-        double m1 = jl_sign(Rs) * x / sq + 0.0;
-        double m2 = jl_sign(Rs) * y / sq + 0.0;
+        double m1 = jl_sign(Rs) * x / sq + poly_dpdy(i + 1, x);
+        double m2 = jl_sign(Rs) * y / sq + poly_dpdy(i + 1, y);
         double m3 = -1.0;
         {
             double nrm = sqrt(m1 * m1 + m2 * m2 + m3 * m3);

@@ -18,6 +18,10 @@ class OracleBackend:
         self.S = S[:, :3].copy()
         self.K = None if K is None else np.asarray(K, dtype=np.float64).copy()
         self.rows = S.shape[0]
+        orc.set_poly(None)                          # like ort_set_layout: a new layout clears the polynomial terms
+
+    def set_polynomials(self, coef=None):
+        orc.set_poly(coef)
 
     def set_apertures(self, a):
         self.a = None if a is None else np.asarray(a, dtype=np.float64).copy()

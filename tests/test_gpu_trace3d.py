@@ -505,3 +505,103 @@ def test_many_fields_one_call_equals_per_field_calls(ctx, ort, pre):
             assert recs[j].tobytes() == allr["stats"][j].tobytes()
             assert np.array_equal(d["ex"][j][:n].cpu().numpy(), allr["ex"][j][:n], equal_nan=True)
             assert np.array_equal(d["theta"][j][:n].cpu().numpy(), allr["theta"][j][:n], equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# EXTENSION: aspheric polynomial terms in coefficient form (the reference's p closures cannot cross the C ABI)
+# ------------------------------------------------------------------------------------------------
+def _poly_layout(ort, name, rng):
+    S = getattr(ort.prescriptions, name)["surfaces"][:, :3]
+    rows = S.shape[0]
+    P = np.zeros((rows, 9))
+    for i in range(1, rows):
+        if np.isfinite(S[i, 0]) and rng.uniform() < 0.7:
+            P[i, 4] = rng.uniform(-3e-7, 3e-7); P[i, 6] = rng.uniform(-3e-10, 3e-10); P[i, 8] = rng.uniform(-1e-13, 1e-13)
+    P[rows - 1, 3] = 1e-7                              # an odd term too
+    K = np.where(np.isfinite(S[:, 0]), rng.uniform(-0.5, 0.2, rows), 0.0); K[0] = 0.0
+    return S, K, P
+
+
+@pytest.mark.parametrize("name", ["COOKE", "DOUBLE_GAUSS", "SINGLET"])
+def test_polynomial_terms_rays(ctx, orc, ort, name):
+    """3-D and 2-D tracers with polynomial terms == the CPU restatement, bit for bit (same Horner / complex-step order);
+    a FAST request runs the reference arithmetic; zero coefficients == no polynomial; clearing works."""
+    rng = np.random.default_rng(21)
+    S, K, P = _poly_layout(ort, name, rng)
+    N = 3000
+    y0, x0 = rng.uniform(-9, 9, N), rng.uniform(-9, 9, N)
+    u0, v0 = rng.uniform(-0.1, 0.1, N), rng.uniform(-0.1, 0.1, N)
+    try:
+        orc.set_poly(P)
+        xo, yo, ko, fo = orc.trace3d_batch(S, y0, x0, u0, v0, K=K)
+        y2o, U2o, tso, f2o = orc.trace2d_batch(S, y0, np.arctan(u0), K=K, aspheric=True)
+    finally:
+        orc.set_poly(None)
+    xn, yn, kn, fn = orc.trace3d_batch(S, y0, x0, u0, v0, K=K)
+    assert np.nanmax(np.abs(yo - yn)) > 1e-6                      # the terms do something
+    ctx.set_layout(S, K)
+    ctx.set_polynomials(P)
+    for arith in (ort.STRICT, ort.FAST):
+        xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=arith)
+        assert np.array_equal(fs, fo)
+        assert n_bits_differ(xs, xo) == 0 and n_bits_differ(ys, yo) == 0 and n_bits_differ(ks, ko) == 0
+    y2, U2, ts, f2 = ctx.trace2d_batch(y0, np.arctan(u0), aspheric=True)
+    assert np.array_equal(f2, f2o)
+    # libm (tan, atan, asin) differs in the last ulp: error relative to the position / angle scale
+    assert abs_rel_err(y2, y2o, 10.0) < TOL and abs_rel_err(U2, U2o, 1.0) < TOL
+    # 3-D == 2-D on meridional rays
+    xm, ym, km, fm = ctx.trace3d_rays(y0, np.zeros(N), u0, np.zeros(N), arith=ort.STRICT)
+    ok = ~np.isnan(ym[-1]) & ~np.isnan(y2[-1])
+    assert np.max(np.abs(ym[:, ok] - y2[1:, ok])) < 1e-10 and np.all(xm[:, ok] == 0.0)
+    # zero coefficients and clearing
+    ctx.set_polynomials(np.zeros_like(P))
+    xz, yz, kz, fz = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+    assert n_bits_differ(yz, yn) == 0
+    ctx.set_polynomials(P); ctx.set_polynomials(None)
+    xc, yc, kc, fc = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+    assert n_bits_differ(yc, yn) == 0
+    ctx.set_polynomials(P); ctx.set_layout(S, K)                  # a new layout clears them too
+    xc, yc, kc, fc = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
+    assert np.nanmax(np.abs(yc - yn)) < 1e-9
+
+
+def test_polynomial_terms_grid_and_full_trace(ctx, orc, pre, ort):
+    """grid sweep with polynomial terms (EXT instantiation, reference arithmetic): spot, mask, flags and counts == oracle;
+    full_trace through the host API (prelude with the 2-D polynomial tracer, reversed chief-ray layout with reverse(p))"""
+    rng = np.random.default_rng(22)
+    S, K, P = _poly_layout(ort, "COOKE", rng)
+    K[:] = 0.0
+    Pc = ort.prescriptions.COOKE
+    sysm = pre.solve(S, Pc["a"], Pc["h"])
+    p = pre.full_trace_inputs(sysm, 0.7, 48)
+    Pext = np.vstack([P, np.zeros((1, P.shape[1]))])
+    try:
+        orc.set_poly(Pext)
+        g = orc.grid_trace(p.ext, p.ys, p.xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
+    finally:
+        orc.set_poly(None)
+    ctx.set_layout(p.ext, p.K)
+    ctx.set_polynomials(Pext)
+    for arith in (ort.STRICT, ort.FAST):
+        for want in (("ex", "ey", "r", "theta", "mask", "flags", "stats"), ("ex", "ey", "mask", "stats")):
+            r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop, arith=arith, want=want)
+            assert np.array_equal(r["mask"][0], g["mask"]) and int(r["stats"]["n_kept"][0]) == g["n_kept"]
+            assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
+    ctx.set_polynomials(None)
+    # host API: a Layout with coefficient polynomials, against the oracle prelude + grid on the same layout
+    L = ort.Layout(S, p=list(P))
+    system = ort.solve(L, Pc["a"], Pc["h"], backend=ctx)
+    e = ort.full_trace(L, system, 0.7, 48, backend=ctx)
+    e0 = ort.full_trace(ort.Layout(S), system, 0.7, 48, backend=ctx)
+    assert e.RMS != e0.RMS and len(e.x) > 1500
+    pp = ort.host._full_trace_setup(L, system, [0.7], 48, None, ctx)      # the product prelude's inputs -> the oracle grid
+    assert pp["P"] is not None and pp["P"].shape[0] == pp["ext"].shape[0]
+    try:
+        orc.set_poly(pp["P"])
+        g = orc.grid_trace(pp["ext"], np.linspace(pp["y1"][0], pp["y2"][0], 48), np.linspace(0.0, pp["y_EP"], 24), pp["stop"],
+                           pp["a_stop"], float(pp["h_prime"][0]), u=float(pp["u"][0]), v=0.0, K=pp["K"])
+    finally:
+        orc.set_poly(None)
+    m = g["mask"]
+    *_, rms = orc.mirror_stats(orc.compact(m, g["ex"]), orc.compact(m, g["ey"]), orc.compact(m, g["r"]), orc.compact(m, g["theta"]))
+    assert len(e.x) == 2 * g["n_kept"] and abs(e.RMS / rms - 1) < 1e-11

@@ -121,9 +121,33 @@ def test_tsa_and_sa(ort, be, cooke):
 
 def test_layout_rejects_polynomials(ort):
     with pytest.raises(ValueError):
-        ort.Layout(ort.prescriptions.COOKE["surfaces"], p=[lambda y: y ** 4])
+        ort.Layout(ort.prescriptions.COOKE["surfaces"], p=[lambda y: y ** 4])      # closures cannot cross the C ABI
     L = ort.Layout(ort.prescriptions.PARABOLA["surfaces"])
-    assert L.aspheric and L.K[1] == -1.0
+    assert L.aspheric and L.K[1] == -1.0 and L.P is None
+
+
+def test_layout_polynomials_in_coefficient_form(ort, orc, be):
+    """EXTENSION: p given as coefficient sequences.  Zero coefficients == no polynomial (bit for bit); a y^4 term on
+    the first surface of a singlet moves the marginal focus the way a weaker rim does; 3-D == 2-D on meridional rays."""
+    S = ort.prescriptions.SINGLET["surfaces"]
+    L0 = ort.Layout(S)
+    Lz = ort.Layout(S, p=[None, [0.0, 0.0, 0.0, 0.0, 0.0], None])
+    assert Lz.P is None and not Lz.aspheric
+    Lp = ort.Layout(S, p=[None, [0.0, 0.0, 0.0, 0.0, -2e-7], None])
+    assert Lp.P.shape == (3, 5) and Lp.aspheric
+    y, U = 12.0, 0.0
+    r0 = ort.raytrace(L0, y, U, ort.RealRay, backend=be)
+    rp = ort.raytrace(Lp, y, U, ort.RealRay, backend=be)
+    # p(y) = -2e-7 y^4 flattens the rim: sag -4.1e-3 mm and surface slope -1.4e-3 at y = 12 -> a weaker refraction
+    assert rp.u[1] != r0.u[1] and abs(rp.u[1]) < abs(r0.u[1]) and abs(rp.u[1] - r0.u[1]) < 2e-3
+    assert rp.y[2] != r0.y[2]
+    xv, yv = ort.raytrace(Lp, y, 0.0, U, 0.0, ort.VectorRealRay, backend=be)
+    assert np.allclose(yv, rp.y[1:], rtol=1e-12, atol=1e-12) and np.all(xv == 0.0)
+    # complex-step derivative of the restatement == analytic derivative to rounding
+    orc.set_poly(Lp.P)
+    rt, ts, fl = orc.trace2d(S, y, U, K=np.zeros(3), aspheric=True)
+    orc.set_poly(None)
+    assert np.array_equal(rt[:, 0], rp.y)
 
 
 def test_merge_stats_matches_direct(ort):
