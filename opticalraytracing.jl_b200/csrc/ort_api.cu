@@ -35,6 +35,7 @@ struct ort_ctx {
     Presc presc;
     int rows;
     bool have_layout;
+    int fast_ok_layout;         // fast_ok as derived from R, t, n, K alone (polynomial terms force it to 0 while set)
     int bps[2][2];              // resident CTAs/SM of k_grid<STRICT|FAST, EXT off|on>
     void* slot[SL_COUNT];
     size_t slot_bytes[SL_COUNT];
@@ -249,6 +250,7 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
     }
     ctx->rows = rows;
     ctx->have_layout = true;
+    ctx->fast_ok_layout = P.fast_ok;
     return ORT_OK;
 }
 
@@ -257,7 +259,7 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
     if (!ctx) return ORT_EINVAL;
     if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: call ort_set_layout first");
     Presc& P = ctx->presc;
-    if (!coef || ncoef <= 0) { P.poly = nullptr; P.npoly = 0; return ORT_OK; }     // cleared; fast_ok is re-derived by ort_set_layout
+    if (!coef || ncoef <= 0) { P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; return ORT_OK; }     // cleared
     if (rows != ctx->rows) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: rows = %d, layout has %d", rows, ctx->rows);
     if (ncoef > ORT_MAX_POLY) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: ncoef = %d > %d", ncoef, ORT_MAX_POLY);
     bool any = false;
@@ -265,7 +267,7 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
         if (isnan(coef[i])) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: NaN coefficient");
         any = any || coef[i] != 0.0;
     }
-    if (!any) { P.poly = nullptr; P.npoly = 0; return ORT_OK; }                       // all zero == Polynomial(zero)
+    if (!any) { P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; return ORT_OK; }     // all zero == Polynomial(zero)
     CK(cudaSetDevice(ctx->device));
     double* d_c; ENSURE(SL_POLY, (size_t)(rows - 1) * ncoef * 8, d_c);
     // surface step i uses Layout row i + 1 (row 0 is object space)
