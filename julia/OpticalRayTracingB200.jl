@@ -98,7 +98,9 @@ function ctx()
     return CTX[]
 end
 
-# Aspheric polynomial terms are Julia closures: they cannot cross the C ABI.
+# Aspheric polynomial terms are Julia closures: they cannot cross the C ABI.  (A Layout whose p are genuine
+# polynomials can pass their COEFFICIENTS through ort_set_polynomials -- see include/ort_b200.h -- but nothing in
+# Polynomial{F} exposes them, so this shim accepts p == zero only.)
 function require_conic(surfaces::Layout)
     all(p -> p.f === zero, surfaces.p) ||
         throw(ArgumentError("OpticalRayTracingB200: polynomial aspheric terms (p ≢ zero) are not supported on the GPU path"))
