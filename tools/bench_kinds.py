@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""One 16 Mi-ray double-Gauss field (spot + mask, FAST arithmetic) timed for three variants of the same prescription,
+so that every surface body of fast_step is measured, not just the one the bench workload uses:
+  spheres   nominal (refracting spheres take the division-free body)
+  conics    every curved surface given K = -0.3 (conic body)
+  weak      nominal lens plus a zero-power, |R| = 1e5 mm dummy refracting pair in front (spheres with the division)
+Prints one JSON object {variant: ms}.  ORT_B200_LIB selects the library build."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ort_b200 as ort  # noqa: E402
+
+NY, NX = 5792, 2896
+ctx = ort.Context(0)
+ort.set_default_backend(ctx)
+P = ort.prescriptions.DOUBLE_GAUSS
+s = ort.solve(P["surfaces"], P["a"], P["h"])
+p = ort.host._full_trace_setup(s.layout, s, (0.7,), 64, None, ctx)
+dev = torch.device("cuda", 0)
+xs = torch.from_numpy(np.linspace(0.0, p["y_EP"], NX)).to(dev)
+ys = torch.from_numpy(np.linspace(p["y1"][0], p["y2"][0], NY)).to(dev)
+b = {k: torch.empty(NY * NX, dtype=torch.float64, device=dev) for k in ("ex", "ey")}
+b["mask"] = torch.empty(NY * NX, dtype=torch.uint8, device=dev)
+st = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
+ptrs = {k: v.data_ptr() for k, v in b.items()}
+ptrs["stats"] = st.data_ptr()
+ext = np.array(p["ext"], dtype=np.float64)
+K0 = np.zeros(len(ext))
+variants = {"spheres": (ext, K0, p["stop"])}
+Kc = np.where(np.isfinite(ext[:, 0]), -0.3, 0.0)
+variants["conics"] = (ext, Kc, p["stop"])
+weak = np.vstack([ext[:1], [[1e5, 1.0, 1.5], [1e5, 1.0, 1.0]], ext[1:]])
+variants["weak"] = (weak, np.zeros(len(weak)), p["stop"] + 2)
+out = {}
+stream = torch.cuda.current_stream().cuda_stream
+for name, (M, K, stop) in variants.items():
+    ctx.set_layout(M, K)
+    fld = [dict(u=float(p["u"][0]), h_prime=float(p["h_prime"][0]))]
+    for _ in range(3):
+        ctx.trace3d_grid_dev(fld, ys.data_ptr(), NY, xs.data_ptr(), NX, stop, p["a_stop"], ptrs, stream=stream, arith=ort.FAST)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        ctx.trace3d_grid_dev(fld, ys.data_ptr(), NY, xs.data_ptr(), NX, stop, p["a_stop"], ptrs, stream=stream, arith=ort.FAST)
+    e1.record()
+    torch.cuda.synchronize()
+    rec = np.frombuffer(st.cpu().numpy().tobytes(), dtype=ort.STATS_DTYPE)[0]
+    out[name] = {"ms": e0.elapsed_time(e1) / 10, "kept": int(rec["n_kept"]), "n_strict": int(rec["n_strict"])}
+print(json.dumps(out))

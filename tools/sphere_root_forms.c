@@ -1,0 +1,86 @@
+/* sphere_root_forms.c -- error study for the two algebraically equal forms of the ray-sphere path parameter in the
+ * FAST (K-form) tracer of csrc/ort_internal.cuh:
+ *
+ *     stable     s = F / (G + sqrt(disc))            one division per sphere (4 DFMA/DMUL + 1 MUFU after the seed)
+ *     cheap      s = (G - sqrt(disc)) * (1 / (c n1^2))   one subtraction + one multiplication by a per-surface constant
+ *
+ * The cheap form cancels: its absolute error is ~ eps * |R| per surface, independent of the gap.  This program traces
+ * the same rays through the double-Gauss of BASELINE config 2 in double (both forms, fma as the GPU contracts) and in
+ * 80-bit long double (stable form = truth), and prints the worst image-plane error of each form relative to the
+ * position scale, for the nominal radii and for the same lens with one weak surface of growing radius.
+ *
+ *   gcc -O2 -ffp-contract=off -o /tmp/srf tools/sphere_root_forms.c -lm && /tmp/srf
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define ROWS 13
+static double Rr[ROWS] = {INFINITY, 54.153, 152.522, 35.951, INFINITY, 22.270, INFINITY, -25.685, INFINITY, -36.980, 196.417, -67.148, INFINITY};
+static double Tt[ROWS] = {0.0, 8.747, 0.5, 14.0, 3.777, 14.253, 12.428, 3.777, 10.834, 0.5, 6.858, 57.5, 0.0};
+static double Nn[ROWS] = {1.0, 1.60738, 1.0, 1.62041, 1.60342, 1.0, 1.0, 1.60342, 1.62041, 1.0, 1.62041, 1.0, 1.0};
+
+#define TRACE(NAME, T, FMA, SQRT, CHEAP)                                                                              \
+    static void NAME(double y0, double x0, double u, double v, T* xo, T* yo)                                           \
+    {                                                                                                                  \
+        T x = x0, y = y0, z = 0, inv = (T)Nn[0] / SQRT((T)v * v + (T)u * u + 1);                                       \
+        T Kx = v * inv, Ky = u * inv, Kz = inv;                                                                        \
+        for (int i = 0; i < ROWS - 1; i++) {                                                                           \
+            const T t = Tt[i], n1 = Nn[i], n2 = Nn[i + 1], dn2 = (n2 - n1) * (n2 + n1);                                \
+            if (isinf(Rr[i + 1])) {                                                                                    \
+                const T s = (t - z) / Kz;                                                                              \
+                x = FMA(s, Kx, x); y = FMA(s, Ky, y); z = 0;                                                           \
+                if (n1 != n2) Kz = SQRT(FMA(Kz, Kz, dn2));                                                             \
+                continue;                                                                                              \
+            }                                                                                                          \
+            const T c = (T)1 / (T)Rr[i + 1], cn1sq = c * n1 * n1;                                                      \
+            const T zr = z - t;                                                                                        \
+            const T PD = FMA(x, Kx, FMA(y, Ky, zr * Kz)), P2 = FMA(x, x, FMA(y, y, zr * zr));                          \
+            const T F = FMA(c, P2, -2 * zr), G = FMA(-c, PD, Kz), disc = FMA(G, G, -(cn1sq * F));                      \
+            const T ssq = SQRT(disc);                                                                                  \
+            const T s = (CHEAP) ? (G - ssq) * ((T)1 / cn1sq) : F / (G + ssq);                                          \
+            x = FMA(s, Kx, x); y = FMA(s, Ky, y); z = FMA(s, Kz, zr);                                                  \
+            const T g = ssq - SQRT(disc + dn2), gc = g * c;                                                            \
+            Kx = FMA(gc, x, Kx); Ky = FMA(gc, y, Ky); Kz = FMA(gc, z, Kz - g);                                         \
+        }                                                                                                              \
+        *xo = x; *yo = y;                                                                                              \
+    }
+
+TRACE(trace_stable, double, fma, sqrt, 0)
+TRACE(trace_cheap, double, fma, sqrt, 1)
+TRACE(trace_truth, long double, fmal, sqrtl, 0)
+
+static double urand(void) { return (double)rand() / RAND_MAX; }
+
+static void study(const char* label)
+{
+    double worst_s = 0, worst_c = 0;
+    const double scale = 25.0;
+    srand(1);
+    for (int k = 0; k < 400000; k++) {
+        const double y0 = -16 + 32 * urand(), x0 = 16 * urand(), u = tan(0.2374 * urand());
+        double xs, ys, xc, yc; long double xt, yt;
+        trace_truth(y0, x0, u, 0.0, &xt, &yt);
+        if (!isfinite((double)xt) || !isfinite((double)yt)) continue;
+        trace_stable(y0, x0, u, 0.0, &xs, &ys);
+        trace_cheap(y0, x0, u, 0.0, &xc, &yc);
+        const double es = fmax(fabs((double)(xs - xt)), fabs((double)(ys - yt))) / scale;
+        const double ec = fmax(fabs((double)(xc - xt)), fabs((double)(yc - yt))) / scale;
+        if (es > worst_s) worst_s = es;
+        if (ec > worst_c) worst_c = ec;
+    }
+    printf("%-34s stable %.2e   cheap %.2e   (relative to %.0f mm)\n", label, worst_s, worst_c, scale);
+}
+
+int main(void)
+{
+    study("double-Gauss, nominal radii");
+    const double weak[] = {1e3, 1e4, 1e5, 1e6, 1e8};
+    for (int w = 0; w < 5; w++) {
+        char lab[64];
+        Rr[2] = weak[w];                       /* second surface made progressively weaker */
+        snprintf(lab, sizeof lab, "surface 2 with R = %.0e", weak[w]);
+        study(lab);
+    }
+    return 0;
+}
