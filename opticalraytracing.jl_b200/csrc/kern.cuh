@@ -127,8 +127,15 @@ struct TransferArgs {
 #ifndef ORT_BPS2E
 #define ORT_BPS2E 3                         // ... for k_grid<FAST,2,EXT> (80 registers, ~190 B of spills: 5-7 % faster than 2 CTAs x 126 registers)
 #endif
-int grid_rays_per_thread(int arith);
-int grid_blocks_per_sm(int arith, int ext);
+#ifndef ORT_SIMPLE_RPT
+#define ORT_SIMPLE_RPT 3                    // rays per thread of k_grid<FAST, .., SIMPLE> (3 x 2 CTAs/SM: 2.53 ms vs 2.60 at 2 x 3)
+#endif
+#ifndef ORT_BPSP
+#define ORT_BPSP 2                          // ... and its resident CTAs/SM (128 registers, no spills)
+#endif
+int grid_variant(const Presc& P, int arith, int ext);
+int grid_rays_per_thread(int arith, int variant);
+int grid_blocks_per_sm(int arith, int variant);
 cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st);
 cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fields, ort_stats* stats,
                                  cudaStream_t st);

@@ -84,7 +84,7 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
 // (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
 // (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
-template <int RPT, bool EXT, class SurfArray, bool MIRROR = true>
+template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, bool SIMPLE = false>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
@@ -104,10 +104,10 @@ __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int st
         }
     }
     int i = 0;
-    for (; i < stop; i++) fast_step<RPT, EXT, MIRROR>(S[i], r, vignette);
+    for (; i < stop; i++) fast_step<RPT, EXT, MIRROR, SIMPLE>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
-    for (; i < nsurf; i++) fast_step<RPT, EXT, MIRROR>(S[i], r, vignette);
+    for (; i < nsurf; i++) fast_step<RPT, EXT, MIRROR, SIMPLE>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         h[j].xf = r.x[j]; h[j].yf = r.y[j];
@@ -277,8 +277,10 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     return kept;
 }
 
-template <int ARITH, int RPT, bool EXT, int LEAN = 0, bool MIRROR = true>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (RPT == 1 ? ORT_BPS1 : (EXT ? ORT_BPS2E : ORT_BPS2)) : ORT_BPSS)
+// SIMPLE (FAST only): the prescription holds refracting spheres and planes only (Presc::simple): ORT_SIMPLE_RPT rays per
+// thread through the three-body fast_step<.., SIMPLE>, ORT_BPSP resident CTAs/SM.
+template <int ARITH, int RPT, bool EXT, int LEAN = 0, bool MIRROR = true, bool SIMPLE = false>
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (SIMPLE ? ORT_BPSP : (RPT == 1 ? ORT_BPS1 : (EXT ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
     __shared__ RawPart s_part[ORT_TILE / 32];
@@ -301,7 +303,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         const double y0 = __ldg(ysf + A.ny / 2), x0 = __ldg(A.xs);
         double u, v; field_slopes(fld, y0, x0, u, v);
         Hit h; int amb = 0;
-        if (ARITH == ORT_ARITH_FAST) trace_fast<1, EXT>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
+        if (ARITH == ORT_ARITH_FAST)
+            trace_fast<1, EXT, decltype(P.s), !SIMPLE, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
         if (ARITH == ORT_ARITH_STRICT || amb < 0)
             h = trace_strict_cold<EXT, decltype(P.s), EXT && ARITH == ORT_ARITH_STRICT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0,
                                                                                        P.nlast, vignette, P.poly, P.npoly);
@@ -352,7 +355,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         Hit h[RPT];
         int amb[RPT];
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<RPT, EXT, decltype(P.s), MIRROR>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
+            trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
                                                         collimated ? K0 : nullptr);
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
@@ -582,16 +585,18 @@ k_candidates(CandArgs A)
     const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
     const double* Rc = A.RtnK + (size_t)c * 4 * rows;
     const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
-    __shared__ int s_mirror;
-    if (threadIdx.x == ORT_TILE - 2) s_mirror = 0;
+    __shared__ int s_mirror, s_general;
+    if (threadIdx.x == ORT_TILE - 2) { s_mirror = 0; s_general = 0; }
     __syncthreads();
     if (threadIdx.x < rows - 1) {
         const int i = threadIdx.x;
         derive_surface(s_surf[i], Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i],
                        Rc[2 * rows + i + 1]);
         if (!(Rc[2 * rows + i] > 0.0) || !(Rc[2 * rows + i + 1] > 0.0)) atomicOr(&s_mirror, 1);   // a reflecting candidate
+        if (ARITH == ORT_ARITH_FAST && !simple_surface(s_surf[i], gap_scale(Rc + rows, rows))) atomicOr(&s_general, 1);
     } else if (AIMED && threadIdx.x == rows - 1) {
         derive_surface(s_surf[rows - 1], CUDART_INF, 0.0, rec[5], Rc[3 * rows - 1], 1.0);
+        if (!(Rc[3 * rows - 1] > 0.0)) atomicOr(&s_general, 1);
     }
     __syncthreads();
     // per-candidate scalars live in shared memory (the shared-grid variant reads them from the constant bank):
@@ -614,6 +619,7 @@ k_candidates(CandArgs A)
     __syncthreads();
     const volatile double* par = s_par;
     const bool mirror = s_mirror != 0;
+    const bool simple = s_general == 0 && !mirror;               // refracting spheres and planes only (simple_surface)
     const int stop = s_stop;
     const bool ok = stop > 0;
 #define CAND_PAR(i, shared_grid_value) (AIMED ? par[i] : (shared_grid_value))
@@ -660,7 +666,8 @@ k_candidates(CandArgs A)
         }
         Hit h[RPT]; int amb[RPT];
         if (ARITH == ORT_ARITH_FAST) {      // CTA-uniform choice between the general and the no-mirror fast path
-            if (mirror) trace_fast<RPT, false, SurfK*, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+            if (simple) trace_fast<RPT, false, SurfK*, false, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+            else if (mirror) trace_fast<RPT, false, SurfK*, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
             else trace_fast<RPT, false, SurfK*, false>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
         }
 #pragma unroll
@@ -737,18 +744,30 @@ cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* 
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from ort_api.cu)
 // ------------------------------------------------------------------------------------------
-int grid_rays_per_thread(int arith) { return arith == ORT_ARITH_FAST ? ORT_FAST_RPT : 1; }
+// kernel variant of a FAST sweep: 0 general, 1 EXT (OPD / apertures / polynomial terms), 2 SIMPLE; STRICT has 0 and 1
+int grid_variant(const Presc& P, int arith, int ext)
+{
+    if (ext || P.poly) return 1;
+    return (arith == ORT_ARITH_FAST && P.simple && !P.has_mirror) ? 2 : 0;
+}
 
-int grid_blocks_per_sm(int arith, int ext)
+int grid_rays_per_thread(int arith, int variant)
+{
+    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : ORT_FAST_RPT) : 1;
+}
+
+int grid_blocks_per_sm(int arith, int variant)
 {
     int nb = 0;
     cudaError_t e;
-    if (arith == ORT_ARITH_FAST)
-        e = ext ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true>, ORT_TILE, 0)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false>, ORT_TILE, 0);
+    if (arith == ORT_ARITH_FAST && variant == 2)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 1, false, true>, ORT_TILE, 0);
+    else if (arith == ORT_ARITH_FAST)
+        e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true>, ORT_TILE, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false>, ORT_TILE, 0);
     else
-        e = ext ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, true>, ORT_TILE, 0)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, false>, ORT_TILE, 0);
+        e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, true>, ORT_TILE, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, false>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
@@ -760,7 +779,11 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool others = A.r || A.theta || A.wx || A.wy || A.flags || A.opd;
         const bool lean = !ext && !others && A.ex && A.ey && A.mask;
         const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
-        if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        const bool simple = grid_variant(P, arith, ext) == 2;
+        if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);

@@ -36,7 +36,7 @@ struct ort_ctx {
     int rows;
     bool have_layout;
     int fast_ok_layout;         // fast_ok as derived from R, t, n, K alone (polynomial terms force it to 0 while set)
-    int bps[2][2];              // resident CTAs/SM of k_grid<STRICT|FAST, EXT off|on>
+    int bps[2][3];              // resident CTAs/SM of k_grid<STRICT|FAST, variant general|EXT|SIMPLE> (grid_variant)
     void* slot[SL_COUNT];
     size_t slot_bytes[SL_COUNT];
     long long launches;
@@ -147,9 +147,9 @@ int ort_init(ort_ctx** out, int device)
     for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) { CKI(cudaEventCreate(&ctx->prof_ev[i][0])); CKI(cudaEventCreate(&ctx->prof_ev[i][1])); }
 #undef CKI
-    for (int e = 0; e < 2; e++) {
-        ctx->bps[ORT_ARITH_STRICT][e] = grid_blocks_per_sm(ORT_ARITH_STRICT, e);
-        ctx->bps[ORT_ARITH_FAST][e] = grid_blocks_per_sm(ORT_ARITH_FAST, e);
+    for (int v = 0; v < 3; v++) {
+        ctx->bps[ORT_ARITH_STRICT][v] = grid_blocks_per_sm(ORT_ARITH_STRICT, v);
+        ctx->bps[ORT_ARITH_FAST][v] = grid_blocks_per_sm(ORT_ARITH_FAST, v);
     }
     *out = ctx;
     return ORT_OK;
@@ -248,6 +248,10 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
             P.fast_ok = 0;
         if (!(n[i] > 0.0) || !(n[i + 1] > 0.0)) P.has_mirror = 1;      // reflection (n2 = -n1) or anything unusual
     }
+    const double L = gap_scale(t, rows);
+    P.simple = P.fast_ok && !P.has_mirror;
+    for (int i = 0; i + 1 < rows; i++)
+        if (!simple_surface(P.s[i], L)) P.simple = 0;
     ctx->rows = rows;
     ctx->have_layout = true;
     ctx->fast_ok_layout = P.fast_ok;
@@ -359,10 +363,11 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
 
 static int grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsigned NN)
 {
+    const int variant = grid_variant(ctx->presc, arith, ext);
     const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;
-    const unsigned rpt = (unsigned)grid_rays_per_thread(arith);
+    const unsigned rpt = (unsigned)grid_rays_per_thread(arith, variant);
     const unsigned ntiles = (nsub + rpt - 1) / rpt;
-    long long gx = (long long)ctx->sm_count * ctx->bps[arith][ext ? 1 : 0] / n_fields;
+    long long gx = (long long)ctx->sm_count * ctx->bps[arith][variant] / n_fields;
     if (gx < 1) gx = 1;
     if (gx > (long long)ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
