@@ -596,7 +596,7 @@ k_candidates(CandArgs A)
         if (ARITH == ORT_ARITH_FAST && !simple_surface(s_surf[i], gap_scale(Rc + rows, rows))) atomicOr(&s_general, 1);
     } else if (AIMED && threadIdx.x == rows - 1) {
         derive_surface(s_surf[rows - 1], CUDART_INF, 0.0, rec[5], Rc[3 * rows - 1], 1.0);
-        if (!(Rc[3 * rows - 1] > 0.0)) atomicOr(&s_general, 1);
+        if (!simple_surface(s_surf[rows - 1], 0.0)) atomicOr(&s_general, 1);
     }
     __syncthreads();
     // per-candidate scalars live in shared memory (the shared-grid variant reads them from the constant bank):

@@ -96,3 +96,36 @@ def test_random_system_grid_mask(ctx, orc, ort, seed):
             sc = max(np.abs(g["ex"][m]).max(), np.abs(g["ey"][m]).max(), 10.0)
             assert np.abs(r["ex"][0][m] - g["ex"][m]).max() / sc < 1e-11
             assert np.abs(r["ey"][0][m] - g["ey"][m]).max() / sc < 1e-11
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_simple_prescription_grid_mask(ctx, orc, ort, seed):
+    """Prescriptions of refracting spheres and planes only take the SIMPLE instantiation of the fast sweep (three-body
+    surface loop, division-free sphere body): hostile over-sized pupils -- most rays miss a surface, cross it at or past
+    its equator, or are totally reflected -- must give the oracle's mask, flags and kept count, and its positions within
+    1e-12 of the position scale on the kept rays."""
+    rng = np.random.default_rng(3000 + seed)
+    S = random_system(rng, mirrors=False, conics=False)
+    if seed % 4 == 3:                                   # a steep surface: equator hits
+        S[1, 0] = rng.choice([-1, 1]) * rng.uniform(9.0, 14.0)
+    K = np.zeros(S.shape[0] + 1)
+    ext = np.vstack([S[:, :3], [np.inf, 0.0, 1.0]])
+    ext[-2, 1] = rng.uniform(20.0, 80.0)
+    stop = int(rng.integers(1, ext.shape[0] - 1))
+    a_stop = rng.uniform(3.0, 12.0)
+    half = (8.0, 16.0, 30.0, 45.0)[seed % 4]
+    ys, xs = np.linspace(-half, half, 97), np.linspace(0, half, 53)
+    u = rng.uniform(-0.25, 0.25)
+    g = orc.grid_trace(ext, ys, xs, stop, a_stop, 0.25, u=u, v=0.0, K=K)
+    ctx.set_layout(ext, K)
+    for want in (("ex", "ey", "mask", "flags", "stats"), ("ex", "ey", "mask", "stats")):     # general / lean output set
+        r = ctx.trace3d_grid([dict(u=u, v=0.0, h_prime=0.25)], ys, xs, stop, a_stop, arith=ort.FAST, want=want)
+        assert np.array_equal(r["mask"][0], g["mask"])
+        if "flags" in want:
+            assert np.array_equal(r["flags"][0], g["flags"])
+        assert int(r["stats"]["n_kept"][0]) == g["n_kept"]
+        m = g["mask"].astype(bool)
+        if m.any():
+            sc = max(np.abs(g["ex"][m]).max(), np.abs(g["ey"][m]).max(), 10.0)
+            assert np.abs(r["ex"][0][m] - g["ex"][m]).max() / sc < TOL
+            assert np.abs(r["ey"][0][m] - g["ey"][m]).max() / sc < TOL
