@@ -133,6 +133,9 @@ struct TransferArgs {
 #ifndef ORT_BPSP
 #define ORT_BPSP 2                          // ... and its resident CTAs/SM (128 registers, no spills)
 #endif
+#ifndef ORT_GRID_WAVES_DEFAULT
+#define ORT_GRID_WAVES_DEFAULT 8            // CTA waves per grid sweep (grid_dims in ort_api.cu)
+#endif
 int grid_variant(const Presc& P, int arith, int ext);
 int grid_rays_per_thread(int arith, int variant);
 int grid_blocks_per_sm(int arith, int variant);

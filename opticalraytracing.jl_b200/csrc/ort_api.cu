@@ -8,6 +8,7 @@
 
 #include <new>
 
+#include <stdlib.h>
 #include "kern.cuh"
 
 namespace {
@@ -367,8 +368,18 @@ static int grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsig
     const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;
     const unsigned rpt = (unsigned)grid_rays_per_thread(arith, variant);
     const unsigned ntiles = (nsub + rpt - 1) / rpt;
-    long long gx = (long long)ctx->sm_count * ctx->bps[arith][variant] / n_fields;
-    if (gx < 1) gx = 1;
+    // Several waves of CTAs instead of one persistent wave: the warp schedulers favour the older of the resident CTAs, so
+    // with one wave of equal shares the CTAs of an SM finish far apart and the SM idles at half occupancy in between
+    // (ncu: 3.4 of 4 warps per scheduler active on average).  With 8 waves the block scheduler refills the slot:
+    // 2.23 ms vs 2.34 (4, 16 waves: 2.25, 2.23; 32: 2.26 -- every CTA first traces its field's centre ray).  A CTA
+    // keeps at least 16 tiles so that prologue stays amortised; the per-CTA partial sums still belong to a fixed set
+    // of tiles, so the statistics stay bit-reproducible.  ORT_GRID_WAVES overrides (tuning).
+    static const int waves = [] { const char* e = getenv("ORT_GRID_WAVES"); const int w = e ? atoi(e) : ORT_GRID_WAVES_DEFAULT; return w < 1 ? 1 : w; }();
+    long long slots = (long long)ctx->sm_count * ctx->bps[arith][variant] / n_fields;
+    if (slots < 1) slots = 1;
+    long long gx = (long long)ntiles / 16;
+    if (gx < slots) gx = slots;
+    if (gx > slots * waves) gx = slots * waves;
     if (gx > (long long)ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     return (int)gx;

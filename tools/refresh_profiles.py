@@ -93,13 +93,14 @@ def main():
                           (f"bench_ref_{tag}.json", "r01_bench_reference_arm.json")):
         if os.path.exists(os.path.join(go, src_name)):
             shutil.copy(os.path.join(go, src_name), os.path.join(pr, dst))
-    # SASS of the dominant kernel (proof of what runs: DFMA / MUFU.RCP64H / MUFU.RSQ64H, LDCU uniform operands)
+    # SASS of the dominant kernel (proof of what runs: DFMA / MUFU.RCP64H / MUFU.RSQ64H, LDCU uniform operands):
+    # k_grid<FAST, 3 rays/thread, spot + mask, no-mirror, SIMPLE>
     lib = os.path.join(ROOT, "opticalraytracing.jl_b200", "lib", "libort_b200.so")
-    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_Z6k_gridILi1ELi2ELb0ELi1ELb0EEv5Presc8GridArgs', lib],
+    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_Z6k_gridILi1ELi3ELb0ELi1ELb0ELb1EEv5Presc8GridArgs', lib],
                           capture_output=True, text=True).stdout
     keep = [ln.split('/*', 2)[0].rstrip() + '  ' + ln.split('*/', 1)[1].rsplit('/*', 1)[0].rstrip() if '*/' in ln and ln.strip().startswith('/*') else ln
             for ln in sass.splitlines() if not ln.strip().startswith('/* 0x')]
-    open(os.path.join(pr, "r01_k_grid_fast_rpt2.sass"), "w").write("\n".join(keep) + "\n")
+    open(os.path.join(pr, "r01_k_grid_fast_simple_rpt3.sass"), "w").write("\n".join(keep) + "\n")
     print(json.dumps(summ["_derived"], indent=1))
 
 
