@@ -241,3 +241,25 @@ def test_vignetting_host_equals_oracle(ort, pre, be, cooke):
         for k in ("limit", "partial", "full"):
             assert list(getattr(h, k)) == list(getattr(o, k))
     assert list(ort.vignetting(cooke, backend=be).partial) == [1, 2, 3, 6, 7]  # test/runtests.jl:243
+
+
+def test_sphere_root_forms_error_study(tmp_path):
+    """The SIMPLE kernels take the ray-sphere path parameter division-free, s = (G - sqrt(disc)) / (c n1^2) (DESIGN.md
+    section 4).  tools/sphere_root_forms.c traces the bench lens in double with both forms and in 80-bit arithmetic: the
+    division-free form must stay as accurate as the one with the division at the lens's own radii, and its error must
+    grow no faster than ~ eps |R| for a weak surface -- the bound behind the |R| <= 64 L admission rule."""
+    import re
+    import subprocess
+    exe = tmp_path / "srf"
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sphere_root_forms.c")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), src, "-lm"])
+    out = subprocess.run([str(exe), "1500"], capture_output=True, text=True, check=True).stdout
+    rows = {}
+    for line in out.splitlines():
+        m = re.match(r"(.*?)\s+stable (\S+)\s+cheap (\S+)\s+centre (\S+)", line)
+        rows[m.group(1).strip()] = tuple(float(m.group(i)) for i in (2, 3, 4))
+    nominal = rows["double-Gauss, nominal radii"]
+    assert nominal[0] < 1e-14 and nominal[1] < 1e-14
+    assert rows["surface 2 with R = 1e+04"][1] < 2e-14           # 64 L = 8.8e3 mm for this lens
+    assert rows["surface 2 with R = 1e+06"][1] < 2e-12           # ~ eps |R|: two decades of R, two decades of error
+    assert rows["surface 2 with R = 1e+06"][0] < 1e-14           # the form with the division does not care

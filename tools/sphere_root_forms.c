@@ -1,4 +1,4 @@
-/* sphere_root_forms.c -- error study for the two algebraically equal forms of the ray-sphere path parameter in the
+/* sphere_root_forms.c -- error study for the three algebraically equal forms of the ray-sphere path parameter in the
  * FAST (K-form) tracer of csrc/ort_internal.cuh:
  *
  *     stable     s = F / (G + sqrt(disc))            one division per sphere (4 DFMA/DMUL + 1 MUFU after the seed)
@@ -11,7 +11,7 @@
  * 80-bit long double (stable form = truth), and prints the worst image-plane error of each form relative to the
  * position scale, for the nominal radii and for the same lens with one weak surface of growing radius.
  *
- *   gcc -O2 -ffp-contract=off -o /tmp/srf tools/sphere_root_forms.c -lm && /tmp/srf
+ *   gcc -O2 -ffp-contract=off -o srf tools/sphere_root_forms.c -lm && ./srf [rays per study, default 20000]
  */
 #include <math.h>
 #include <stdio.h>
@@ -87,12 +87,14 @@ static void trace_centre(double y0, double x0, double u, double v, double* xo, d
 
 static double urand(void) { return (double)rand() / RAND_MAX; }
 
+static int n_rays = 20000;
+
 static void study(const char* label)
 {
     double worst_s = 0, worst_c = 0, worst_z = 0;
     const double scale = 25.0;
     srand(1);
-    for (int k = 0; k < 20000; k++) {
+    for (int k = 0; k < n_rays; k++) {
         const double y0 = -16 + 32 * urand(), x0 = 16 * urand(), u = tan(0.2374 * urand());
         double xs, ys, xc, yc, xz, yz; long double xt, yt;
         trace_truth(y0, x0, u, 0.0, &xt, &yt);
@@ -110,8 +112,9 @@ static void study(const char* label)
     printf("%-34s stable %.2e   cheap %.2e   centre %.2e   (relative to %.0f mm)\n", label, worst_s, worst_c, worst_z, scale);
 }
 
-int main(void)
+int main(int argc, char** argv)
 {
+    if (argc > 1) n_rays = atoi(argv[1]);
     study("double-Gauss, nominal radii");
     const double weak[] = {1e3, 1e4, 1e5, 1e6, 1e8};
     for (int w = 0; w < 5; w++) {
