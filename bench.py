@@ -195,7 +195,7 @@ def _main(real_stdout):
     d_mask = torch.empty((nf, NN), dtype=torch.uint8, device=dev)
     # statistics records go through a ring of RING buffers so the all-gather of step k (NCCL's own stream) overlaps
     # the traces of the following steps (launching stream); a buffer is reused only after its gather has completed.
-    # RING = 4: the persistent k_grid fills every SM, so a gather kernel may only find a free slot at a later kernel
+    # RING = 4: k_grid fills every SM, so a gather kernel may only find a free slot at a later CTA or kernel
     # boundary; with four buffers in flight its latency and the inter-rank skew stay off the critical path.
     RING = 4
     d_stats2 = [torch.zeros((nf, SB), dtype=torch.uint8, device=dev) for _ in range(RING)]

@@ -622,7 +622,7 @@ cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaS
     const long long per = 256 * PX_RPT;
     const long long ntl = (A.N + per - 1) / per;
     if (ntl == 0) return cudaSuccess;
-    const unsigned nb = (unsigned)(ntl < 148 * 8 ? ntl : 148 * 8);     // persistent: 8 CTAs of 256 threads per SM
+    const unsigned nb = (unsigned)(ntl < 148 * 8 ? ntl : 148 * 8);     // 1.6 waves of the 5 resident CTAs/SM; whole-wave grids measured slower
     const bool table = A.y_all || A.w_all;
     const bool clip = L.clip != 0;
 #define PX_LAUNCH(AR, TB, CL) k_paraxial<AR, TB, CL><<<nb, 256, 0, st>>>(L, A)

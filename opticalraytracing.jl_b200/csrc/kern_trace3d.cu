@@ -5,7 +5,8 @@
 //                      registers, prescription in the constant bank (__grid_constant__ kernel
 //                      parameter), fused mask / eps / r / theta / wavegrad epilogue, per-thread
 //                      shifted-moment accumulation + warp-shuffle reduction for the spot statistics.
-//                      Persistent: gridDim.x * gridDim.y CTAs = SMs * resident CTAs/SM, tile-strided.
+//                      Tile-strided CTAs, gridDim.x * gridDim.y = SMs * resident CTAs/SM * waves (grid_dims, ort_api.cu).
+//                      SIMPLE instantiation for prescriptions of refracting spheres and planes (three-body surface loop).
 //   k_grid_finalize    K6: deterministic fold of the per-CTA partials into ort_stats per field.
 //   k_tile_scan / k_compact   ordered compaction in the reference's push! order (:134-137).
 //   k_rays<ARITH>      arbitrary rays, every surface recorded (raytrace(...,Vector{RealRay}) :34-65).
