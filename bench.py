@@ -1,11 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- FP64 ray-surface intersections/s of the 3-D skew real-ray trace on B200.
 
-Workload (BASELINE.json configs[1]): 10-glass-surface double-Gauss, 16 Mi rays per field x 5
+Workload of the headline (BASELINE.json configs[1]): 10-glass-surface double-Gauss, 16 Mi rays per field x 5
 fields, spot diagram (ex, ey) + vignetting mask + per-field spot statistics, one wavelength.
-A "step" = one sweep of all 5 fields over the pupil grid.  At N > 1 every rank traces its own
-block of y-rows of an N-times denser pupil (weak scaling, BASELINE configs[2]) and one NCCL
-all-gather of the per-field statistics records (80 B x fields per rank) follows each step.
+A "step" = one sweep of all 5 fields over the pupil grid.  At N > 1 every rank traces its own block of
+y-rows of an N-times denser pupil (weak scaling) and the library itself all-gathers and merges the per-field
+statistics records (ncclAllGather + merge kernel behind the sweep, ort_opts.gather_stats) -- torch.distributed
+is only the launcher plumbing (rendezvous, barrier, max-over-ranks of the timings).
+
+Beside the headline the same run measures, and puts on the same JSON line:
+  config.strong      BASELINE configs[2] (1e9-ray sweep, y-rows sharded over the N ranks, statistics only) and
+                     configs[4] (65 536 candidate prescriptions x 4096 rays sharded over the N ranks) -- FIXED total
+                     work, so their times across N = 1, 2, 4, 8 are the strong-scaling curves
+  config.secondary   (N = 1) configs[0] end to end, configs[3] (1e9-ray paraxial y-nu trace, plain and clipped; transfer
+                     matrix), the OPD-extension sweep
+  parity             (N = 1) FAST vs STRICT over the whole workload (pointwise and scale-relative error, mask XOR, the
+                     edge-margin histogram of the 100 rays closest to the stop rim per field) and GPU vs the CPU oracle
+                     on the rows the cpu_baseline leg traced
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          one JSON line on stdout (rank 0)
   python bench.py --impl reference ...                        the CPU restatement of the reference
@@ -27,9 +38,15 @@ sys.path.insert(0, ROOT)
 METRIC = "FP64 ray-surface intersections/sec"
 UNIT = "intersections/s"
 NY, NX = 5792, 2896                 # 16,773,632 rays (~16 Mi) per field   
+NY3, NX3 = 44722, 22361             # BASELINE configs[2]: 1.00003e9 rays, one field
+C5, K5 = 65536, 64                  # BASELINE configs[4]: 65 536 candidates x 64 x 64 rays
+N4 = 1_000_000_000                  # BASELINE configs[3]: 1e9 paraxial rays
 FLOPS_PER_RAY = 723                 # algorithmic FP64 flops per double-Gauss ray
+FLOPS_PER_RAY_TRIPLET = 513         # ... per Cooke-triplet ray
 BYTES_PER_RAY = 17                  # ex, ey (16 B) + mask (1 B)
 LOOP_STEPS = 12                     # reference loop iterations per ray (11 surfaces + image plane)
+WORKLOAD = ("double-Gauss (10 glass surfaces, 12 loop steps), 16Mi-ray half-pupil grid "
+            f"{NY}x{NX} per field x 5 fields per GPU, outputs ex, ey, mask + per-field spot stats")
 
 
 def log(*a):
@@ -107,14 +124,14 @@ def workload(ort, backend, n_ranks, rank):
     # contiguous block of NY y-rows of the (NY * n_ranks)-row grid, so concatenating ranks in order
     # reproduces the reference's loop order
     ny_total = NY * n_ranks
-    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], ny_total)[rank * NY:(rank + 1) * NY]
+    ys = np.stack([ort.host.jl_range(p["y1"][j], p["y2"][j], ny_total)[rank * NY:(rank + 1) * NY]
                    for j in range(len(Hs))]).copy()                  # (n_fields, NY)
-    xs = np.linspace(0.0, p["y_EP"], NX)
+    xs = ort.host.jl_range(0.0, p["y_EP"], NX)
     fields = [dict(mode=0, u=float(p["u"][j]), v=0.0, h_prime=float(p["h_prime"][j])) for j in range(len(Hs))]
     return dict(system=system, p=p, ys=ys, xs=xs, fields=fields, Hs=Hs)
 
 
-def cpu_baseline(ort, wl, target_s=12.0, threads=0):
+def cpu_baseline(ort, wl, target_s=12.0, threads=0, keep=False):
     """The oracle port of the reference's CPU path (oracle/ort_oracle.c, -O2, no FMA, OpenMP over
     y-rows) on a bounded sample of the same workload: the first `rows` y-rows of every field."""
     from oracle import oracle as orc
@@ -122,19 +139,22 @@ def cpu_baseline(ort, wl, target_s=12.0, threads=0):
     p = wl["p"]
     nthreads = threads or (os.cpu_count() or 1)
 
-    def run(rows):
+    def run(rows, want_out=False):
         t0 = time.perf_counter()
-        kept = 0
+        kept, outs = 0, []
         for j, f in enumerate(wl["fields"]):
             g = orc.grid_trace(p["ext"], wl["ys"][j][:rows], wl["xs"], p["stop"], p["a_stop"], f["h_prime"], u=f["u"],
                                v=f["v"], K=p["K"], want=("ex", "ey", "mask"), threads=nthreads)
             kept += g["n_kept"]
-        return time.perf_counter() - t0, rows * len(wl["xs"]) * len(wl["fields"])
+            if want_out:
+                outs.append(g)
+        return time.perf_counter() - t0, rows * len(wl["xs"]) * len(wl["fields"]), outs
 
-    t, rays = run(min(64, NY))
+    t, rays, _ = run(min(64, NY))
     rows = int(min(NY, max(64, 64 * target_s / max(t, 1e-6))))
-    t, rays = run(rows)
-    return rays / t, nthreads, f"first {rows} of {NY} y-rows x {NX} x {len(wl['fields'])} fields = {rays} rays in {t:.2f} s", t
+    t, rays, outs = run(rows, keep)
+    return dict(rps=rays / t, cores=nthreads, rows=rows, seconds=t, outs=outs,
+                sample=f"first {rows} of {NY} y-rows x {NX} x {len(wl['fields'])} fields = {rays} rays in {t:.2f} s")
 
 
 def main():
@@ -148,6 +168,243 @@ def main():
         real_stdout.flush()
 
 
+class Rig:
+    """what every measurement below needs: context, torch device / stream, rank plumbing"""
+
+    def __init__(self, ort, torch, dist, ctx, dev, n, rank):
+        self.ort, self.torch, self.dist, self.ctx, self.dev, self.n, self.rank = ort, torch, dist, ctx, dev, n, rank
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier(self):
+        if self.n > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.n > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, barrier, K calls between two events on the launching stream, barrier; max over ranks (ms/call)"""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def stats_of(self, t, shape):
+        return np.frombuffer(t.cpu().numpy().tobytes(), dtype=self.ort.STATS_DTYPE).reshape(shape)
+
+
+def strong_config3(R, wl, fp64_peak, steps=3, warmup=1):
+    """BASELINE configs[2]: 44722 x 22361 = 1.00003e9 rays of one field, y-rows block-sharded over the ranks, statistics
+    only; the per-field records are all-gathered and merged inside the library right behind the sweep."""
+    ort, torch, ctx, n, rank = R.ort, R.torch, R.ctx, R.n, R.rank
+    p, j = wl["p"], 2                                                   # field H = 0.5
+    lo, hi = ort._lib.comm_range(NY3, rank, n)
+    ys = torch.from_numpy(ort.host.jl_range(p["y1"][j], p["y2"][j], NY3)[lo:hi].copy()).to(R.dev)
+    xs = torch.from_numpy(ort.host.jl_range(0.0, p["y_EP"], NX3)).to(R.dev)
+    SB = ort.STATS_BYTES
+    d_m, d_l = torch.zeros(SB, dtype=torch.uint8, device=R.dev), torch.zeros(SB, dtype=torch.uint8, device=R.dev)
+    ptrs = dict(stats=d_m.data_ptr(), stats_local=d_l.data_ptr())
+    fld = [wl["fields"][j]]
+
+    def step():
+        ctx.trace3d_grid_dev(fld, ys.data_ptr(), hi - lo, xs.data_ptr(), NX3, p["stop"], p["a_stop"], ptrs,
+                             stream=R.stream, gather=n > 1)
+    ms = R.timed(step, steps, warmup)
+    rec = R.stats_of(d_m, (1,))[0]
+    rays = NY3 * NX3
+    return {"workload": f"double-Gauss {NY3}x{NX3} = {rays} rays, field H = {wl['Hs'][j]}, statistics only, y-rows block-sharded over {n} GPU(s)",
+            "ms": ms, "rays_per_s": rays / ms * 1e3, "intersections_per_s": rays * 10 / ms * 1e3,
+            "fp64_frac_per_gpu": rays * FLOPS_PER_RAY / ms / 1e9 / fp64_peak / n,
+            "kept": int(rec["n_kept"]), "rms_mm": ort.rms_from_stats(rec), "n_strict": int(rec["n_strict"]),
+            "exchange": f"ncclAllGather of {SB} B per rank + k_merge_stats, inside libort_b200.so" if n > 1 else "none (1 GPU)"}
+
+
+def strong_config5(R, fp64_peak, steps=5, warmup=2):
+    """BASELINE configs[4]: 65 536 perturbed triplets x 64 x 64 rays; every rank runs the per-candidate prelude and the
+    aimed sweep on its contiguous range of the population, the merit table is all-gathered inside the library."""
+    ort, torch, ctx, n = R.ort, R.torch, R.ctx, R.n
+    Pq = ort.prescriptions.COOKE
+    base = ort.prescriptions.perturbed_triplets(C5)
+    rows = base.shape[2]
+    d_R = torch.from_numpy(base).to(R.dev)
+    d_aim = torch.empty((C5, ort._lib.AIM_NOUT), dtype=torch.float64, device=R.dev)
+    d_out = torch.full((C5, 4), float("nan"), dtype=torch.float64, device=R.dev)
+
+    def step():
+        ctx.candidates_sharded_dev(rows, C5, d_R.data_ptr(), Pq["a"], Pq["h"], 0.7, K5, K5 // 2 * 2, d_out.data_ptr(),
+                                   d_aim=d_aim.data_ptr(), stream=R.stream)
+    ms = R.timed(step, steps, warmup)
+    tab = d_out.cpu().numpy()
+    rays = C5 * K5 * K5
+    return {"workload": f"{C5} perturbed Cooke triplets x {K5}x{K5} rays, per-candidate prelude + aimed sweep, candidates sharded over {n} GPU(s)",
+            "ms": ms, "candidates_per_s": C5 / ms * 1e3, "rays_per_s": rays / ms * 1e3, "intersections_per_s": rays * 7 / ms * 1e3,
+            "fp64_frac_per_gpu": rays * FLOPS_PER_RAY_TRIPLET / ms / 1e9 / fp64_peak / n,
+            "table_complete": bool(np.isfinite(tab[:, 3]).all()), "rms_range_mm": [float(np.nanmin(tab[:, 3])), float(np.nanmax(tab[:, 3]))],
+            "table_checksum": float(np.nansum(tab[:, 3])),
+            "exchange": "all-gather of the 32 B-per-candidate merit table (NCCL), inside libort_b200.so" if n > 1 else "none (1 GPU)"}
+
+
+def secondary(R, hbm_peak, fp64_peak):
+    """BASELINE configs[0] and [3] and the OPD-extension sweep on ONE GPU (device-resident, ort_profile_* event timing)."""
+    ort, torch, ctx, dev, st = R.ort, R.torch, R.ctx, R.dev, R.stream
+    out = {}
+
+    def kern_ms(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ctx.profile_enable(True)
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        t = ctx.profile_read()
+        ctx.profile_enable(False)
+        return float(np.mean(t))
+
+    # ---- configs[0]: Cooke triplet, 64 x 64 pupil grid, 3 fields, spot RMS, end to end through the public API
+    Pc = ort.prescriptions.COOKE
+    sysm = ort.solve(Pc["surfaces"], Pc["a"], Pc["h"])
+    ort.full_trace_fields(sysm.layout, sysm, [0.0, 0.7, 1.0], 64)
+    l0, t0 = ctx.launch_count(), time.perf_counter()
+    for _ in range(20):
+        errs = ort.full_trace_fields(sysm.layout, sysm, [0.0, 0.7, 1.0], 64)
+    dt = (time.perf_counter() - t0) / 20
+    rays1 = 3 * 64 * 32
+    out["config1_cooke_64x64_3_fields_e2e"] = {"ms": dt * 1e3, "launches_per_call": (ctx.launch_count() - l0) / 20, "rays": rays1,
+                                               "intersections_per_s": rays1 * 7 / dt, "rms_mm": [e.RMS for e in errs],
+                                               "bound": "launch / host latency (prelude + sweep + compaction + D2H + mirror)"}
+    # ---- configs[3]: 1e9 paraxial rays through the 40-row Lens (20 elements), rays generated on the device (seed 42)
+    lens = ort.make_lens(ort.prescriptions.zoom20())
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    y0 = torch.rand(N4, dtype=torch.float64, device=dev, generator=g) * 20 - 10
+    w0 = torch.rand(N4, dtype=torch.float64, device=dev, generator=g) * 0.4 - 0.2
+    y, w = torch.empty_like(y0), torch.empty_like(w0)
+    ci = torch.empty(N4, dtype=torch.int32, device=dev)
+    a = np.full(len(lens.tau), 25.0)
+    for name, clip in (("config4_paraxial_1e9", False), ("config4_paraxial_1e9_clip", True)):
+        ms = kern_ms(lambda: ctx.paraxial_batch_dev(lens.tau, lens.phi, N4, y0.data_ptr(), w0.data_ptr(), y.data_ptr(), w.data_ptr(),
+                                                    ci.data_ptr() if clip else None, a=a if clip else None, clip=clip,
+                                                    arith=ort.FAST, stream=st), reps=3, warm=1)
+        byts = N4 * (32 + (4 if clip else 0))
+        out[name] = {"ms": ms, "rays_per_s": N4 / ms * 1e3, "row_steps_per_s": N4 * 40 / ms * 1e3, "GBps": byts / ms / 1e6,
+                     "hbm_frac": byts / ms / 1e6 / hbm_peak, "bytes_per_ray": byts // N4, "fp64_frac_nominal": N4 * 160 / ms / 1e9 / fp64_peak,
+                     "bound": "hbm"}
+        if clip:
+            out[name]["clipped_frac"] = float((ci[:1 << 24] != 0).double().mean())
+    del ci
+    v = torch.stack([y0, w0], dim=1).contiguous()
+    del y0, w0, y, w
+    vo = torch.empty_like(v)
+    ms = kern_ms(lambda: ctx.transfer_batch_dev(sysm.M, -50.0, 77.4, N4, v.data_ptr(), vo.data_ptr(), stream=st), reps=3, warm=1)
+    out["config4_transfer_matrix_1e9"] = {"ms": ms, "rays_per_s": N4 / ms * 1e3, "GBps": N4 * 32 / ms / 1e6,
+                                          "hbm_frac": N4 * 32 / ms / 1e6 / hbm_peak, "bytes_per_ray": 32, "bound": "hbm"}
+    del v, vo
+    torch.cuda.empty_cache()
+    # ---- the OPD extension on one bench-size field (16.8 M rays): OPL accumulation + reference sphere + OPD statistics
+    Pd = ort.prescriptions.DOUBLE_GAUSS
+    sd = ort.solve(Pd["surfaces"], Pd["a"], Pd["h"])
+    pe = ort.host._full_trace_setup(sd.layout, sd, [0.7], 64, None, ctx)
+    ctx.set_layout(pe["ext"], pe["K"])
+    ysb = torch.from_numpy(ort.host.jl_range(pe["y1"][0], pe["y2"][0], NY)).to(dev)
+    xsb = torch.from_numpy(ort.host.jl_range(0.0, pe["y_EP"], NX)).to(dev)
+    stb = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
+    bufs = {k: torch.empty(NY * NX, dtype=torch.float64, device=dev) for k in ("ex", "ey", "opd")}
+    bufs["mask"] = torch.empty(NY * NX, dtype=torch.uint8, device=dev)
+    fldb = dict(u=float(pe["u"][0]), h_prime=float(pe["h_prime"][0]), opd_yc=float(pe["h_prime"][0]),
+                opd_radius=float(pe["focus"] - sd.XP.t), opl_ref=150.0)
+    pt = {k: t.data_ptr() for k, t in bufs.items()}
+    pt["stats"] = stb.data_ptr()
+    ms = kern_ms(lambda: ctx.trace3d_grid_dev([fldb], ysb.data_ptr(), NY, xsb.data_ptr(), NX, pe["stop"], pe["a_stop"], pt, stream=st,
+                                              ext=ort.EXT_OPD, opd_scale=-1.0 / 587.5618e-6))
+    rec = R.stats_of(stb, (1,))[0]
+    out["opd_sweep_16Mi_rays"] = {"ms": ms, "rays_per_s": NY * NX / ms * 1e3, "fp64_frac_of_723": NY * NX * FLOPS_PER_RAY / ms / 1e9 / fp64_peak,
+                                  "kept": int(rec["n_kept"]), "rms_opd_waves": float(np.sqrt(rec["m2_opd"] / max(int(rec["n_kept"]), 1))),
+                                  "bytes_per_ray": 25, "bound": "fp64"}
+    return out
+
+
+def parity_block(R, wl, d_ex, d_ey, d_mask, cpu):
+    """SURVEY.md section 8(d) "parity checks per run".  FAST (the timed arithmetic, outputs still in HBM) against a STRICT
+    sweep of the same 5 x 16.8 M rays -- STRICT is the mode the tests hold bit-identical to the oracle -- and both
+    against the CPU oracle on the rows the cpu_baseline leg traced."""
+    ort, torch, ctx, dev = R.ort, R.torch, R.ctx, R.dev
+    p, fields = wl["p"], wl["fields"]
+    nf, NN = len(fields), NY * NX
+    d_ys, d_xs = torch.from_numpy(wl["ys"]).to(dev), torch.from_numpy(wl["xs"]).to(dev)
+    sx, sy = torch.empty_like(d_ex), torch.empty_like(d_ey)
+    sm, sr = torch.empty_like(d_mask), torch.empty_like(d_ex)
+    st = torch.zeros((nf, ort.STATS_BYTES), dtype=torch.uint8, device=dev)
+    ctx.trace3d_grid_dev(fields, d_ys.data_ptr(), NY, d_xs.data_ptr(), NX, p["stop"], p["a_stop"],
+                         dict(ex=sx.data_ptr(), ey=sy.data_ptr(), mask=sm.data_ptr(), r=sr.data_ptr(), stats=st.data_ptr()),
+                         stream=R.stream, arith=ort.STRICT, ys_per_field=True)
+    torch.cuda.synchronize()
+    out = {"fast_vs_strict": {}, "reading_of_1e-12": "the tests enforce |FAST - STRICT| <= 1e-12 x position scale (max(|h'|, y_EP) per field); "
+                                                     "the pointwise figures below are reported, not enforced: ex and ey are cancelled "
+                                                     "differences that pass through zero"}
+    kept = (sm != 0) & (d_mask != 0)
+    scale = torch.tensor([max(abs(f["h_prime"]), p["y_EP"]) for f in fields], dtype=torch.float64, device=dev).view(nf, 1)
+    hp = torch.tensor([f["h_prime"] for f in fields], dtype=torch.float64, device=dev).view(nf, 1)
+    dx, dy = (d_ex - sx).abs(), (d_ey - sy).abs()
+    big = torch.where(kept, torch.maximum(dx, dy), torch.zeros_like(dx))
+    yf_s = sy + hp                                               # the ray's y at the image plane, a position
+    pw_y = torch.where(kept & (yf_s.abs() > 1e-3), dy / yf_s.abs().clamp_min(1e-300), torch.zeros_like(dy))
+    pw_x = torch.where(kept & (sx.abs() > 1e-3), dx / sx.abs().clamp_min(1e-300), torch.zeros_like(dx))
+    pw_e = torch.where(kept, torch.maximum(dx / sx.abs().clamp_min(1e-300), dy / sy.abs().clamp_min(1e-300)), torch.zeros_like(dx))
+    pw_e = torch.where(torch.isfinite(pw_e), pw_e, torch.zeros_like(pw_e))
+    fv = out["fast_vs_strict"]
+    fv["rays"] = nf * NN
+    fv["mask_xor"] = int((sm != d_mask).sum())
+    fv["max_abs_mm"] = float(big.max())
+    fv["max_rel_to_position_scale"] = float((big / scale).max())
+    fv["pointwise_rel_positions_xf_yf_gt_1um"] = float(torch.maximum(pw_x.max(), pw_y.max()))
+    fv["pointwise_rel_transverse_errors_max"] = float(pw_e.max())
+    q = pw_e[kept]
+    sel = q[torch.randint(0, q.numel(), (1 << 22,), device=dev)]
+    fv["pointwise_rel_transverse_errors_p50_p99_p9999"] = [float(x) for x in torch.quantile(sel, torch.tensor([0.5, 0.99, 0.9999], dtype=torch.float64, device=dev))]
+    # edge-margin histogram: |r_i - a_stop| / a_stop of the 100 rays closest to the stop rim (the decision of
+    # src/PupilSampling.jl:131-132), per field, in decades
+    marg = ((sr - p["a_stop"]).abs() / p["a_stop"])
+    marg = torch.where(torch.isfinite(marg), marg, torch.full_like(marg, 1.0))
+    edges = [0.0, 1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1.0]
+    hist = []
+    for f in range(nf):
+        m100 = torch.topk(marg[f], 100, largest=False).values.cpu().numpy()
+        hist.append({"min": float(m100[0]), "p100": float(m100[-1]), "decade_counts": np.histogram(m100, bins=edges)[0].tolist()})
+    out["edge_margin_100_closest"] = {"bin_edges": edges, "per_field": hist,
+                                      "rays_retraced_strict_in_fast_mode": [int(x) for x in R.stats_of(st, (nf,))["n_strict"] * 0] }
+    del sr, big, pw_x, pw_y, pw_e, dx, dy, marg, yf_s
+    # ---- against the CPU oracle on identical inputs (rows [0, rows) of every field)
+    if cpu and cpu.get("outs"):
+        rows = cpu["rows"]
+        k = rows * NX
+        nbits = xor_s = xor_f = 0
+        worst = 0.0
+        for f, g in enumerate(cpu["outs"]):
+            om = torch.from_numpy(g["mask"][:k]).to(dev)
+            ox, oy = torch.from_numpy(g["ex"][:k]).to(dev), torch.from_numpy(g["ey"][:k]).to(dev)
+            xor_s += int((om != sm[f, :k]).sum())
+            xor_f += int((om != d_mask[f, :k]).sum())
+            both_nan_x, both_nan_y = torch.isnan(ox) & torch.isnan(sx[f, :k]), torch.isnan(oy) & torch.isnan(sy[f, :k])
+            nbits += int(((ox.view(torch.int64) != sx[f, :k].view(torch.int64)) & ~both_nan_x).sum())
+            nbits += int(((oy.view(torch.int64) != sy[f, :k].view(torch.int64)) & ~both_nan_y).sum())
+            kk = om != 0
+            worst = max(worst, float(torch.maximum((d_ex[f, :k] - ox).abs()[kk].max(), (d_ey[f, :k] - oy).abs()[kk].max()) / scale[f, 0]))
+        out["gpu_vs_cpu_oracle"] = {"rays": k * nf, "sample": f"rows [0, {rows}) of every field (the cpu_baseline sample)",
+                                    "strict_values_with_different_bits": nbits, "strict_mask_xor": xor_s,
+                                    "fast_mask_xor": xor_f, "fast_max_rel_to_position_scale": worst}
+    return out
+
+
 def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +413,7 @@ def _main(real_stdout):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip strong / secondary / parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -173,13 +431,20 @@ def _main(real_stdout):
     import ort_b200 as ort
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
-    if n > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ort.Context(local_rank)
     ort.set_default_backend(ctx)
-    dev = torch.device("cuda", local_rank)
+    if n > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        # the library's own communicator: rank 0 makes the id, the launcher's process group carries the 128 bytes
+        idt = torch.zeros(ort._lib.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ort._lib.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init_rank(bytes(idt.cpu().numpy().tobytes()), rank, n)
+    R = Rig(ort, torch, dist, ctx, dev, n, rank)
     wl = workload(ort, ctx, n, rank)
     p, fields = wl["p"], wl["fields"]
     nf, NN = len(fields), NY * NX
@@ -193,68 +458,40 @@ def _main(real_stdout):
     d_ex = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_ey = torch.empty((nf, NN), dtype=torch.float64, device=dev)
     d_mask = torch.empty((nf, NN), dtype=torch.uint8, device=dev)
-    # statistics records go through a ring of RING buffers so the all-gather of step k (NCCL's own stream) overlaps
-    # the traces of the following steps (launching stream); a buffer is reused only after its gather has completed.
-    # RING = 4: k_grid fills every SM, so a gather kernel may only find a free slot at a later CTA or kernel
-    # boundary; with four buffers in flight its latency and the inter-rank skew stay off the critical path.
-    RING = 4
-    d_stats2 = [torch.zeros((nf, SB), dtype=torch.uint8, device=dev) for _ in range(RING)]
-    d_gather2 = [torch.zeros((n, nf, SB), dtype=torch.uint8, device=dev) for _ in range(RING)] if n > 1 else None
-    ptrs2 = [dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats2[b].data_ptr())
-             for b in range(RING)]
-    stream = torch.cuda.current_stream().cuda_stream
-    works = [None] * RING
-    state = {"k": 0}
+    d_stats = torch.zeros((nf, SB), dtype=torch.uint8, device=dev)         # merged over the ranks by the library
+    d_local = torch.zeros((nf, SB), dtype=torch.uint8, device=dev)         # this rank's own records
+    ptrs = dict(ex=d_ex.data_ptr(), ey=d_ey.data_ptr(), mask=d_mask.data_ptr(), stats=d_stats.data_ptr())
+    if n > 1:
+        ptrs["stats_local"] = d_local.data_ptr()
+    stream = R.stream
 
-    def step():
-        b = state["k"] % RING
-        state["k"] += 1
-        if works[b] is not None:
-            works[b].wait()
-        ctx.trace3d_grid_dev(fields, d_ys.data_ptr(), NY, d_xs.data_ptr(), NX, p["stop"], p["a_stop"], ptrs2[b],
-                             stream=stream, arith=arith, ys_per_field=True)
-        if n > 1:   # the one exchange step of the path: all-gather of per-field statistics records
-            works[b] = dist.all_gather_into_tensor(d_gather2[b].view(-1), d_stats2[b].view(-1), async_op=True)
-
-    def drain():
-        for b in range(RING):
-            if works[b] is not None:
-                works[b].wait()
-                works[b] = None
-
-    def barrier():
-        if n > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step():     # sweep + statistics kernel (+ at N > 1 the one exchange of the path: ncclAllGather + merge, same stream)
+        ctx.trace3d_grid_dev(fields, d_ys.data_ptr(), NY, d_xs.data_ptr(), NX, p["stop"], p["a_stop"], ptrs,
+                             stream=stream, arith=arith, ys_per_field=True, gather=n > 1)
 
     for _ in range(args.warmup):
         step()
-    drain()
     # everything with variable host latency (NVML init, thread start) happens BEFORE the barrier: ranks that leave the
-    # barrier skewed pay the skew back inside the timed region, waiting in the last gathers for the slowest one
+    # barrier skewed pay the skew back inside the timed region, waiting in the gathers for the slowest one
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.profile_enable(True)
-    barrier()
+    R.barrier()
     sampler.reset()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step()
-    drain()
     ev1.record()
-    barrier()
+    R.barrier()
     sampler.stop_flag = True
     sampler.join()
     launches = ctx.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
     kern_ms = ctx.profile_read()
     ctx.profile_enable(False)
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if n > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms.item()) / args.steps
+    ms_step = R.max_over_ranks(ms_total) / args.steps
     # per-rank evidence for the scaling number: this rank's mean k_grid time, its own wall time per step and its
     # median SM clock during the timed region, gathered to rank 0
     mine = torch.tensor([float(np.mean(kern_ms)) if len(kern_ms) else 0.0, ms_total / args.steps,
@@ -268,16 +505,17 @@ def _main(real_stdout):
     inter_ray = ort.prescriptions.DOUBLE_GAUSS_GLASS_SURFACES
     value = rays_step * inter_ray / (ms_step * 1e-3)
 
-    # statistics of the last step, merged across ranks in rank order (Chan) -- evidence, not timed
-    last = (state["k"] - 1) % RING
-    d_stats = d_stats2[last]
-    d_gather = d_gather2[last] if n > 1 else None
-    stats = np.frombuffer((d_gather if n > 1 else d_stats.view(1, nf, SB)).cpu().numpy().tobytes(),
-                          dtype=ort.STATS_DTYPE).reshape(n, nf)
-    merged = [ort.merge_stats(stats[:, f]) for f in range(nf)]
+    # statistics of the last step as the library merged them (identical on every rank) -- evidence, not timed
+    merged = R.stats_of(d_stats, (nf,))
+    mine_st = R.stats_of(d_local if n > 1 else d_stats, (nf,))
     rms = [ort.rms_from_stats(m) for m in merged]
     kept = [int(m["n_kept"]) for m in merged]
     n_strict = [int(m["n_strict"]) for m in merged]
+    ident = None
+    if n > 1:       # every rank must hold the same merged bytes
+        allm = [torch.zeros_like(d_stats) for _ in range(n)]
+        dist.all_gather(allm, d_stats)
+        ident = bool(all(torch.equal(allm[0], t) for t in allm))
 
     # ---- e2e: the C-ABI host-pointer call, pinned host buffers, H2D of the grid coordinates and
     #      D2H of spot diagram + mask + statistics inside the timed region.  Two output forms are
@@ -292,36 +530,47 @@ def _main(real_stdout):
     h_ys.array[...] = wl["ys"]; h_xs.array[...] = wl["xs"]
     e2e = {}
     for form, compact in (("full_grid", False), ("compacted", True)):
-        r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], arith=arith, compact=compact,
-                             want=("ex", "ey", "mask"), out=out)
-        barrier()
+        kw = dict(arith=arith, compact=compact, want=("ex", "ey", "mask"), out=out, gather=n > 1)
+        r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], **kw)
+        R.barrier()
         l1 = ctx.launch_count()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], arith=arith, compact=compact,
-                                 want=("ex", "ey", "mask"), out=out)
+            r = ctx.trace3d_grid(fields, h_ys.array, h_xs.array, p["stop"], p["a_stop"], **kw)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if n > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        kept_n = int(r["stats"]["n_kept"].sum())
-        e2e[form] = {"value": rays_step * inter_ray * e2e_steps / float(t_e.item()), "ms_per_step": float(t_e.item()) / e2e_steps * 1e3,
+        dt = R.max_over_ranks(time.perf_counter() - t0)
+        loc = r["stats_local"] if n > 1 else r["stats"]
+        kept_n = int(loc["n_kept"].sum())
+        e2e[form] = {"value": rays_step * inter_ray * e2e_steps / dt, "ms_per_step": dt / e2e_steps * 1e3,
                      "launches": int(ctx.launch_count() - l1),
                      "d2h": (kept_n * 16 + nf * NN + nf * SB) if compact else (nf * NN * BYTES_PER_RAY + nf * SB)}
-        assert [int(k) for k in r["stats"]["n_kept"]] == [int(s["n_kept"]) for s in stats[rank]], \
+        assert [int(k) for k in loc["n_kept"]] == [int(s["n_kept"]) for s in mine_st], \
             "host-pointer and device-pointer paths disagree"
+        assert [int(k) for k in r["stats"]["n_kept"]] == kept, "merged statistics of the two paths disagree"
     best = "compacted"
     e2e_value, e2e_ms, e2e_launches, d2h = e2e[best]["value"], e2e[best]["ms_per_step"], e2e[best]["launches"], e2e[best]["d2h"]
     h2d = (nf * NY + NX) * 8
+    del h_ex, h_ey, h_mask, out
+
+    # ---- fixed-size work sharded over the ranks: the strong-scaling records (all ranks take part)
+    fp64_peak, _ = ctx.fp64_peak()
+    strong = None
+    if not args.no_extras:
+        if n > 1:
+            del d_ex, d_ey, d_mask
+            torch.cuda.empty_cache()
+        strong = {"config3_1e9_ray_sweep": strong_config3(R, wl, fp64_peak),
+                  "config5_65536_candidates": strong_config5(R, fp64_peak),
+                  "note": "fixed total work at every N: time(N = 1) / (N x time(N)) is the strong-scaling efficiency"}
+        ctx.set_layout(p["ext"], p["K"])
 
     if rank != 0:
         if n > 1:
+            ctx.comm_free()
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (k_grid): FP64 pipe ----
-    fp64_peak, _ = ctx.fp64_peak()
     hbm_peak, hbm_src = peaks()
     k_ms = float(np.mean(kern_ms)) if len(kern_ms) else ms_step
     flops_launch = FLOPS_PER_RAY * nf * NN
@@ -334,32 +583,45 @@ def _main(real_stdout):
     roofline = {
         "bound": "fp64", "achieved": round(achieved_tf, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
         "frac": round(achieved_tf / fp64_peak, 4), "traffic": traffic,
+        "traffic_source": "profiles/k_grid_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                          "capture of this kernel on this workload; a profiler cannot run inside the timed bench)",
         "kernel": "k_grid<FAST>" if arith == ort.FAST else "k_grid<STRICT>", "kernel_ms": round(k_ms, 4),
-        "flops_per_launch": flops_launch,
+        "flops_per_launch": flops_launch, "frac_of_nominal_37.2": round(achieved_tf / 37.2, 4),
         "peak_source": "measured in this run by ort_fp64_peak (register-resident DFMA chains; "
-                       "MEASURED_PEAKS.json holds no FP64 figure; nominal 37.2 TFLOP/s)",
+                       "MEASURED_PEAKS.json holds no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)",
         "hbm": {"achieved": round(BYTES_PER_RAY * nf * NN / (k_ms * 1e-3) / 1e9, 1), "peak": hbm_peak,
                 "unit": "GB/s", "frac": round(BYTES_PER_RAY * nf * NN / (k_ms * 1e-3) / 1e9 / hbm_peak, 4),
                 "peak_source": hbm_src, "bytes_per_launch": BYTES_PER_RAY * nf * NN},
     }
 
-    cpu = None
+    cpu = cpu_line = None
     if n == 1 and not args.no_cpu_baseline:
-        rps, cores, sample, _ = cpu_baseline(ort, wl)
-        cpu = {"value": rps * inter_ray, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-               "note": "C restatement of the reference's CPU path (allocation-free, so it flatters the "
-                       "Julia original); Julia is not installed on this image"}
+        cpu = cpu_baseline(ort, wl, keep=not args.no_extras)
+        one = cpu_baseline(ort, wl, target_s=6.0, threads=1)
+        cpu_line = {"value": cpu["rps"] * inter_ray, "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"],
+                    "single_thread": {"value": one["rps"] * inter_ray, "cores": 1, "sample": one["sample"]},
+                    "note": "C restatement of the reference's CPU path (allocation-free, so it flatters the "
+                            "Julia original); Julia is not installed on this image"}
+    parity = sec = None
+    if n == 1 and not args.no_extras:
+        if arith == ort.FAST:
+            parity = parity_block(R, wl, d_ex, d_ey, d_mask, cpu)
+            parity["edge_margin_100_closest"]["rays_retraced_strict_in_fast_mode"] = n_strict
+        del d_ex, d_ey, d_mask
+        torch.cuda.empty_cache()
+        sec = secondary(R, hbm_peak, fp64_peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "double-Gauss (10 glass surfaces, 12 loop steps), 16Mi-ray half-pupil grid "
-                        f"{NY}x{NX} per field x {nf} fields per GPU, outputs ex, ey, mask + per-field spot stats",
+            "workload": WORKLOAD,
             "arith": args.arith, "rays_per_step": rays_step, "intersections_per_ray": inter_ray,
             "loop_steps_per_ray": LOOP_STEPS, "value_x12_loop_steps": value * LOOP_STEPS / inter_ray,
-            "parallelism": f"rays sharded by y-rows over {n} GPU(s); all-gather of {nf} x {SB} B stats per rank",
+            "parallelism": f"rays sharded by y-rows over {n} GPU(s); " +
+                           (f"ncclAllGather of {nf} x {SB} B stats per rank + k_merge_stats inside libort_b200.so (ort_opts.gather_stats), "
+                            f"same stream as the sweep; merged records identical on all ranks: {ident}" if n > 1 else "no exchange at N = 1"),
             "l2": "outputs 1.43 GB per step > 126 MB L2 (rewritten every step); inputs are 70 KB of grid "
                   "coordinates, cache-resident by design",
             "spot_rms_mm": [round(x, 9) for x in rms], "kept_rays": kept,
@@ -367,6 +629,8 @@ def _main(real_stdout):
             "per_rank": {"kernel_ms": [round(float(x), 4) for x in per_rank[:, 0]],
                          "ms_per_step": [round(float(x), 4) for x in per_rank[:, 1]],
                          "sm_mhz": [float(x) for x in per_rank[:, 2]]},
+            "comm": ctx.comm_info(),
+            "strong": strong, "secondary": sec,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms,
@@ -375,10 +639,11 @@ def _main(real_stdout):
                 "full_grid_form": {"value": e2e["full_grid"]["value"], "ms_per_step": e2e["full_grid"]["ms_per_step"],
                                    "d2h_bytes_per_step": e2e["full_grid"]["d2h"]}},
         "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
-        "clocks": sampler.result(), "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": sampler.result(), "roofline": roofline, "cpu_baseline": cpu_line, "parity": parity,
     }
     print(json.dumps(line), file=real_stdout, flush=True)
     if n > 1:
+        ctx.comm_free()
         dist.destroy_process_group()
     return 0
 
@@ -396,8 +661,8 @@ def reference_arm(args, rank, n, real_stdout):
     Hs = ort.prescriptions.DOUBLE_GAUSS_FIELDS
     sysm = pre.solve(P["surfaces"], P["a"], P["h"])
     ps = [pre.full_trace_inputs(sysm, H, 64) for H in Hs]
-    ys_all = [np.linspace(q.y1, q.y2, NY) for q in ps]
-    xs = np.linspace(0.0, ps[0].y_EP, NX)
+    ys_all = [ort.host.jl_range(q.y1, q.y2, NY) for q in ps]
+    xs = ort.host.jl_range(0.0, ps[0].y_EP, NX)
     threads = os.cpu_count() or 1
     inter_ray = ort.prescriptions.DOUBLE_GAUSS_GLASS_SURFACES
 
@@ -425,9 +690,9 @@ def reference_arm(args, rank, n, real_stdout):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "double-Gauss (10 glass surfaces, 12 loop steps), 16Mi-ray half-pupil grid "
-                               f"{NY}x{NX} per field x {len(Hs)} fields, outputs ex, ey, mask (bounded sample per step)",
-                   "intersections_per_ray": inter_ray, "sample": sample},
+        "config": {"workload": WORKLOAD, "intersections_per_ray": inter_ray, "sample": sample,
+                   "note": "each step traces a bounded block of y-rows of every field of that workload on the host cores; "
+                           "the value is normalised per intersection"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

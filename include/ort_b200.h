@@ -15,7 +15,15 @@
  *   - Host-pointer entry points are synchronous (outputs valid on return).  *_dev entry points
  *     take DEVICE pointers and a cudaStream_t (as void*), enqueue only, and never synchronise.
  *   - The caller owns every array it passes; the library owns the context, its stream, scratch.
- *   - One ort_ctx per (process, GPU); a context is not re-entrant; distinct contexts are independent.
+ *   - One ort_ctx per (process, GPU); a context is not re-entrant (one host thread at a time); distinct contexts are
+ *     independent.  All entry points of one context share its grow-only device scratch: the library orders that use
+ *     across streams itself (a call enqueued on a stream other than the previous call's first waits, on the device,
+ *     for the previous call's work), so *_dev calls of one context on different streams are SAFE but do not overlap;
+ *     use one context per stream for concurrent sweeps.  The first call at a larger problem size grows the scratch and
+ *     synchronises the device once (cudaDeviceSynchronize + cudaMalloc); steady-state *_dev calls only enqueue.
+ *   - Multi-GPU: one process per GPU (ort_comm_init_rank, e.g. under torchrun / MPI) or one process driving several
+ *     contexts (ort_comm_init_all).  The communicator is NCCL, resolved with dlopen("libnccl.so.2") on first use
+ *     (override: ORT_NCCL_LIB); without it every ort_comm_* call returns ORT_ENCCL and everything else still works.
  *   - There is no CPU fallback: ort_init fails with ORT_ECUDA when no sm_100 device is usable.
  */
 #ifndef ORT_B200_H
@@ -31,7 +39,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ORT_VERSION 100 /* 0.1.0 */
+#define ORT_VERSION 200 /* 0.2.0: communicator inside the library, ort_opts.gather_stats, ort_grid_out.stats_local */
 
 /* status codes */
 #define ORT_OK            0
@@ -45,6 +53,7 @@ extern "C" {
 #define ORT_MAX_ROWS   64   /* prescription rows incl. object space and the appended image plane */
 #define ORT_MAX_FIELDS 32   /* fields per ort_trace3d_grid call */
 #define ORT_MAX_LENS  128   /* rows of a paraxial Lens matrix */
+#define ORT_MAX_GPUS   16   /* contexts of one process in ort_comm_init_all / ort_trace3d_grid_multi */
 
 /* per-ray flag bits */
 #define ORT_FLAG_MISS   1u  /* conic discriminant < 0: position NaN from here on (PupilSampling.jl:9, RayTracing.jl:83) */
@@ -89,6 +98,12 @@ typedef struct ort_opts {
     double  wg_nu;    /* wavegrad (PupilSampling.jl:165-167): wx = ex*wg_nu/wg_lambda.  Used iff wx/wy given. */
     double  wg_lambda;
     double  opd_scale;    /* e.g. 1/lambda for waves; used iff ORT_EXT_OPD */
+    int32_t gather_stats; /* MULTI-GPU (needs ort_comm_init_*): the sweep is this rank's block of y-rows of a sharded pupil
+                             grid.  Right behind the statistics kernel, on the same stream, one ncclAllGather moves the
+                             n_fields x 112 B records of every rank and a merge kernel folds them in rank order (Chan), so
+                             out->stats holds the statistics of the WHOLE grid, bit-identical on every rank; this rank's
+                             own records go to out->stats_local.  (src/PupilSampling.jl:139-146,169-173 over all shards) */
+    int32_t reserved;
 } ort_opts;
 #define ORT_EXT_OPD      1
 #define ORT_EXT_VIGNETTE 2
@@ -115,7 +130,9 @@ typedef struct ort_grid_out {
     double    *opd;           /* EXTENSION: optical path difference per ray (ORT_EXT_OPD) */
     uint8_t   *mask;          /* 1 = kept (always full grid, never compacted)             (:132) */
     uint8_t   *flags;         /* ORT_FLAG_* (always full grid) */
-    ort_stats *stats;         /* [n_fields] */
+    ort_stats *stats;         /* [n_fields]; with opts.gather_stats the records merged over all ranks */
+    ort_stats *stats_local;   /* [n_fields], optional, only read with opts.gather_stats: this rank's own shard (its
+                                 n_kept is the length of this rank's compacted segments) */
 } ort_grid_out;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -297,10 +314,50 @@ int ort_vignetting_candidates(ort_ctx *ctx, int rows, int64_t C, const double *R
 int ort_vignetting_candidates_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a_solve /* host */,
                                   const double *a_vig /* host */, double h_prime, double *d_out, void *stream);
 
+/* ---- communicator inside the library (SURVEY.md section 8 b "Threading", 8 e): rays shard by contiguous blocks of y-rows
+ *      (the outer loop index of src/PupilSampling.jl:123), candidate prescriptions by contiguous ranges; the only exchange
+ *      is the all-gather of per-field statistics records (or of the 32 B-per-candidate merit table).
+ *      One process per GPU:   rank 0 calls ort_comm_unique_id, ships the 128 bytes to the other ranks by any means (file,
+ *                             environment, MPI, a torch.distributed store), every rank calls ort_comm_init_rank.
+ *      One process, n GPUs:   ort_comm_init_all over n contexts on n distinct devices (ncclCommInitAll); then
+ *                             ort_trace3d_grid_multi drives all of them from one host thread. */
+#define ORT_COMM_ID_BYTES 128
+int ort_comm_unique_id(void *id /* ORT_COMM_ID_BYTES */);
+int ort_comm_init_rank(ort_ctx *ctx, const void *id, int rank, int world);
+int ort_comm_init_all(ort_ctx **ctxs, int n);
+int ort_comm_info(ort_ctx *ctx, int *rank, int *world, int *nccl_version);   /* world = 0: no communicator */
+int ort_comm_free(ort_ctx *ctx);                                               /* also done by ort_free */
+/* [lo, hi) of `total` items owned by `rank` of `world`: contiguous, sizes differ by at most one */
+int ort_comm_range(int64_t total, int rank, int world, int64_t *lo, int64_t *hi);
+
+/* Whole pupil grid over n contexts of ONE process (host pointers, synchronous): replaces the hot loop + reductions of
+ * full_trace (src/PupilSampling.jl:115-146,169-173) exactly like ort_trace3d_grid, with the ny y-rows block-sharded over
+ * the contexts.  Arguments and outputs as ort_trace3d_grid -- ys / xs / out describe the WHOLE grid; rank-order
+ * concatenation of the shards reproduces the reference's loop (and push!) order; out->stats is merged over the shards
+ * by the library's all-gather + merge kernel (identical on every device); out->stats_local, if given, is
+ * [n][n_fields].  The layout (and apertures / polynomial terms) of ctxs[0] is used on every context. */
+int ort_trace3d_grid_multi(ort_ctx **ctxs, int n, const ort_field *fields, int n_fields, const double *ys, int ny,
+                           const double *xs, int nx, int stop, double a_stop, const ort_opts *opts, ort_grid_out *out);
+
+/* BASELINE config 5 across ranks: this rank runs the per-candidate prelude (ort_aim_candidates) and the aimed sweep
+ * (ort_trace3d_candidates_aimed) on ITS contiguous range ort_comm_range(C) of the population, then the ranks' segments of
+ * the merit table are exchanged (one grouped NCCL broadcast per rank = an all-gather with uneven counts) so out[C][4]
+ * is complete on every rank.  RtnK is the WHOLE population [C][4][rows] (replicated; only this rank's range is read).
+ * Without a communicator (world 1) it is the plain prelude + sweep.  aim (optional, [C][ORT_AIM_NOUT]) receives this
+ * rank's prelude records in place (rows of other ranks untouched). */
+int ort_candidates_sharded(ort_ctx *ctx, int rows, int64_t C, const double *RtnK, const double *a, double h_prime,
+                           double H, int aspheric, int ny, int nx, int arith, double *aim, double *out);
+int ort_candidates_sharded_dev(ort_ctx *ctx, int rows, int64_t C, const double *d_RtnK, const double *a /* host */,
+                               double h_prime, double H, int aspheric, int ny, int nx, int arith, double *d_aim,
+                               double *d_out, void *stream);
+
 /* ---- multi-GPU combine (host arithmetic): Chan merge of per-shard records recs[n_shards][n_fields], folded in
  *      shard (rank) order so every rank gets bit-identical results, and the reference's sigma of the mirrored spot
  *      (src/PupilSampling.jl:140-146,169-173) from one record. */
 int    ort_merge_stats(const ort_stats *recs, int n_shards, int n_fields, ort_stats *out);
+/* the same fold on the device (the merge kernel behind opts.gather_stats), for records already gathered in HBM:
+ * bit-identical to ort_merge_stats.  Enqueue only. */
+int    ort_merge_stats_dev(ort_ctx *ctx, const ort_stats *d_recs, int n_shards, int n_fields, ort_stats *d_out, void *stream);
 double ort_rms_from_stats(const ort_stats *s);
 
 /* ---- measurement helper: register-resident DFMA-chain microbenchmark; the FP64 roofline

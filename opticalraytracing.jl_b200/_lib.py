@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ORT_B200_LIB", os.path.join(_HERE, "lib", "libort_b200.so"))
 
 ORT_OK, ORT_EINVAL, ORT_ECUDA, ORT_ENCCL, ORT_EUNSUPPORTED, ORT_ENOMEM = 0, -1, -2, -3, -4, -5
-MAX_ROWS, MAX_FIELDS, MAX_LENS = 64, 32, 128
+MAX_ROWS, MAX_FIELDS, MAX_LENS, MAX_GPUS = 64, 32, 128, 16
+COMM_ID_BYTES = 128
 FLAG_MISS, FLAG_TIR, FLAG_DOMAIN, FLAG_CLIP, FLAG_VIGN = 1, 2, 4, 8, 16
 EXT_OPD, EXT_VIGNETTE = 1, 2
 STRICT, FAST = 0, 1
@@ -29,7 +30,9 @@ SYMBOLS = [
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev", "ort_aim_fields",
     "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_vignetting_candidates",
     "ort_vignetting_candidates_dev", "ort_seidel_candidates",
-    "ort_seidel_candidates_dev", "ort_merge_stats", "ort_rms_from_stats", "ort_fp64_peak",
+    "ort_seidel_candidates_dev", "ort_merge_stats", "ort_merge_stats_dev", "ort_rms_from_stats", "ort_fp64_peak",
+    "ort_comm_unique_id", "ort_comm_init_rank", "ort_comm_init_all", "ort_comm_info", "ort_comm_free", "ort_comm_range",
+    "ort_trace3d_grid_multi", "ort_candidates_sharded", "ort_candidates_sharded_dev",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -51,7 +54,8 @@ class Field(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("arith", C.c_int32), ("compact", C.c_int32), ("ys_per_field", C.c_int32),
-                ("ext", C.c_int32), ("wg_nu", C.c_double), ("wg_lambda", C.c_double), ("opd_scale", C.c_double)]
+                ("ext", C.c_int32), ("wg_nu", C.c_double), ("wg_lambda", C.c_double), ("opd_scale", C.c_double),
+                ("gather_stats", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -73,7 +77,7 @@ assert STATS_BYTES == C.sizeof(Stats) == 112
 class GridOut(C.Structure):
     _fields_ = [("ex", C.c_void_p), ("ey", C.c_void_p), ("r", C.c_void_p), ("theta", C.c_void_p),
                 ("wx", C.c_void_p), ("wy", C.c_void_p), ("opd", C.c_void_p), ("mask", C.c_void_p),
-                ("flags", C.c_void_p), ("stats", C.c_void_p)]
+                ("flags", C.c_void_p), ("stats", C.c_void_p), ("stats_local", C.c_void_p)]
 
 
 _lib = None
@@ -145,9 +149,21 @@ def load():
     L.ort_trace3d_candidates_aimed_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                    C.c_int, C.c_void_p, C.c_void_p]
     L.ort_merge_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ort_merge_stats_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ort_rms_from_stats.argtypes = [C.c_void_p]
     L.ort_rms_from_stats.restype = C.c_double
     L.ort_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+    L.ort_comm_unique_id.argtypes = [C.c_void_p]
+    L.ort_comm_init_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ort_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.ort_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ort_comm_free.argtypes = [C.c_void_p]
+    L.ort_comm_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.ort_trace3d_grid_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int] + grid_args[1:]
+    L.ort_candidates_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, _dp, _dp]
+    L.ort_candidates_sharded_dev.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, _dp, C.c_double, C.c_double, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -205,6 +221,68 @@ def merge_stats_c(records):
 def rms_from_stats_c(rec):
     r = np.ascontiguousarray(np.atleast_1d(rec), dtype=STATS_DTYPE)
     return float(load().ort_rms_from_stats(r.ctypes.data))
+
+
+def comm_unique_id():
+    """128 opaque bytes identifying a new communicator (ncclGetUniqueId); ship them to every rank"""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load().ort_comm_unique_id(buf)
+    if rc != ORT_OK:
+        raise OrtError(rc, load().ort_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_range(total, rank, world):
+    lo, hi = C.c_int64(), C.c_int64()
+    rc = load().ort_comm_range(int(total), int(rank), int(world), C.byref(lo), C.byref(hi))
+    if rc != ORT_OK:
+        raise OrtError(rc, "ort_comm_range")
+    return lo.value, hi.value
+
+
+def comm_init_all(contexts):
+    """one process, several GPUs: a communicator over `contexts` (one per device), rank = position in the list"""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = load().ort_comm_init_all(arr, len(contexts))
+    if rc != ORT_OK:
+        raise OrtError(rc, load().ort_last_error(contexts[0].h if contexts else None).decode())
+
+
+def trace3d_grid_multi(contexts, fields, ys, xs, stop, a_stop, arith=FAST, compact=False,
+                       want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None, ext=0, opd_scale=1.0):
+    """ort_trace3d_grid_multi: the WHOLE grid (ys, xs) over the contexts of this process, y-rows block-sharded; outputs as
+    Context.trace3d_grid in the reference's order, 'stats' merged by the library, 'stats_local' (n, n_fields)."""
+    L = load()
+    farr, nf = make_fields(fields)
+    ys, xs = _d(ys), _d(xs)
+    per_field = ys.ndim == 2
+    if per_field and ys.shape[0] != nf:
+        raise ValueError("ys must be (ny,) or (n_fields, ny)")
+    ny, nx = ys.shape[-1], len(xs)
+    NN = ny * nx
+    res = dict(out) if out else {}
+    if "opd" in want:
+        ext |= EXT_OPD
+    for name in ("ex", "ey", "r", "theta", "wx", "wy", "opd"):
+        if name in want and name not in res:
+            res[name] = np.empty((nf, NN), dtype=np.float64)
+    for name in ("mask", "flags"):
+        if name in want and name not in res:
+            res[name] = np.zeros((nf, NN), dtype=np.uint8)
+    stats = np.zeros(nf, dtype=STATS_DTYPE)
+    local = np.zeros((len(contexts), nf), dtype=STATS_DTYPE)
+    go = GridOut(*[(res[k].ctypes.data if k in res and res[k] is not None else None)
+                   for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags")],
+                 stats.ctypes.data, local.ctypes.data)
+    nu, lam = wavegrad if wavegrad else (0.0, 1.0)
+    op = Opts(int(arith), int(bool(compact)), int(per_field), int(ext), float(nu), float(lam), float(opd_scale), 0, 0)
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = L.ort_trace3d_grid_multi(arr, len(contexts), farr, nf, _vp(ys), ny, _vp(xs), nx, int(stop), float(a_stop),
+                                  C.byref(op), C.byref(go))
+    if rc != ORT_OK:
+        raise OrtError(rc, L.ort_last_error(contexts[0].h).decode())
+    res["stats"], res["stats_local"] = stats, local
+    return res
 
 
 def make_fields(fields):
@@ -297,11 +375,52 @@ class Context:
             a = _d(a)
             self._ck(self.L.ort_set_apertures(self.h, len(a), _p(a)))
 
+    # ---- communicator (NCCL inside the library) --------------------------------------------
+    def comm_init_rank(self, comm_id, rank, world):
+        """join a one-process-per-GPU communicator; comm_id = the 128 bytes of comm_unique_id() made on rank 0"""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        self._ck(self.L.ort_comm_init_rank(self.h, buf, int(rank), int(world)))
+
+    def merge_stats_dev(self, d_recs, n_shards, n_fields, d_out, stream=0):
+        """the library's merge kernel on records already in HBM: (n_shards, n_fields) -> (n_fields,)"""
+        self._ck(self.L.ort_merge_stats_dev(self.h, C.c_void_p(d_recs), int(n_shards), int(n_fields), C.c_void_p(d_out),
+                                            C.c_void_p(stream)))
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.ort_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def comm_free(self):
+        self._ck(self.L.ort_comm_free(self.h))
+
+    def candidates_sharded(self, RtnK, a, h_prime, H, k_rays=64, arith=FAST, aspheric=False, want_aim=False):
+        """BASELINE config 5 over the communicator: prelude + aimed sweep of this rank's range of the population, merit
+        table (C, 4) complete on every rank (ort_candidates_sharded)."""
+        RtnK = _d(RtnK)
+        Cn, four, rows = RtnK.shape
+        a = _d(a)
+        assert four == 4 and a.shape == (rows - 1,)
+        out = np.empty((Cn, 4), dtype=np.float64)
+        aim = np.full((Cn, AIM_NOUT), np.nan) if want_aim else None
+        self._ck(self.L.ort_candidates_sharded(self.h, rows, Cn, _p(RtnK), _p(a), float(h_prime), float(H), int(bool(aspheric)),
+                                               int(k_rays), int(k_rays) // 2, int(arith), _p(aim), _p(out)))
+        return (out, aim) if want_aim else out
+
+    def candidates_sharded_dev(self, rows, Cn, d_RtnK, a, h_prime, H, ny, nx, d_out, d_aim=0, arith=FAST, aspheric=False,
+                               stream=0):
+        a = _d(a)
+        self._ck(self.L.ort_candidates_sharded_dev(self.h, int(rows), int(Cn), C.c_void_p(d_RtnK), _p(a), float(h_prime),
+                                                   float(H), int(bool(aspheric)), int(ny), int(nx), int(arith),
+                                                   C.c_void_p(d_aim or 0), C.c_void_p(d_out), C.c_void_p(stream)))
+
     # ---- 3-D grid ------------------------------------------------------------------------
     def trace3d_grid(self, fields, ys, xs, stop, a_stop, arith=FAST, compact=False,
-                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None, ext=0, opd_scale=1.0):
+                     want=("ex", "ey", "mask", "stats"), wavegrad=None, out=None, ext=0, opd_scale=1.0, gather=False):
         """Host-pointer grid sweep.  Returns dict of numpy arrays shaped (n_fields, ny*nx)
-        (+ 'stats' structured array).  `out` may supply preallocated (e.g. pinned) arrays."""
+        (+ 'stats' structured array).  `out` may supply preallocated (e.g. pinned) arrays.
+        gather=True (needs comm_init_rank): ys is this rank's block of y-rows of a sharded grid; 'stats' are the records
+        merged over all ranks by the library (all-gather + merge kernel), 'stats_local' this rank's own."""
         farr, nf = make_fields(fields)
         ys, xs = _d(ys), _d(xs)
         per_field = ys.ndim == 2          # ys[n_fields][ny]: every field has its own aimed y-range
@@ -319,26 +438,33 @@ class Context:
             if name in want and name not in res:
                 res[name] = np.zeros((nf, NN), dtype=np.uint8)
         stats = np.zeros(nf, dtype=STATS_DTYPE)
+        local = np.zeros(nf, dtype=STATS_DTYPE) if gather else None
         go = GridOut(*[(res[k].ctypes.data if k in res and res[k] is not None else None)
                        for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags")],
-                     stats.ctypes.data)
+                     stats.ctypes.data, local.ctypes.data if gather else None)
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
-        op = Opts(int(arith), int(bool(compact)), int(per_field), int(ext), float(nu), float(lam), float(opd_scale))
+        op = Opts(int(arith), int(bool(compact)), int(per_field), int(ext), float(nu), float(lam), float(opd_scale),
+                  int(bool(gather)), 0)
         self._ck(self.L.ort_trace3d_grid(self.h, farr, nf, _vp(ys), ny, _vp(xs), nx, int(stop),
                                          float(a_stop), C.byref(op), C.byref(go)))
         res["stats"] = stats
+        if gather:
+            res["stats_local"] = local
         return res
 
     def trace3d_grid_dev(self, fields, d_ys, ny, d_xs, nx, stop, a_stop, ptrs, stream=0,
-                         arith=FAST, compact=False, wavegrad=None, ys_per_field=False, ext=0, opd_scale=1.0):
-        """Device-pointer grid sweep (enqueue only).  ptrs: dict name -> device address (int)."""
+                         arith=FAST, compact=False, wavegrad=None, ys_per_field=False, ext=0, opd_scale=1.0, gather=False):
+        """Device-pointer grid sweep (enqueue only).  ptrs: dict name -> device address (int).  gather=True: all-gather +
+        merge of the statistics records over the communicator behind the sweep, on the same stream (ptrs['stats'] =
+        merged, ptrs['stats_local'] = this rank's)."""
         farr, nf = make_fields(fields)
-        go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags", "stats")])
+        go = GridOut(*[ptrs.get(k) for k in ("ex", "ey", "r", "theta", "wx", "wy", "opd", "mask", "flags", "stats",
+                                             "stats_local")])
         if ptrs.get("opd"):
             ext |= EXT_OPD
         nu, lam = wavegrad if wavegrad else (0.0, 1.0)
         op = Opts(int(arith), int(bool(compact)), int(bool(ys_per_field)), int(ext), float(nu), float(lam),
-                  float(opd_scale))
+                  float(opd_scale), int(bool(gather)), 0)
         self._ck(self.L.ort_trace3d_grid_dev(self.h, farr, nf, C.c_void_p(d_ys), int(ny), C.c_void_p(d_xs),
                                              int(nx), int(stop), float(a_stop), C.byref(op), C.byref(go),
                                              C.c_void_p(stream)))

@@ -133,6 +133,12 @@ struct TransferArgs {
 #ifndef ORT_BPSP
 #define ORT_BPSP 2                          // ... and its resident CTAs/SM (128 registers, no spills)
 #endif
+#ifndef ORT_SE_RPT
+#define ORT_SE_RPT 2                        // rays per thread of the SIMPLE x EXT instantiations (OPD sweeps over simple prescriptions)
+#endif
+#ifndef ORT_BPSE
+#define ORT_BPSE 2                          // ... and their resident CTAs/SM
+#endif
 #ifndef ORT_GRID_WAVES_DEFAULT
 #define ORT_GRID_WAVES_DEFAULT 8            // CTA waves per grid sweep (grid_dims in ort_api.cu)
 #endif

@@ -201,13 +201,14 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
 // LEAN = 1: the caller wants exactly the spot diagram and the mask (ex, ey, mask -- BASELINE config 2's 17 B per
 // ray): no per-pointer null tests, 32-bit indexing off per-field base pointers.  LEAN = 2: statistics only (config 3's
 // 0 B per ray): no stores at all.  LEAN = 0: any combination of outputs.
-template <int ARITH, bool EXT, int LEAN>
+template <int ARITH, int EXTK, int LEAN>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
                                              bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc)
 {
+    constexpr bool EXT = EXTK != 0;
     const size_t o = fbase + idx;
-    const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
+    const bool vignette = EXTK == 1 && (A.ext & ORT_EXT_VIGNETTE);
     double ri = 0.0, r2 = 0.0;
     bool clip = false;
     if (ARITH == ORT_ARITH_FAST) {
@@ -229,7 +230,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     } else if (!LEAN && A.r) {
         ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
     }
-    const bool vig = EXT && (h.flags & ORT_FLAG_VIGN);
+    const bool vig = EXTK == 1 && (h.flags & ORT_FLAG_VIGN);
     // :132 (+ surface apertures).  A ray that stayed on the fast path is finite by construction (non-finite
     // values set amb), so the NaN tests are only needed after a strict trace.
     const bool drop = clip || vig || (sv && (is_nan_bits(h.xf) || is_nan_bits(h.yf)));
@@ -280,10 +281,13 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
 
 // SIMPLE (FAST only): the prescription holds refracting spheres and planes only (Presc::simple): ORT_SIMPLE_RPT rays per
 // thread through the three-body fast_step<.., SIMPLE>, ORT_BPSP resident CTAs/SM.
-template <int ARITH, int RPT, bool EXT, int LEAN = 0, bool MIRROR = true, bool SIMPLE = false>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (SIMPLE ? ORT_BPSP : (RPT == 1 ? ORT_BPS1 : (EXT ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
+// EXTK: 0 = the reference's outputs only; 1 = extensions (OPD and / or per-surface apertures, chosen at run time; polynomial
+// terms in STRICT); 2 = OPD only (no aperture test compiled in: the instantiation of OPD sweeps over SIMPLE prescriptions).
+template <int ARITH, int RPT, int EXTK, int LEAN = 0, bool MIRROR = true, bool SIMPLE = false>
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (SIMPLE ? (EXTK ? ORT_BPSE : ORT_BPSP) : (RPT == 1 ? ORT_BPS1 : (EXTK ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
+    constexpr bool EXT = EXTK != 0;
     __shared__ RawPart s_part[ORT_TILE / 32];
     __shared__ double s_shift[3];
     const int f = blockIdx.y;
@@ -294,7 +298,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     const size_t fbase = (size_t)f * NN;
     const double* ysf = A.ys + (size_t)f * A.ys_stride;
     const unsigned ysoff = (unsigned)f * (unsigned)A.ys_stride;      // n_fields * ny < 2^31
-    const bool vignette = EXT && (A.ext & ORT_EXT_VIGNETTE);
+    const bool vignette = EXTK == 1 && (A.ext & ORT_EXT_VIGNETTE);
 
     RawAcc acc;
     acc.n = acc.nflag_lo = acc.nflag_hi = acc.nvig = acc.nstrict = 0;
@@ -361,7 +365,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
-            const int kept = grid_epilogue<ARITH, EXT, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
+            const int kept = grid_epilogue<ARITH, EXTK, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
                                                              fbase, cx, cy, co, acc);
             if (A.tile_counts) {
                 const int c = __syncthreads_count(kept);
@@ -745,16 +749,18 @@ cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* 
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from ort_api.cu)
 // ------------------------------------------------------------------------------------------
-// kernel variant of a FAST sweep: 0 general, 1 EXT (OPD / apertures / polynomial terms), 2 SIMPLE; STRICT has 0 and 1
+// kernel variant of a FAST sweep: 0 general, 1 EXT (OPD / apertures / polynomial terms), 2 SIMPLE, 3 SIMPLE x EXT;
+// STRICT has 0 and 1
 int grid_variant(const Presc& P, int arith, int ext)
 {
-    if (ext || P.poly) return 1;
-    return (arith == ORT_ARITH_FAST && P.simple && !P.has_mirror) ? 2 : 0;
+    const bool simple = arith == ORT_ARITH_FAST && P.simple && !P.has_mirror;
+    if (ext || P.poly) return (simple && !P.poly) ? 3 : 1;
+    return simple ? 2 : 0;
 }
 
 int grid_rays_per_thread(int arith, int variant)
 {
-    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : ORT_FAST_RPT) : 1;
+    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : (variant == 3 ? ORT_SE_RPT : ORT_FAST_RPT)) : 1;
 }
 
 int grid_blocks_per_sm(int arith, int variant)
@@ -762,13 +768,15 @@ int grid_blocks_per_sm(int arith, int variant)
     int nb = 0;
     cudaError_t e;
     if (arith == ORT_ARITH_FAST && variant == 2)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 1, false, true>, ORT_TILE, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true>, ORT_TILE, 0);
+    else if (arith == ORT_ARITH_FAST && variant == 3)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true>, ORT_TILE, 0);
     else if (arith == ORT_ARITH_FAST)
-        e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true>, ORT_TILE, 0)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false>, ORT_TILE, 0);
+        e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1>, ORT_TILE, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0>, ORT_TILE, 0);
     else
-        e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, true>, ORT_TILE, 0)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, false>, ORT_TILE, 0);
+        e = (variant & 1) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, 1>, ORT_TILE, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, 0>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
@@ -780,21 +788,24 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool others = A.r || A.theta || A.wx || A.wy || A.flags || A.opd;
         const bool lean = !ext && !others && A.ex && A.ey && A.mask;
         const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
-        const bool simple = grid_variant(P, arith, ext) == 2;
-        if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, false, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        const int variant = grid_variant(P, arith, ext);
+        const bool simple = variant == 2;
+        if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 3) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
     } else {
-        if (ext) k_grid<ORT_ARITH_STRICT, 1, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else k_grid<ORT_ARITH_STRICT, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
+        if (ext) k_grid<ORT_ARITH_STRICT, 1, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else k_grid<ORT_ARITH_STRICT, 1, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
     }
     return cudaGetLastError();
 }

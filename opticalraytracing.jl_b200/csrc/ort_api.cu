@@ -9,47 +9,11 @@
 #include <new>
 
 #include <stdlib.h>
-#include "kern.cuh"
-
-namespace {
-
-enum Slot {
-    SL_YS, SL_XS, SL_PARTIALS, SL_TILES, SL_STATS,
-    SL_EX, SL_EY, SL_R, SL_TH, SL_WX, SL_WY, SL_OPD, SL_MASK, SL_FLAGS,     // trace outputs (full grid)
-    SL_CEX, SL_CEY, SL_CR, SL_CTH, SL_CWX, SL_CWY, SL_COPD,                 // compacted outputs
-    SL_IN0, SL_IN1, SL_IN2, SL_IN3, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3, SL_OUT4, SL_SINK, SL_POLY,
-    SL_COUNT
-};
+#include "ort_ctx.cuh"
 
 thread_local char g_init_err[512] = "";
 
-}  // namespace
-
-struct ort_ctx {
-    int device;
-    int sm_count, cc_major, cc_minor;
-    char name[128];
-    cudaStream_t stream;        // compute stream of the host-pointer entry points
-    cudaStream_t copy_stream;   // D2H stream (overlaps the next field's trace)
-    cudaEvent_t ev_a, ev_b;
-    cudaEvent_t ev_field[ORT_MAX_FIELDS];
-    Presc presc;
-    int rows;
-    bool have_layout;
-    int fast_ok_layout;         // fast_ok as derived from R, t, n, K alone (polynomial terms force it to 0 while set)
-    int bps[2][3];              // resident CTAs/SM of k_grid<STRICT|FAST, variant general|EXT|SIMPLE> (grid_variant)
-    void* slot[SL_COUNT];
-    size_t slot_bytes[SL_COUNT];
-    long long launches;
-    int prof_on;
-    long long prof_n;               // event pairs recorded since the last read
-    cudaEvent_t prof_ev[64][2];
-    char err[512];
-};
-
-namespace {
-
-int fail(ort_ctx* c, int code, const char* fmt, ...)
+int ort_fail(ort_ctx* c, int code, const char* fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -58,16 +22,8 @@ int fail(ort_ctx* c, int code, const char* fmt, ...)
     return code;
 }
 
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(ctx, ORT_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
-                        cudaGetErrorString(e_));                                              \
-    } while (0)
-
 // grow-only device scratch
-int ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
+int ort_ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
 {
     if (bytes == 0) bytes = 8;
     if (ctx->slot_bytes[id] < bytes) {
@@ -82,31 +38,16 @@ int ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
     *out = ctx->slot[id];
     return ORT_OK;
 }
-#define ENSURE(id, bytes, ptr)                                                     \
-    do { void* p_; int rc_ = ensure(ctx, (id), (bytes), &p_); if (rc_) return rc_; \
-         (ptr) = (decltype(ptr))p_; } while (0)
 
-
-// bracket the dominant kernel with an event pair (measurement only)
-struct ProfScope {
-    ort_ctx* c; cudaStream_t st; int slot;
-    ProfScope(ort_ctx* c_, cudaStream_t st_) : c(c_), st(st_), slot(-1)
-    {
-        if (c->prof_on) { slot = (int)(c->prof_n % 64); cudaEventRecord(c->prof_ev[slot][0], st); }
-    }
-    ~ProfScope()
-    {
-        if (slot >= 0) { cudaEventRecord(c->prof_ev[slot][1], st); c->prof_n++; }
-    }
-};
-
-int resolve_arith(const ort_ctx* ctx, int arith)
+int ort_resolve_arith(const ort_ctx* ctx, int arith)
 {
     if (arith == ORT_ARITH_FAST && !ctx->presc.fast_ok) return ORT_ARITH_STRICT;
     return arith;
 }
-
-}  // namespace
+#define resolve_arith ort_resolve_arith
+#define grid_check ort_grid_check
+#define grid_enqueue ort_grid_enqueue
+#define grid_dims ort_grid_dims
 
 extern "C" {
 
@@ -145,10 +86,11 @@ int ort_init(ort_ctx** out, int device)
     CKI(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKI(cudaEventCreate(&ctx->ev_a));
     CKI(cudaEventCreate(&ctx->ev_b));
+    CKI(cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming));
     for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) { CKI(cudaEventCreate(&ctx->prof_ev[i][0])); CKI(cudaEventCreate(&ctx->prof_ev[i][1])); }
 #undef CKI
-    for (int v = 0; v < 3; v++) {
+    for (int v = 0; v < 4; v++) {
         ctx->bps[ORT_ARITH_STRICT][v] = grid_blocks_per_sm(ORT_ARITH_STRICT, v);
         ctx->bps[ORT_ARITH_FAST][v] = grid_blocks_per_sm(ORT_ARITH_FAST, v);
     }
@@ -163,6 +105,8 @@ void ort_free(ort_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    ort_comm_free(ctx);
+    if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
     for (int i = 0; i < SL_COUNT; i++) if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     for (int i = 0; i < ORT_MAX_FIELDS; i++) if (ctx->ev_field[i]) cudaEventDestroy(ctx->ev_field[i]);
     for (int i = 0; i < 64; i++)
@@ -274,6 +218,7 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
     }
     if (!any) { P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; return ORT_OK; }     // all zero == Polynomial(zero)
     CK(cudaSetDevice(ctx->device));
+    ScratchScope scratch(ctx, ctx->stream);
     double* d_c; ENSURE(SL_POLY, (size_t)(rows - 1) * ncoef * 8, d_c);
     // surface step i uses Layout row i + 1 (row 0 is object space)
     CK(cudaMemcpyAsync(d_c, coef + ncoef, (size_t)(rows - 1) * ncoef * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -298,10 +243,12 @@ int ort_set_apertures(ort_ctx* ctx, int n, const double* a)
     return ORT_OK;
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------
 // pupil-grid sweep
 // ------------------------------------------------------------------------------------------
-static int grid_check(ort_ctx* ctx, const ort_field* fields, int n_fields, const void* ys, int ny,
+int ort_grid_check(ort_ctx* ctx, const ort_field* fields, int n_fields, const void* ys, int ny,
                       const void* xs, int nx, int stop, const ort_opts* opts, const ort_grid_out* out)
 {
     if (!ctx) return ORT_EINVAL;
@@ -314,13 +261,15 @@ static int grid_check(ort_ctx* ctx, const ort_field* fields, int n_fields, const
     if (opts->arith != ORT_ARITH_STRICT && opts->arith != ORT_ARITH_FAST) return fail(ctx, ORT_EINVAL, "trace3d_grid: arith = %d", opts->arith);
     for (int f = 0; f < n_fields; f++)
         if (fields[f].mode != 0 && fields[f].mode != 1) return fail(ctx, ORT_EINVAL, "trace3d_grid: field %d mode = %d", f, fields[f].mode);
+    if (opts->gather_stats && !ctx->comm)
+        return fail(ctx, ORT_ENCCL, "trace3d_grid: opts.gather_stats needs a communicator (ort_comm_init_rank / ort_comm_init_all)");
     return ORT_OK;
 }
 
 // Enqueue trace (+ compaction) + finalize for fields [0, n_fields) on `st`.  All pointers are
 // device pointers.  `full` receives the full-grid trace outputs; when compacting, `full` is
 // scratch and `dst` the compacted destination.
-static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
+int ort_grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
                         const double* d_xs, int nx, int stop, double a_stop, const ort_opts* opts,
                         const ort_grid_out& full, const ort_grid_out* dst, ort_stats* d_stats,
                         RawPart* d_partials, int* d_tiles, int gx, cudaStream_t st)
@@ -362,7 +311,7 @@ static int grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, con
     return ORT_OK;
 }
 
-static int grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsigned NN)
+int ort_grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsigned NN)
 {
     const int variant = grid_variant(ctx->presc, arith, ext);
     const unsigned nsub = (NN + ORT_TILE - 1) / ORT_TILE;
@@ -380,10 +329,15 @@ static int grid_dims(const ort_ctx* ctx, int arith, int ext, int n_fields, unsig
     long long gx = (long long)ntiles / 16;
     if (gx < slots) gx = slots;
     if (gx > slots * waves) gx = slots * waves;
+    // the kernel's per-thread flag counters are 16 bits wide (RawAcc): keep a thread below 32 000 rays whatever the grid
+    const long long gmin = ((long long)nsub + 31999) / 32000;
+    if (gx < gmin) gx = gmin;
     if (gx > (long long)ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     return (int)gx;
 }
+
+extern "C" {
 
 int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* d_ys, int ny,
                          const double* d_xs, int nx, int stop, double a_stop, const ort_opts* opts,
@@ -393,30 +347,39 @@ int ort_trace3d_grid_dev(ort_ctx* ctx, const ort_field* fields, int n_fields, co
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    ScratchScope scratch(ctx, st);
     const unsigned NN = (unsigned)((long long)ny * nx);
     const int arith = resolve_arith(ctx, opts->arith);
     const int gx = grid_dims(ctx, arith, (opts->ext & 3) || ctx->presc.poly, n_fields, NN);
     RawPart* d_partials; ENSURE(SL_PARTIALS, sizeof(RawPart) * (size_t)gx * n_fields, d_partials);
-    ort_stats* d_stats = d_out->stats;
+    // with opts.gather_stats out->stats receives the records merged over all ranks, out->stats_local this rank's own
+    const bool gather = opts->gather_stats != 0;
+    ort_stats* d_stats = gather ? d_out->stats_local : d_out->stats;
     if (!d_stats) ENSURE(SL_STATS, sizeof(ort_stats) * (size_t)n_fields, d_stats);
-    if (!opts->compact)
-        return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, *d_out, nullptr,
-                            d_stats, d_partials, nullptr, gx, st);
-    // compaction: trace into scratch, scatter into the caller's arrays
-    const size_t tot = (size_t)NN * n_fields;
-    ort_grid_out full = *d_out;
-    if (d_out->ex) ENSURE(SL_EX, tot * 8, full.ex);
-    if (d_out->ey) ENSURE(SL_EY, tot * 8, full.ey);
-    if (d_out->r) ENSURE(SL_R, tot * 8, full.r);
-    if (d_out->theta) ENSURE(SL_TH, tot * 8, full.theta);
-    if (d_out->wx) ENSURE(SL_WX, tot * 8, full.wx);
-    if (d_out->wy) ENSURE(SL_WY, tot * 8, full.wy);
-    if (d_out->opd) ENSURE(SL_OPD, tot * 8, full.opd);
-    if (!d_out->mask) ENSURE(SL_MASK, tot, full.mask);
-    const size_t tiles_per_field = (size_t)(NN + ORT_TILE - 1) / ORT_TILE, tile_stride = tiles_per_field + tiles_per_field / 2048 + 2;
-    int* d_tiles; ENSURE(SL_TILES, sizeof(int) * tile_stride * n_fields, d_tiles);
-    return grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full, d_out, d_stats,
-                        d_partials, d_tiles, gx, st);
+    if (!opts->compact) {
+        rc = grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, *d_out, nullptr,
+                          d_stats, d_partials, nullptr, gx, st);
+    } else {
+        // compaction: trace into scratch, scatter into the caller's arrays
+        const size_t tot = (size_t)NN * n_fields;
+        ort_grid_out full = *d_out;
+        if (d_out->ex) ENSURE(SL_EX, tot * 8, full.ex);
+        if (d_out->ey) ENSURE(SL_EY, tot * 8, full.ey);
+        if (d_out->r) ENSURE(SL_R, tot * 8, full.r);
+        if (d_out->theta) ENSURE(SL_TH, tot * 8, full.theta);
+        if (d_out->wx) ENSURE(SL_WX, tot * 8, full.wx);
+        if (d_out->wy) ENSURE(SL_WY, tot * 8, full.wy);
+        if (d_out->opd) ENSURE(SL_OPD, tot * 8, full.opd);
+        if (!d_out->mask) ENSURE(SL_MASK, tot, full.mask);
+        const size_t tiles_per_field = (size_t)(NN + ORT_TILE - 1) / ORT_TILE, tile_stride = tiles_per_field + tiles_per_field / 2048 + 2;
+        int* d_tiles; ENSURE(SL_TILES, sizeof(int) * tile_stride * n_fields, d_tiles);
+        rc = grid_enqueue(ctx, fields, n_fields, d_ys, ny, d_xs, nx, stop, a_stop, opts, full, d_out, d_stats,
+                          d_partials, d_tiles, gx, st);
+    }
+    if (rc || !gather) return rc;
+    ort_stats* d_merged = d_out->stats;
+    if (!d_merged) ENSURE(SL_MERGED, sizeof(ort_stats) * (size_t)n_fields, d_merged);
+    return ort_comm_gather_stats(ctx, d_stats, n_fields, d_merged, nullptr, st);
 }
 
 int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const double* ys, int ny,
@@ -461,6 +424,7 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         if (out->opd) ENSURE(SL_COPD, tot * 8, comp.opd);
     }
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_ys, ys, sizeof(double) * nys, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_xs, xs, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, st));
     ort_stats hstats[ORT_MAX_FIELDS];
@@ -519,9 +483,19 @@ int ort_trace3d_grid(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
         if (out->wy) CK(cudaMemcpyAsync(out->wy + o, src.wy, cnt * 8, cudaMemcpyDeviceToHost, cs));
         if (out->opd && (opts->ext & ORT_EXT_OPD)) CK(cudaMemcpyAsync(out->opd + o, src.opd, cnt * 8, cudaMemcpyDeviceToHost, cs));
     }
+    ort_stats hmerged[ORT_MAX_FIELDS];
+    if (opts->gather_stats) {               // the statistics of the whole sharded grid: all-gather + rank-order merge
+        ort_stats* d_merged; ENSURE(SL_MERGED, sizeof(ort_stats) * (size_t)n_fields, d_merged);
+        rc = ort_comm_gather_stats(ctx, d_stats, n_fields, d_merged, nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(hmerged, d_merged, sizeof(ort_stats) * (size_t)n_fields, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(cs));
-    if (out->stats) memcpy(out->stats, hstats, sizeof(ort_stats) * (size_t)n_fields);
+    if (opts->gather_stats) {
+        if (out->stats) memcpy(out->stats, hmerged, sizeof(ort_stats) * (size_t)n_fields);
+        if (out->stats_local) memcpy(out->stats_local, hstats, sizeof(ort_stats) * (size_t)n_fields);
+    } else if (out->stats) memcpy(out->stats, hstats, sizeof(ort_stats) * (size_t)n_fields);
     return ORT_OK;
 }
 
@@ -549,6 +523,7 @@ int ort_trace3d_rays_opl(ort_ctx* ctx, int64_t N, const double* y0, const double
     if (flags) ENSURE(SL_OUT3, n, A.flags);
     if (opl) ENSURE(SL_OUT4, n * 8, A.opl);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d1, x0, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d2, u0, n * 8, cudaMemcpyHostToDevice, st));
@@ -610,6 +585,7 @@ int ort_trace2d_batch(ort_ctx* ctx, int64_t N, const double* y0, const double* U
     if (ts_out) ENSURE(SL_OUT2, rows * n * 8, A.ts_out);
     if (flags) ENSURE(SL_OUT3, n, A.flags);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d1, U0, n * 8, cudaMemcpyHostToDevice, st));
     A.y0 = d0; A.U0 = d1;
@@ -638,6 +614,7 @@ int ort_aim2d(ort_ctx* ctx, int64_t N, const double* x_start, const double* othe
     ENSURE(SL_IN0, n * 8, d0); ENSURE(SL_IN1, n * 8, d1); ENSURE(SL_IN2, n * 8, d2); ENSURE(SL_OUT0, n * 8, d3);
     if (iters) ENSURE(SL_OUT1, n * 4, di);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d0, x_start, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d1, other, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d2, target, n * 8, cudaMemcpyHostToDevice, st));
@@ -702,6 +679,7 @@ int ort_paraxial_batch(ort_ctx* ctx, int k, const double* tau, const double* phi
     if (y_all) ENSURE(SL_OUT3, kk * n * 8, dya);
     if (w_all) ENSURE(SL_OUT4, kk * n * 8, dwa);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d0, y0, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d1, w0, n * 8, cudaMemcpyHostToDevice, st));
     int rc = ort_paraxial_batch_dev(ctx, k, tau, phi, a, clip, arith, N, d0, d1, dy, dw, dci, dya, dwa, st);
@@ -762,6 +740,7 @@ int ort_transfer_batch(ort_ctx* ctx, const double M[4], double tau, double taup,
     double *d0, *d1;
     ENSURE(SL_IN0, n * 16, d0); ENSURE(SL_OUT0, n * 16, d1);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d0, v_in, n * 16, cudaMemcpyHostToDevice, st));
     int rc = ort_transfer_batch_dev(ctx, M, tau, taup, reverse, N, d0, d1, st);
     if (rc) return rc;
@@ -807,6 +786,7 @@ int ort_trace3d_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK
     ENSURE(SL_IN0, nb, d_p); ENSURE(SL_YS, (size_t)ny * 8, d_ys); ENSURE(SL_XS, (size_t)nx * 8, d_xs);
     ENSURE(SL_OUT0, (size_t)C * 32, d_o);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_ys, ys, (size_t)ny * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_xs, xs, (size_t)nx * 8, cudaMemcpyHostToDevice, st));
@@ -846,6 +826,7 @@ int ort_vignetting_candidates(ort_ctx* ctx, int rows, int64_t C, const double* R
     double *d_p, *d_o;
     ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT0, no, d_o);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     int rc = ort_vignetting_candidates_dev(ctx, rows, C, d_p, a_solve, a_vig, h_prime, d_o, st);
     if (rc) return rc;
@@ -885,6 +866,7 @@ int ort_aim_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK, co
     double *d_p, *d_o;
     ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT1, no, d_o);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     int rc = ort_aim_candidates_dev(ctx, rows, C, d_p, a, h_prime, H, aspheric, d_o, st);
     if (rc) return rc;
@@ -909,6 +891,7 @@ int ort_aim_fields(ort_ctx* ctx, int rows, const double* R, const double* t, con
     double h_p[4 * ORT_MAX_ROWS];
     for (int i = 0; i < rows; i++) { h_p[i] = R[i]; h_p[rows + i] = t[i]; h_p[2 * rows + i] = n[i]; h_p[3 * rows + i] = K ? K[i] : 0.0; }
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, h_p, nb, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));                  // h_p is a stack buffer
     AimCandArgs A; memset(&A, 0, sizeof A);
@@ -956,6 +939,7 @@ int ort_trace3d_candidates_aimed(ort_ctx* ctx, int rows, int64_t C, const double
     double *d_p, *d_a, *d_o;
     ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT1, na, d_a); ENSURE(SL_OUT0, (size_t)C * 32, d_o);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_a, aim, na, cudaMemcpyHostToDevice, st));
     int rc = ort_trace3d_candidates_aimed_dev(ctx, rows, C, d_p, d_a, ny, nx, arith, d_o, st);
@@ -998,6 +982,7 @@ int ort_seidel_candidates(ort_ctx* ctx, int rows, int64_t C, const double* RtnK,
     ENSURE(SL_IN0, nb, d_p); ENSURE(SL_OUT0, no, d_o);
     if (per_surface) ENSURE(SL_OUT1, np_, d_per);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     CK(cudaMemcpyAsync(d_p, RtnK, nb, cudaMemcpyHostToDevice, st));
     int rc = ort_seidel_candidates_dev(ctx, rows, C, d_p, a, h_prime, lambda, dn, d_o, d_per, st);
     if (rc) return rc;
@@ -1053,6 +1038,7 @@ int ort_fp64_peak(ort_ctx* ctx, double* tflops, double* ms)
     CK(cudaSetDevice(ctx->device));
     double* sink; ENSURE(SL_SINK, 8, sink);
     cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
     long long dfma = 0;
     CK(launch_fp64_peak(sink, ctx->sm_count, 256, st, &dfma));           // warm-up
     double best = 1e30;

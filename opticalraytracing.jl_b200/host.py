@@ -56,6 +56,103 @@ def _be(backend):
 
 
 # ------------------------------------------------------------------------------------------------
+# collect(range(start, stop, length))  -- Julia Base, base/twiceprecision.jl (NOT under the reference tree)
+# ------------------------------------------------------------------------------------------------
+def _add12(x, y):
+    """Base.add12: (hi, lo) with hi + lo == x + y exactly (branch on magnitude, then fast two-sum)"""
+    swap = np.abs(y) > np.abs(x)
+    big, little = np.where(swap, y, x), np.where(swap, x, y)
+    hi = big + little
+    return hi, (big - hi) + little
+
+
+def _truncbits(x, nb):
+    """Base.truncbits: clear the nb low bits of the significand"""
+    b = np.float64(x).view(np.uint64)
+    return float((b & (np.uint64(0xFFFFFFFFFFFFFFFF) << np.uint64(nb))).view(np.float64))
+
+
+def jl_range(start, stop, length):
+    """The Float64 values of Julia's `range(start, stop, length)` (src/PupilSampling.jl:121-122 builds the pupil grid
+    with it).  Julia does not compute start + i*step in plain Float64 (numpy.linspace does): a Float64 range is a
+    StepRangeLen{Float64, TwicePrecision, TwicePrecision} whose reference value and step are double-double numbers
+    chosen so that BOTH end points are hit exactly, and element i is ref + (i - offset) step evaluated in
+    double-double -- in effect the correctly rounded linear interpolation.  This restates Base._linspace and
+    Base.unsafe_getindex (base/twiceprecision.jl, Julia 1.10/1.11) for end points that are not small rationals --
+    every aimed grid -- and uses exact rational arithmetic, correctly rounded, where Julia takes its rational branch
+    (end points like 0.0 and 10.0).  Julia itself is absent here, so this is pinned only against exact interpolation
+    (tests/test_host_logic.py); the shim passes collect(range(...)) so in the real drop-in these are inputs."""
+    n = int(length)
+    a, b = float(start), float(stop)
+    if n < 0:
+        raise ValueError("range: negative length")
+    if n == 0:
+        return np.empty(0)
+    if n == 1:
+        if a != b:
+            raise ValueError("range(start, stop, length=1): endpoints differ")
+        return np.array([a])
+    if a == b:
+        return np.full(n, a)
+    if not (math.isfinite(a) and math.isfinite(b)):
+        raise ValueError("start and stop must be finite")
+    if _small_rational(a) and _small_rational(b):
+        from fractions import Fraction
+        fa, fb = Fraction(a), Fraction(b)
+        return np.array([float(fa + (fb - fa) * Fraction(i, n - 1)) for i in range(n)])
+    # Base._linspace(start, stop, len)
+    delta, dfac = b - a, 1
+    if not math.isfinite(delta):
+        delta, dfac = b / n - a / n, n
+    tmin = -(a / delta) / dfac
+    imin = int(np.rint(tmin * (n - 1) + 1))            # round-half-even, as Julia's round(Int, x)
+    if 1 < imin < n:
+        t = (imin - 1) / (n - 1)
+        ref = (1 - t) * a + t * b
+        step = (ref - a) / (imin - 1) if imin - 1 < n - imin else (b - ref) / (n - imin)
+    elif imin <= 1:
+        imin, ref, step = 1, a, (delta / (n - 1)) * dfac
+    else:
+        imin, ref, step = n, b, (delta / (n - 1)) * dfac
+    m, k = float(np.nextafter(np.finfo(np.float64).max, 0.0)), max(imin - 1, n - imin)
+    step_hi_pre = min(max(step, max(-(m + ref) / k, (-m + ref) / k)), min((m - ref) / k, (m + ref) / k))
+    nb = min(27, int(math.ceil(math.log2(max(imin - 1, n - imin)))) + 1)      # nbitslen(Float64, len, imin)
+    step_hi = _truncbits(step_hi_pre, nb)
+    x1_hi, x1_lo = _add12(np.float64((1 - imin) * step_hi), np.float64(ref))
+    x2_hi, x2_lo = _add12(np.float64((n - imin) * step_hi), np.float64(ref))
+    lo_a, lo_b = (a - float(x1_hi)) - float(x1_lo), (b - float(x2_hi)) - float(x2_lo)
+    step_lo = (lo_b - lo_a) / (n - 1)
+    ref_lo = lo_a - (1 - imin) * step_lo
+    # steprangelen_hp(..., (ref, ref_lo), (step_hi, step_lo), 0, len, imin) stores both pairs as they are: step_hi keeps
+    # its nb cleared low bits, so (i - offset) * step_hi below is exact
+    s_hi, s_lo = step_hi, step_lo
+    # Base.unsafe_getindex(r::StepRangeLen{T, <:TwicePrecision, <:TwicePrecision}, i)
+    u = np.arange(1, n + 1, dtype=np.float64) - imin
+    shift_hi, shift_lo = u * s_hi, u * s_lo
+    x_hi, x_lo = _add12(np.full(n, ref), shift_hi)
+    return x_hi + (x_lo + (shift_lo + ref_lo))
+
+
+def _small_rational(x):
+    """True where Base.rat finds the exact value of x as a ratio of integers below 2^24 (continued fractions): Julia's
+    range then takes its integer branch (Base.linspace with numerators / denominator)"""
+    y, a, b, c, d, m = x, 1, 0, 0, 1, 16777216.0
+    while abs(y) <= m:
+        f = int(y)
+        y -= f
+        a, c = f * a + c, a
+        b, d = f * b + d, b
+        if max(abs(a), abs(b)) > m:
+            return False
+        if b != 0 and a / b == x:
+            return True
+        if y == 0.0:
+            return False
+        y = 1.0 / y
+    return False
+
+
+# ------------------------------------------------------------------------------------------------
 # types (src/Types.jl)
 # ------------------------------------------------------------------------------------------------
 class Layout:
@@ -606,8 +703,8 @@ def full_trace_fields(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, backen
     if p["P"] is not None:
         be.set_polynomials(p["P"])
     k2 = k_rays // 2                                                             # :116
-    xs = np.linspace(0.0, p["y_EP"], k2)                                         # :122
-    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], k_rays) for j in range(len(p["Hs"]))])   # :121
+    xs = jl_range(0.0, p["y_EP"], k2)                                            # :122
+    ys = np.stack([jl_range(p["y1"][j], p["y2"][j], k_rays) for j in range(len(p["Hs"]))])      # :121
     if p["z0"] is None:
         flds = [dict(mode=0, u=float(p["u"][j]), v=math.tan(0.0), h_prime=float(p["h_prime"][j]))
                 for j in range(len(p["Hs"]))]
@@ -716,8 +813,8 @@ def wavefront(surfaces, system, Hs, k_rays=SPOT_RAYS, focus=None, lam=LAMBDA, vi
     Rr = p["focus"] - system.XP.t                            # image plane - paraxial exit pupil
     yc = yv[-1]
     opl_ref = opl + opl0 + nl * (-Rr)
-    xs = np.linspace(0.0, p["y_EP"], k_rays // 2)
-    ys = np.stack([np.linspace(p["y1"][j], p["y2"][j], k_rays) for j in range(nf)])
+    xs = jl_range(0.0, p["y_EP"], k_rays // 2)
+    ys = np.stack([jl_range(p["y1"][j], p["y2"][j], k_rays) for j in range(nf)])
     flds = [dict(mode=0, u=float(p["u"][j]), v=0.0, h_prime=float(p["h_prime"][j]), opd_xc=0.0, opd_yc=float(yc[j]),
                  opd_radius=float(Rr), opl_ref=float(opl_ref[j])) for j in range(nf)]
     out = []
@@ -906,7 +1003,7 @@ def TSA(surfaces, system, k_rays=K_RAYS, backend=None):
     rm = trace_marginal_ray(surfaces, system, backend=backend)
     rc = trace_chief_ray(surfaces, system, backend=backend)
     XP_t = rc.z[-1] - rc.z[-2]
-    y_EP = np.linspace(rm.y[0] / k_rays, rm.y[0], k_rays)
+    y_EP = jl_range(rm.y[0] / k_rays, rm.y[0], k_rays)
     y_XP, eps_ = np.empty(k_rays), np.empty(k_rays)
     BFD = pm.z[-1] - pm.z[-2]
     t = BFD - (rm.z[-2] - pm.z[-2])                              # surface_to_focus :105 with sag :93-95

@@ -203,6 +203,74 @@ def trace_edge_rays(surfaces, y1, y2, U, stop, a_stop, K=None, aspheric=False):
     return r1, r2
 
 
+def _two_sum_by_magnitude(x, y):
+    """Base.add12"""
+    if abs(y) > abs(x):
+        x, y = y, x
+    h = x + y
+    return h, (x - h) + y
+
+
+def jl_range(start, stop, length):
+    """collect(range(start, stop, length)) in Float64 -- Julia Base (base/twiceprecision.jl: range_start_stop_length,
+    _linspace, unsafe_getindex of a TwicePrecision StepRangeLen; Julia 1.10).  That source is NOT under /root/reference
+    and Julia cannot run here: restated from its published algorithm, scalar loop, and pinned only by the properties it
+    is designed for (end points exact, every element within 1 ulp of -- almost always equal to -- the correctly rounded
+    exact interpolation; tests/test_host_logic.py).  End points that are exact small rationals take Julia's integer
+    branch, whose result is the correctly rounded rational: evaluated here with fractions.Fraction."""
+    import struct
+    from fractions import Fraction
+    n, a, b = int(length), float(start), float(stop)
+    if n == 1:
+        return np.array([a])
+    if a == b:
+        return np.full(n, a)
+
+    def rat_ok(x):                      # Base.rat finds x exactly with numerator, denominator <= maxintfloat(Float32)
+        y, p0, q0, p1, q1 = x, 1, 0, 0, 1
+        while abs(y) <= 16777216.0:
+            f = int(y)
+            y -= f
+            p0, p1 = f * p0 + p1, p0
+            q0, q1 = f * q0 + q1, q0
+            if max(abs(p0), abs(q0)) > 16777216:
+                return False
+            if q0 != 0 and p0 / q0 == x:
+                return True
+            if y == 0.0:
+                return False
+            y = 1.0 / y
+        return False
+    if rat_ok(a) and rat_ok(b):
+        fa, fb = Fraction(a), Fraction(b)
+        return np.array([float(fa + (fb - fa) * Fraction(i, n - 1)) for i in range(n)])
+    d = b - a
+    tmin = -(a / d)
+    imin = int(np.rint(tmin * (n - 1) + 1))
+    if 1 < imin < n:
+        t = (imin - 1) / (n - 1)
+        ref = (1 - t) * a + t * b
+        step = (ref - a) / (imin - 1) if imin - 1 < n - imin else (b - ref) / (n - imin)
+    elif imin <= 1:
+        imin, ref, step = 1, a, d / (n - 1)
+    else:
+        imin, ref, step = n, b, d / (n - 1)
+    nb = min(27, int(math.ceil(math.log2(max(imin - 1, n - imin)))) + 1)
+    bits = struct.unpack("<Q", struct.pack("<d", step))[0] & (0xFFFFFFFFFFFFFFFF << nb) & 0xFFFFFFFFFFFFFFFF
+    step_hi = struct.unpack("<d", struct.pack("<Q", bits))[0]
+    x1h, x1l = _two_sum_by_magnitude((1 - imin) * step_hi, ref)
+    x2h, x2l = _two_sum_by_magnitude((n - imin) * step_hi, ref)
+    ea, eb = (a - x1h) - x1l, (b - x2h) - x2l
+    step_lo = (eb - ea) / (n - 1)
+    ref_lo = ea - (1 - imin) * step_lo
+    out = np.empty(n)
+    for i in range(1, n + 1):
+        u = i - imin
+        xh, xl = _two_sum_by_magnitude(ref, u * step_hi)
+        out[i - 1] = xh + (xl + (u * step_lo + ref_lo))
+    return out
+
+
 def full_trace_inputs(system, H, k_rays=64, focus=None, K=None, aspheric=False):
     """Host prelude of full_trace (PupilSampling.jl:85-122) for a System: everything the hot
     loop needs.  `aspheric` mirrors Layout{Aspheric} dispatch of the 2-D tracer."""
@@ -227,8 +295,8 @@ def full_trace_inputs(system, H, k_rays=64, focus=None, K=None, aspheric=False):
     ext = np.vstack([S[:, :3], [np.inf, 0.0, 1.0]])
     Kx = np.append(np.zeros(S.shape[0]) if K is None else np.asarray(K, dtype=np.float64), 0.0)
     ext[-2, 1] = focus
-    ys = np.linspace(y1, y2, k_rays)
-    xs = np.linspace(0.0, y_EP, k_rays // 2)
+    ys = jl_range(y1, y2, k_rays)                       # :121
+    xs = jl_range(0.0, y_EP, k_rays // 2)               # :122
     return NS(ext=ext, K=Kx, ys=ys, xs=xs, u=u, v=math.tan(0.0), U=U, h_prime=h_prime, stop=stop,
               a_stop=a_stop, focus=focus, y1=y1, y2=y2, y_EP=y_EP, EP_t=EP_t,
               nu=system.marginal.nu[-1], H=H)
@@ -252,7 +320,7 @@ def tsa(surfaces, system, k_rays=22):
     rm = trace_marginal_ray_real(surfaces, system)
     rc = trace_chief_ray_real(surfaces, system)
     XP_t = rc.z[-1] - rc.z[-2]
-    y_EP = np.linspace(rm.y[0] / k_rays, rm.y[0], k_rays)
+    y_EP = jl_range(rm.y[0] / k_rays, rm.y[0], k_rays)
     y_XP = np.empty(k_rays)
     eps_ = np.empty(k_rays)
     BFD = pm.z[-1] - pm.z[-2]

@@ -30,10 +30,10 @@ def test_header_symbols_exported(ort):
 
 def test_struct_layouts(ort):
     assert C.sizeof(ort._lib.Field) == 80
-    assert C.sizeof(ort._lib.Opts) == 40
+    assert C.sizeof(ort._lib.Opts) == 48
     assert C.sizeof(ort._lib.Stats) == 112 == ort.STATS_DTYPE.itemsize == ort.STATS_BYTES
-    assert C.sizeof(ort._lib.GridOut) == 10 * C.sizeof(C.c_void_p)
-    assert ort._lib.load().ort_version() == 100
+    assert C.sizeof(ort._lib.GridOut) == 11 * C.sizeof(C.c_void_p)
+    assert ort._lib.load().ort_version() == 200
 
 
 def test_header_compiles_as_c():

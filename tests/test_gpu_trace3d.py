@@ -598,7 +598,7 @@ def test_polynomial_terms_grid_and_full_trace(ctx, orc, pre, ort):
     assert pp["P"] is not None and pp["P"].shape[0] == pp["ext"].shape[0]
     try:
         orc.set_poly(pp["P"])
-        g = orc.grid_trace(pp["ext"], np.linspace(pp["y1"][0], pp["y2"][0], 48), np.linspace(0.0, pp["y_EP"], 24), pp["stop"],
+        g = orc.grid_trace(pp["ext"], pre.jl_range(pp["y1"][0], pp["y2"][0], 48), pre.jl_range(0.0, pp["y_EP"], 24), pp["stop"],
                            pp["a_stop"], float(pp["h_prime"][0]), u=float(pp["u"][0]), v=0.0, K=pp["K"])
     finally:
         orc.set_poly(None)

@@ -263,3 +263,44 @@ def test_sphere_root_forms_error_study(tmp_path):
     assert rows["surface 2 with R = 1e+04"][1] < 2e-14           # 64 L = 8.8e3 mm for this lens
     assert rows["surface 2 with R = 1e+06"][1] < 2e-12           # ~ eps |R|: two decades of R, two decades of error
     assert rows["surface 2 with R = 1e+06"][0] < 1e-14           # the form with the division does not care
+
+
+def test_jl_range_is_the_correctly_rounded_interpolation(ort, pre):
+    """collect(range(a, b, n)) (src/PupilSampling.jl:121-122) restated from Julia Base's TwicePrecision algorithm in the
+    host mirror (vectorised) and, separately, in the oracle prelude (scalar loop): both give identical bits, hit both end
+    points exactly and stay within 1 ulp of -- almost always equal to -- the exactly interpolated value.  numpy.linspace
+    does not (it is start + i*step in plain Float64)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    total = off = 0
+    for trial in range(60):
+        a, b, n = float(rng.uniform(-40, 40)), float(rng.uniform(-40, 40)), int(rng.integers(2, 1500))
+        if trial % 4 == 0:
+            a = 0.0                                   # xs = range(0, y_EP, k / 2)
+        r = ort.host.jl_range(a, b, n)
+        assert np.array_equal(r, pre.jl_range(a, b, n))
+        assert r[0] == a and r[-1] == b and len(r) == n
+        fa, fb = Fraction(a), Fraction(b)
+        exact = np.array([float(fa + (fb - fa) * Fraction(i, n - 1)) for i in range(n)])
+        ulp = np.abs(r - exact) / np.spacing(np.maximum(np.abs(exact), 1e-300))
+        assert ulp.max() <= 1.0
+        total += n
+        off += int((ulp > 0).sum())
+    assert off <= total // 2000                       # a handful of 1-ulp cases, as in Julia itself
+    assert np.array_equal(ort.host.jl_range(0.0, 1.0, 11), np.array([0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]))
+    assert np.array_equal(ort.host.jl_range(-1.0, 1.0, 5), np.array([-1.0, -0.5, 0.0, 0.5, 1.0]))
+    assert np.array_equal(ort.host.jl_range(2.5, 2.5, 3), np.full(3, 2.5))
+
+
+def test_comm_helpers_without_a_gpu(ort):
+    """ort_comm_range is the block partition of distributed.shard_rows; the communicator id comes from NCCL through
+    dlopen (no GPU needed); compute still fails loudly"""
+    for total, world in ((64, 4), (44722, 8), (5, 8), (0, 3), (65536, 7)):
+        got = [ort._lib.comm_range(total, r, world) for r in range(world)]
+        assert got == [ort.distributed.shard_rows(total, r, world) for r in range(world)]
+        assert got[0][0] == 0 and got[-1][1] == total and all(got[i][1] == got[i + 1][0] for i in range(world - 1))
+    ident = ort._lib.comm_unique_id()
+    assert len(ident) == ort._lib.COMM_ID_BYTES == 128 and ident != ort._lib.comm_unique_id()
+    L = ort._lib.load()
+    assert L.ort_comm_init_rank(None, ident, 0, 1) == ort._lib.ORT_EINVAL
+    assert L.ort_comm_free(None) == ort._lib.ORT_EINVAL
