@@ -52,7 +52,9 @@ extern "C" {
 /* limits */
 #define ORT_MAX_ROWS   64   /* prescription rows incl. object space and the appended image plane */
 #define ORT_MAX_FIELDS 32   /* fields per ort_trace3d_grid call */
+#ifndef ORT_MAX_LENS
 #define ORT_MAX_LENS  128   /* rows of a paraxial Lens matrix */
+#endif
 #define ORT_MAX_GPUS   16   /* contexts of one process in ort_comm_init_all / ort_trace3d_grid_multi */
 
 /* per-ray flag bits */

@@ -3,12 +3,20 @@
 #
 #   * No CUDA.jl, no Triton, no multi-backend dispatch, no CPU fallback: if the library or a B200 is
 #     missing, `ort_init` fails and the error is thrown.
-#   * The public API is unchanged: this module only ADDS methods with the reference's own
-#     signatures / return types (and batch variants taking vectors).
-#   * NOT RUNNABLE in the build environment (Julia is not installed there); the same C ABI is driven
-#     from Python (opticalraytracing.jl_b200/_lib.py, host.py) in tests and benchmarks.
+#   * The public API is unchanged.  Batch variants (vectors of rays / candidates) and every method that takes the
+#     backend tag `B200()` first are ADDED.  `full_trace(surfaces::Layout, system, H, k_rays, focus)` has exactly the
+#     reference's signature (src/PupilSampling.jl:85), so routing existing calls through the GPU means REPLACING that
+#     method: this is done at load time by `__init__` (an `@eval` into this module, which is why the module opts out of
+#     precompilation -- Julia >= 1.10 rejects method overwriting while precompiling) unless ENV["ORT_B200_OVERRIDE"] = "0".
+#     Without the override, call `full_trace(B200(), surfaces, system, H, ...)`.
+#   * Multi-GPU: ENV["ORT_B200_GPUS"] = n (default 1) opens n contexts, joins them with ort_comm_init_all (NCCL inside
+#     the library) and full_trace goes through ort_trace3d_grid_multi: y-rows block-sharded over the n GPUs, outputs in the
+#     reference's order, statistics all-gathered and merged inside the library.
+#   * NOT RUNNABLE in the build environment (Julia is not installed there) and therefore UNTESTED; the same C ABI is
+#     driven from Python (opticalraytracing.jl_b200/_lib.py, host.py) and from plain C (examples/) in tests and benchmarks.
 #
 # Library path: ENV["ORT_B200_LIB"] (default "libort_b200.so" on the loader path).
+__precompile__(false)
 module OpticalRayTracingB200
 
 using OpticalRayTracing
@@ -21,6 +29,10 @@ const LIB = get(ENV, "ORT_B200_LIB", "libort_b200.so")
 
 const ORT_ARITH_STRICT = Cint(0)
 const ORT_ARITH_FAST = Cint(1)
+
+"Backend tag: `full_trace(B200(), surfaces, system, H, ...)` never touches the reference's own methods."
+struct B200 end
+export B200
 
 # --- POD mirrors of include/ort_b200.h -------------------------------------------------------
 struct OrtField            # ort_field
@@ -45,6 +57,8 @@ struct OrtOpts             # ort_opts
     wg_nu::Float64
     wg_lambda::Float64
     opd_scale::Float64
+    gather_stats::Int32    # 1: this call is one rank's block of y-rows; stats = merged over the communicator
+    reserved::Int32
 end
 
 struct OrtStats            # ort_stats
@@ -75,6 +89,7 @@ struct OrtGridOut          # ort_grid_out
     mask::Ptr{UInt8}
     flags::Ptr{UInt8}
     stats::Ptr{OrtStats}
+    stats_local::Ptr{OrtStats}
 end
 
 # --- context ---------------------------------------------------------------------------------
@@ -86,14 +101,21 @@ function check(rc::Cint)
     error("libort_b200 error $rc: $msg")
 end
 
+const CTXS = Ptr{Cvoid}[]          # all contexts of this process (CTXS[1] == CTX[]); more than one with ORT_B200_GPUS
+
 function ctx()
     if CTX[] == C_NULL
-        out = Ref{Ptr{Cvoid}}(C_NULL)
-        dev = parse(Cint, get(ENV, "LOCAL_RANK", "0"))
-        rc = ccall((:ort_init, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), out, dev)
-        CTX[] = out[]
-        check(rc)
-        atexit(() -> ccall((:ort_free, LIB), Cvoid, (Ptr{Cvoid},), CTX[]))
+        ngpu = parse(Int, get(ENV, "ORT_B200_GPUS", "1"))
+        dev0 = parse(Cint, get(ENV, "LOCAL_RANK", "0"))
+        for d in 0:ngpu-1
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            rc = ccall((:ort_init, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), out, dev0 + d)
+            d == 0 && (CTX[] = out[])
+            check(rc)
+            push!(CTXS, out[])
+        end
+        ngpu > 1 && check(ccall((:ort_comm_init_all, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), CTXS, ngpu))
+        atexit(() -> foreach(c -> ccall((:ort_free, LIB), Cvoid, (Ptr{Cvoid},), c), CTXS))
     end
     return CTX[]
 end
@@ -115,7 +137,7 @@ end
 # --- full_trace: src/PupilSampling.jl:85-147 -------------------------------------------------
 # Lines :85-114 (prelude, ray aiming, Optim) are kept verbatim; the hot loop :115-138 and the
 # reductions :139-146 become ONE ccall.
-function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
+function full_trace(::B200, surfaces::Layout, system::SystemOrRayBasis, H::Float64,
                     k_rays::Int = spot_rays,
                     focus = system.marginal.z[end] - system.marginal.z[end-1];
                     arith = ORT_ARITH_FAST)
@@ -149,21 +171,28 @@ function full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
     N = length(ys) * length(xs)
     εx = Vector{Float64}(undef, N); εy = similar(εx); r = similar(εx); θ = similar(εx)
     stats = Ref(OrtStats(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
-    opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0, 1.0))   # compact = 1: the reference's push! order
+    opts = Ref(OrtOpts(arith, 1, 0, 0, 0.0, 1.0, 1.0, 0, 0))   # compact = 1: the reference's push! order
     GC.@preserve εx εy r θ stats begin
         out = Ref(OrtGridOut(pointer(εx), pointer(εy), pointer(r), pointer(θ), C_NULL, C_NULL, C_NULL,
-                             C_NULL, C_NULL, Base.unsafe_convert(Ptr{OrtStats}, stats)))
-        check(ccall((:ort_trace3d_grid, LIB), Cint,
-                    (Ptr{Cvoid}, Ref{OrtField}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64,
-                     Ref{OrtOpts}, Ref{OrtGridOut}),
-                    ctx(), Ref(field), 1, ys, length(ys), xs, length(xs), stop, a_stop, opts, out))
+                             C_NULL, C_NULL, Base.unsafe_convert(Ptr{OrtStats}, stats), C_NULL))
+        if length(CTXS) > 1      # one call, all GPUs of this process: rows block-sharded, stats merged in the library
+            check(ccall((:ort_trace3d_grid_multi, LIB), Cint,
+                        (Ptr{Ptr{Cvoid}}, Cint, Ref{OrtField}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64,
+                         Ref{OrtOpts}, Ref{OrtGridOut}),
+                        CTXS, length(CTXS), Ref(field), 1, ys, length(ys), xs, length(xs), stop, a_stop, opts, out))
+        else
+            check(ccall((:ort_trace3d_grid, LIB), Cint,
+                        (Ptr{Cvoid}, Ref{OrtField}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64,
+                         Ref{OrtOpts}, Ref{OrtGridOut}),
+                        ctx(), Ref(field), 1, ys, length(ys), xs, length(xs), stop, a_stop, opts, out))
+        end
     end
     nk = stats[].n_kept
     resize!(εx, nk); resize!(εy, nk); resize!(r, nk); resize!(θ, nk)
     # take advantage of symmetry (:139-146)
     εy = [εy; εy]
     εx = [εx; -εx]
-    ρ = r / stats[].r_max
+    ρ = min.(r / stats[].r_max, 1.0)     # r_max is the correctly rounded maximum; max(ρ) == 1 as in the reference (:142)
     ρ = [ρ; ρ]
     θ = [θ; π .- θ]
     nu = system.marginal.nu[end]
@@ -273,5 +302,19 @@ end
 
 transfer(system::System, V::Matrix{Float64}, τ, τ′) = transfer(system.M, V, τ, τ′)
 reverse_transfer(system::System, V::Matrix{Float64}, τ′, τ) = reverse_transfer(system.M, V, τ′, τ)
+
+full_trace(b::B200, system::System, H::Float64, args...; kw...) = full_trace(b, system.layout, system, H, args...; kw...)
+
+# The drop-in proper: replace the reference's own method (same signature, src/PupilSampling.jl:85) so that existing
+# user code -- full_trace(system, H), spot_diagram, ... -- runs on the GPU unchanged.  Done at load time, not at
+# definition time (see the header); ENV["ORT_B200_OVERRIDE"] = "0" leaves the reference's method in place.
+function __init__()
+    get(ENV, "ORT_B200_OVERRIDE", "1") == "0" && return
+    @eval function OpticalRayTracing.full_trace(surfaces::Layout, system::SystemOrRayBasis, H::Float64,
+                                                k_rays::Int = spot_rays,
+                                                focus = system.marginal.z[end] - system.marginal.z[end-1])
+        full_trace(B200(), surfaces, system, H, k_rays, focus)
+    end
+end
 
 end # module

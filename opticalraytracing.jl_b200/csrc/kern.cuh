@@ -51,6 +51,7 @@ struct CandArgs {
     int stop; double a_stop, a_stop2, u, v, h_prime;
     const double* aim;                      // NULL, or [C][ORT_AIM_NOUT]: per-candidate grid, stop, field, focus
     double* out;
+    int* lists;                             // FAST: device scratch of 2 + 2 C ints for k_cand_classify (NULL: one CTA per candidate, general kernel)
 };
 
 struct SeidelArgs {
@@ -83,7 +84,13 @@ struct AimCandArgs {
 struct LensK {                              // paraxial Lens rows in the constant bank
     int k; int clip;
     double tau[ORT_MAX_LENS], phi[ORT_MAX_LENS], a[ORT_MAX_LENS];
+    float2 csm[ORT_MAX_LENS];               // clip classifier of k_paraxial: z = fma(|float(hi word of y)|, csm.x, csm.y)
+    float ctf[ORT_MAX_LENS];                // clip classifier of k_paraxial_final: z = |float(hi word of y)| - ctf  (+Inf: the row never clips)
+    float amb_thr;                          // 1.5 x the largest ulp(ctf[row]): below it a decision was within two high-word units
+    int tau_finite;                         // every tau finite (Lens(surfaces) guarantees it, src/RayTracing.jl:42)
+    int clip_nice;                          // every aperture is +Inf / NaN (never clips) or > 2.2e-7 with a normal float pattern
 };
+
 
 struct ParaxArgs {
     long long N;
@@ -150,7 +157,7 @@ cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fiel
                                  cudaStream_t st);
 cudaError_t launch_compact(int* tile_counts, const CompactArgs& C, int n_fields, cudaStream_t st);
 cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream_t st);
-cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st);
+cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st, int sm_count);
 cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st);
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st);
 cudaError_t launch_transfer(const TransferArgs& A, cudaStream_t st);

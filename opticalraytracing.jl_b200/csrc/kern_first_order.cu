@@ -1,5 +1,7 @@
 // kern_first_order.cu -- the batched 2-D meridional real-ray trace (K2), the paraxial y-nu trace
 // (K3), the transfer-matrix apply (K4) and the FP64 peak microbenchmark (sm_100a).
+#include <stdlib.h>
+
 #include "kern.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -146,9 +148,47 @@ k_aim2d(const __grid_constant__ Presc P, AimArgs A)
 // Clip test `abs(y) - a[i] > 1e-13` (:135): an integer pre-filter on the exponent/mantissa high
 // word skips the exact FP64 test for rays that are not within 2^-19 of the aperture edge.
 // ------------------------------------------------------------------------------------------
+#ifndef PX_RPT
 #define PX_RPT 4
+#endif
+// The one-argument form of __launch_bounds__ on purpose: with a minimum-blocks argument (whatever its value) ptxas feeds the
+// per-row constants through predicated LDC loads into vector registers instead of uniform registers, +30 % kernel time.
+#if defined(PX_MINB)
+#define PX_BOUNDS __launch_bounds__(256, PX_MINB)
+#else
+#define PX_BOUNDS __launch_bounds__(256)
+#endif
+
+// Clip test of :135 for final-only output (no per-row table), one FFMA + one SHF per ray and row plus one shared FMNMX,
+// all off the FP64 pipe (which the 2 DFMA per ray and row already keep ~75 % busy):
+//   The high word of a double, read as a float, orders like |y| itself (IEEE bit patterns of positive numbers are
+//   monotonic), and FP32 instructions take |.| for free.  Per row the host prepares S = 1 / ulp_float(T) and M = T S for
+//   T = float(high word of a[row]): z = fma(|hf|, S, -M) is then EXACTLY the distance k = hi(|y|) - hi(a) in high-word units
+//   (2^-20 relative) whenever |y| is near the aperture.  k <= -1 means |y| < a (not clipped), k >= 2 means
+//   |y| - a > a 2^-21 > 1e-13 (clipped; rows with a <= 2.2e-7 take the exact path), k in {0, 1} is undecided.
+//     sign(z) goes into a 32-row bit mask with one funnel shift  -> first row with k >= 0 by clz at the end of the chunk
+//     amb = min(amb, |z|) over all rows and the thread's rays     -> amb < 1.5 iff some |k| <= 1 occurred
+//   A thread with an undecided row (or a non-finite ray) re-traces its rays from the inputs with the exact FP64 test --
+//   same arithmetic, so the same values: a few threads in a million.  A clipped ray simply keeps running; its outputs
+//   are NaN (:136) and its clip row is the first mask bit.
+struct ParaxOne { double y, w; int ci; };
+template <int ARITH>
+__device__ __noinline__ ParaxOne paraxial_exact_clip(const LensK& L, double yy, double ww)
+{
+    const int k = L.k;
+    int c = 0;
+    for (int row = 0; row < k; row++) {
+        const double tau = L.tau[row], phi = L.phi[row];
+        if (isfinite(tau)) yy = (ARITH == ORT_ARITH_STRICT) ? SA(yy, SM(ww, tau)) : fma(ww, tau, yy);   // :62
+        ww = (ARITH == ORT_ARITH_STRICT) ? SS(ww, SM(yy, phi)) : fma(-yy, phi, ww);                      // :67
+        if (c == 0 && SS(fabs(yy), L.a[row]) > 1e-13) c = row + 1;                                      // :135
+    }
+    ParaxOne o; o.y = yy; o.w = ww; o.ci = c;
+    return o;
+}
+
 template <int ARITH, bool TABLE, bool CLIP>
-__global__ void __launch_bounds__(256)
+__global__ void PX_BOUNDS
 k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
 {
     // Persistent CTAs, tile-strided, with a software prefetch: the loads of tile k+1 are issued before the
@@ -157,6 +197,7 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
     const long long per = 256 * PX_RPT;
     const long long ntiles = (N + per - 1) / per;
     const int k = L.k;
+    constexpr bool MASKCLIP = CLIP && !TABLE;
     double yn[PX_RPT], wn[PX_RPT];
     long long tile = blockIdx.x;
     if (tile < ntiles) {
@@ -195,6 +236,54 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
                 if (A.w_all) A.w_all[idx[j]] = w[j];
             }
         }
+        if (MASKCLIP) {
+            float amb = 4.0f;
+            unsigned msk[PX_RPT];
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++) msk[j] = 0xFFFFFFFFu;
+            // one flat row loop (the shape ptxas unrolls and feeds from uniform registers); the 32-row mask is folded
+            // into the clip row in a uniform branch every 32nd row and once behind the loop
+#define PX_FOLD(BASE, C)                                                                                      \
+            {                                                                                                 \
+                const unsigned live = ((C) == 32) ? 0xFFFFFFFFu : ((1u << (C)) - 1u);                         \
+                _Pragma("unroll") for (int j = 0; j < PX_RPT; j++) {                                          \
+                    const unsigned over = ~msk[j] & live;     /* bit (C - 1 - i): row BASE + i had k >= 0 */  \
+                    if (ci[j] == 0 && over) ci[j] = (BASE) + (C) - 31 + __clz(over);                          \
+                    msk[j] = 0xFFFFFFFFu;                                                                     \
+                }                                                                                             \
+            }
+#pragma unroll 4
+            for (int row = 0; row < k; row++) {
+                const double tau = L.tau[row], phi = L.phi[row];
+                const float2 csm = L.csm[row]; const float cs = csm.x, ncm = csm.y;
+                const bool fin = isfinite(tau);                      // uniform (:62)
+                if (fin) {
+#pragma unroll
+                    for (int j = 0; j < PX_RPT; j++)
+                        y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < PX_RPT; j++) {
+                    w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);   // :67
+                    const float z = fmaf(fabsf(__int_as_float(__double2hiint(y[j]))), cs, ncm);
+                    msk[j] = __funnelshift_l(__float_as_uint(z), msk[j], 1);
+                    amb = fminf(amb, fabsf(z));
+                }
+                if ((row & 31) == 31) PX_FOLD(row - 31, 32)
+            }
+            if (k & 31) PX_FOLD(k & ~31, k & 31)
+#undef PX_FOLD
+            bool slow = !(amb >= 1.5f);
+#pragma unroll
+            for (int j = 0; j < PX_RPT; j++) slow = slow || !isfinite(y[j]) || !isfinite(w[j]);
+            if (slow) {
+#pragma unroll
+                for (int j = 0; j < PX_RPT; j++) {
+                    const ParaxOne o = paraxial_exact_clip<ARITH>(L, A.y0[idx[j]], A.w0[idx[j]]);
+                    y[j] = o.y; w[j] = o.w; ci[j] = o.ci;
+                }
+            }
+        } else {
         for (int row = 0; row < k; row++) {
             const double tau = L.tau[row], phi = L.phi[row];
             const bool fin = isfinite(tau);                  // uniform (:62)
@@ -209,9 +298,9 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
             for (int j = 0; j < PX_RPT; j++)
                 w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);       // :67
             if (CLIP) {
-                // One integer pre-filter for the thread's 4 rays: only if some |y| >= a (1 - 2^-20) by high word (or
-                // is NaN) run the exact test of :135.  A clipped ray continues as (0, 0) -- finite, so it never
-                // re-enters the exact test -- and is written out as NaN (:136) at the end.
+                // (table output) One integer pre-filter for the thread's rays: only if some |y| >= a (1 - 2^-20) by high
+                // word (or is NaN) run the exact test of :135.  A clipped ray continues as (0, 0) -- finite, so it never
+                // re-enters the exact test -- and is written out as NaN (:136).
                 int mx = 0;
 #pragma unroll
                 for (int j = 0; j < PX_RPT; j++) mx = max(mx, __double2hiint(y[j]) & 0x7FFFFFFF);
@@ -230,12 +319,135 @@ k_paraxial(const __grid_constant__ LensK L, ParaxArgs A)
                 }
             }
         }
+        }
 #pragma unroll
         for (int j = 0; j < PX_RPT; j++) {
             if (!valid[j]) continue;
             if (A.y) __stcs(A.y + idx[j], ci[j] ? CUDART_NAN : y[j]);
             if (A.w) __stcs(A.w + idx[j], ci[j] ? CUDART_NAN : w[j]);
             if (A.clip_idx) A.clip_idx[idx[j]] = ci[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3, the streaming form: final (y, nu) only (no per-row table), every tau finite (Lens(surfaces) guarantees it:
+// src/RayTracing.jl:42 zeroes an infinite t[1]), apertures "nice" (LensK::clip_nice).  Everything else runs k_paraxial above.
+// ncu on k_paraxial showed the plain kernel issue-bound (82 % of the issue slots, 10.6 non-FP64 instructions per row for
+// 8 DFMA) and the clip kernel latency-bound at 33 instructions per row.  Here a row of PX2_RPT rays costs 2 uniform loads +
+// 2 PX2_RPT DFMA, plus per ray FADD + SHF + half an FMNMX3 when clipping:
+//   hf = the high word of y read as a float, T[row] = the high word of a[row] read as a float (host): z = |hf| - T is the
+//   distance between |y| and a in float ulps of T (= 2^-20-relative units of the doubles), exact when they are close.
+//   sign(z) -> one bit of a 32-row mask per ray (funnel shift); amb = min |z| over rows and the thread's rays.
+//   With U = the largest ulp(T[row]) (host, LensK::amb_thr = 1.5 U): amb >= 1.5 U means every |z| was at least two units,
+//   i.e. every decision was clear of the 1e-13 threshold of :135 (k <= -2: |y| < a; k >= 2: |y| - a > a 2^-21 > 1e-13 for
+//   a > 2.2e-7) and the first clear bit of the mask is the clip row.  Otherwise (a few threads in a million), or when a
+//   ray went non-finite, the thread re-traces its rays with the exact FP64 test -- same arithmetic, same values.
+// ------------------------------------------------------------------------------------------
+// Rays per thread: 8 without the clip test (5.67 ms per 1e9 rays against 6.03 at 4: fewer warps, more loads in flight per
+// thread), 4 with it (11.4 ms against 12.8 at 8; the clip kernel is bound by issue slots, not by HBM -- DESIGN.md section 3).
+#ifndef PX2_RPT
+#define PX2_RPT 8
+#endif
+#ifndef PX2_RPT_CLIP
+#define PX2_RPT_CLIP 4
+#endif
+template <int ARITH, bool CLIP>
+__global__ void __launch_bounds__(256)
+k_paraxial_final(const __grid_constant__ LensK L, ParaxArgs A)
+{
+    constexpr int R = CLIP ? PX2_RPT_CLIP : PX2_RPT;
+    const long long N = A.N;
+    const long long per = 256 * R;
+    const long long ntiles = (N + per - 1) / per;
+    const int k = L.k;
+    double yn[R], wn[R];
+    long long tile = blockIdx.x;
+    if (tile < ntiles) {
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const long long i = min(tile * per + (long long)j * 256 + threadIdx.x, N - 1);
+            yn[j] = __ldcs(A.y0 + i); wn[j] = __ldcs(A.w0 + i);
+        }
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long i0 = tile * per + threadIdx.x;
+        double y[R], w[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) { y[j] = yn[j]; w[j] = wn[j]; }
+        const long long nxt = tile + gridDim.x;
+        if (nxt < ntiles) {                          // prefetch the next tile of this CTA behind this tile's arithmetic
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const long long i = min(nxt * per + (long long)j * 256 + threadIdx.x, N - 1);
+                yn[j] = __ldcs(A.y0 + i); wn[j] = __ldcs(A.w0 + i);
+            }
+        }
+        unsigned msk[R];
+        int ci[R];
+        float amb = CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < R; j++) { msk[j] = 0xFFFFFFFFu; ci[j] = 0; }
+#define PX2_ROW(ROWIDX)                                                                                              \
+        {                                                                                                             \
+            const double tau = L.tau[ROWIDX], phi = L.phi[ROWIDX];                                                    \
+            const float tf = CLIP ? L.ctf[ROWIDX] : 0.0f;                                                             \
+            _Pragma("unroll") for (int j = 0; j < R; j++) {                                                           \
+                y[j] = (ARITH == ORT_ARITH_STRICT) ? SA(y[j], SM(w[j], tau)) : fma(w[j], tau, y[j]);     /* :62 */    \
+                w[j] = (ARITH == ORT_ARITH_STRICT) ? SS(w[j], SM(y[j], phi)) : fma(-y[j], phi, w[j]);    /* :67 */    \
+                if (CLIP) {                                                                                           \
+                    const float z = fabsf(__int_as_float(__double2hiint(y[j]))) - tf;                                 \
+                    msk[j] = __funnelshift_l(__float_as_uint(z), msk[j], 1);                                          \
+                    amb = fminf(amb, fabsf(z));                                                                       \
+                }                                                                                                     \
+            }                                                                                                         \
+        }
+#define PX2_FOLD(BASE, C)                                                                                             \
+        {                                                                                                             \
+            const unsigned live = ((C) == 32) ? 0xFFFFFFFFu : ((1u << (C)) - 1u);                                     \
+            _Pragma("unroll") for (int j = 0; j < R; j++) {                                                           \
+                const unsigned over = ~msk[j] & live;         /* bit (C - 1 - i): |y| >= a at row BASE + i */          \
+                if (ci[j] == 0 && over) ci[j] = (BASE) + (C) - 31 + __clz(over);                                      \
+                msk[j] = 0xFFFFFFFFu;                                                                                 \
+            }                                                                                                         \
+        }
+        if (CLIP) {
+            int row = 0;
+            for (; row + 32 <= k; row += 32) {
+#pragma unroll 4
+                for (int i = 0; i < 32; i++) PX2_ROW(row + i)
+                PX2_FOLD(row, 32)
+            }
+            if (row < k) {
+                const int c = k - row;
+#pragma unroll 4
+                for (int i = 0; i < c; i++) PX2_ROW(row + i)
+                PX2_FOLD(row, c)
+            }
+            bool slow = !(amb >= L.amb_thr);
+#pragma unroll
+            for (int j = 0; j < R; j++) slow = slow || !isfinite(y[j]) || !isfinite(w[j]);
+            if (slow) {
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const long long i = min(i0 + (long long)j * 256, N - 1);
+                    const ParaxOne o = paraxial_exact_clip<ARITH>(L, A.y0[i], A.w0[i]);
+                    y[j] = o.y; w[j] = o.w; ci[j] = o.ci;
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int row = 0; row < k; row++) PX2_ROW(row)
+        }
+#undef PX2_ROW
+#undef PX2_FOLD
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const long long i = i0 + (long long)j * 256;
+            if (i >= N) continue;
+            if (A.y) __stcs(A.y + i, (CLIP && ci[j]) ? CUDART_NAN : y[j]);
+            if (A.w) __stcs(A.w + i, (CLIP && ci[j]) ? CUDART_NAN : w[j]);
+            if (CLIP && A.clip_idx) __stcs(A.clip_idx + i, ci[j]);
         }
     }
 }
@@ -619,12 +831,23 @@ cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st
 
 cudaError_t launch_paraxial(const LensK& L, const ParaxArgs& A, int arith, cudaStream_t st)
 {
+    const bool table = A.y_all || A.w_all;
+    const bool clip = L.clip != 0;
+    // ORT_PX_GRID = CTAs per SM of the persistent grids (tuning)
+    static const int per_sm = [] { const char* e = getenv("ORT_PX_GRID"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+    if (!table && L.tau_finite && (!clip || L.clip_nice)) {       // the streaming form
+        const long long per = 256 * (clip ? PX2_RPT_CLIP : PX2_RPT), ntl = (A.N + per - 1) / per;
+        if (ntl == 0) return cudaSuccess;
+        const unsigned nb = (unsigned)(ntl < 148LL * per_sm ? ntl : 148LL * per_sm);
+        if (arith == ORT_ARITH_FAST) { if (clip) k_paraxial_final<ORT_ARITH_FAST, true><<<nb, 256, 0, st>>>(L, A); else k_paraxial_final<ORT_ARITH_FAST, false><<<nb, 256, 0, st>>>(L, A); }
+        else                         { if (clip) k_paraxial_final<ORT_ARITH_STRICT, true><<<nb, 256, 0, st>>>(L, A); else k_paraxial_final<ORT_ARITH_STRICT, false><<<nb, 256, 0, st>>>(L, A); }
+        return cudaGetLastError();
+    }
     const long long per = 256 * PX_RPT;
     const long long ntl = (A.N + per - 1) / per;
     if (ntl == 0) return cudaSuccess;
-    const unsigned nb = (unsigned)(ntl < 148 * 8 ? ntl : 148 * 8);     // 1.6 waves of the 5 resident CTAs/SM; whole-wave grids measured slower
-    const bool table = A.y_all || A.w_all;
-    const bool clip = L.clip != 0;
+    // 1.6 waves of the 5 resident CTAs/SM; whole-wave grids measured slower
+    const unsigned nb = (unsigned)(ntl < 148LL * per_sm ? ntl : 148LL * per_sm);
 #define PX_LAUNCH(AR, TB, CL) k_paraxial<AR, TB, CL><<<nb, 256, 0, st>>>(L, A)
     if (arith == ORT_ARITH_FAST) {
         if (table) { if (clip) PX_LAUNCH(ORT_ARITH_FAST, true, true); else PX_LAUNCH(ORT_ARITH_FAST, true, false); }

@@ -243,6 +243,8 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     if (LEAN) {
         if (valid) {
             if (LEAN == 1) { (A.ex + fbase)[idx] = ex; (A.ey + fbase)[idx] = ey; (A.mask + fbase)[idx] = (uint8_t)kept; }
+            if (LEAN == 1 && EXT) (A.opd + fbase)[idx] = opd;       // the OPD sweep's output set: ex, ey, opd, mask
+            if (EXTK == 1) acc.nvig += vig ? 1 : 0;
             if (sv) {
                 acc.nstrict++;
                 acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
@@ -586,7 +588,12 @@ k_candidates(CandArgs A)
 {
     __shared__ SurfK s_surf[ORT_MAX_ROWS];
     __shared__ Part s_part[ORT_TILE / 32];
-    const long long c = blockIdx.x;
+    // FAST sweeps come with the classified lists of k_cand_classify: this kernel then takes the GENERAL candidates
+    // (mirrors, conics, weak or dummy spheres), one per CTA, grid-strided
+    const int nlist = A.lists ? A.lists[1] : 0;
+    for (long long li = blockIdx.x; li < (A.lists ? (long long)nlist : A.C); li += gridDim.x) {
+    if (li != (long long)blockIdx.x) __syncthreads();           // the previous candidate's shared state is still being read
+    const long long c = A.lists ? (long long)A.lists[2 + A.C + li] : li;
     const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
     const double* Rc = A.RtnK + (size_t)c * 4 * rows;
     const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
@@ -624,7 +631,6 @@ k_candidates(CandArgs A)
     __syncthreads();
     const volatile double* par = s_par;
     const bool mirror = s_mirror != 0;
-    const bool simple = s_general == 0 && !mirror;               // refracting spheres and planes only (simple_surface)
     const int stop = s_stop;
     const bool ok = stop > 0;
 #define CAND_PAR(i, shared_grid_value) (AIMED ? par[i] : (shared_grid_value))
@@ -671,8 +677,7 @@ k_candidates(CandArgs A)
         }
         Hit h[RPT]; int amb[RPT];
         if (ARITH == ORT_ARITH_FAST) {      // CTA-uniform choice between the general and the no-mirror fast path
-            if (simple) trace_fast<RPT, false, SurfK*, false, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
-            else if (mirror) trace_fast<RPT, false, SurfK*, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+            if (mirror) trace_fast<RPT, false, SurfK*, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
             else trace_fast<RPT, false, SurfK*, false>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
         }
 #pragma unroll
@@ -704,6 +709,166 @@ k_candidates(CandArgs A)
         o[0] = ok ? (double)p.n : CUDART_NAN;
         if (ok && p.n > 0) { o[1] = p.mx; o[2] = p.my; o[3] = sqrt((p.m2x + p.m2y) / (double)p.n); }
         else { o[1] = o[2] = o[3] = CUDART_NAN; }
+    }
+    }
+}
+
+// FAST sweeps first sort the population (one thread per candidate): lists[0] / lists[1] = number of SIMPLE / GENERAL
+// candidates, lists[2 ..) / lists[2 + C ..) their indices.  SIMPLE = refracting spheres (|R| <= 64 L) and planes only,
+// every index positive (simple_surface): those go to k_candidates_simple.  The order inside a list is whatever the
+// atomics produce; every candidate's result is computed alone and written to its own slot, so results do not depend on it.
+__global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, const double* RtnK, int aimed, int* lists)
+{
+    const long long c = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const double* Rc = RtnK + (size_t)c * 4 * rows;
+    const double L = gap_scale(Rc + rows, rows);
+    bool simple = true;
+    for (int i = 0; i + 1 < rows; i++) {
+        SurfK S;
+        derive_surface(S, Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i], Rc[2 * rows + i + 1]);
+        if (!(Rc[2 * rows + i] > 0.0) || !(Rc[2 * rows + i + 1] > 0.0) || !simple_surface(S, L)) simple = false;
+    }
+    if (aimed && !(Rc[3 * rows - 1] > 0.0)) simple = false;     // the appended image plane refracts into n = 1
+    const int slot = atomicAdd(&lists[simple ? 0 : 1], 1);
+    lists[2 + (simple ? 0 : C) + slot] = (int)c;
+}
+
+// K5 for SIMPLE candidates: the three-body surface loop (fast_step<.., SIMPLE>), CS_RPT rays per thread, its own launch
+// bounds (no spills), plain shifted sums instead of per-thread Chan records.  One candidate per CTA pass, grid-strided
+// over the list of k_cand_classify.  4096 rays = 10.67 passes of 128 x 3 rays (3 % padding; 256 x 3 would pad 11 %).
+#define CS_THREADS 128
+#define CS_RPT 3
+template <bool AIMED>
+__global__ void __launch_bounds__(CS_THREADS, 4)
+k_candidates_simple(CandArgs A)
+{
+    __shared__ SurfK s_surf[ORT_MAX_ROWS];
+    __shared__ double s_par[12];
+    __shared__ int s_stop;
+    __shared__ double s_red[CS_THREADS / 32][6];
+    __shared__ int s_redn[CS_THREADS / 32];
+    const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
+    const int nlist = A.lists[0];
+    const unsigned NN = (unsigned)A.ny * (unsigned)A.nx, nxu = (unsigned)A.nx;
+    const unsigned step = CS_THREADS * CS_RPT, dq = step / nxu, dr = step - dq * nxu;
+    for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
+        if (li != (int)blockIdx.x) __syncthreads();
+        const long long c = A.lists[2 + li];
+        const double* Rc = A.RtnK + (size_t)c * 4 * rows;
+        const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
+        if (threadIdx.x < rows - 1) {
+            const int i = threadIdx.x;
+            derive_surface(s_surf[i], Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i], Rc[2 * rows + i + 1]);
+            simple_surface(s_surf[i], gap_scale(Rc + rows, rows));
+        } else if (AIMED && threadIdx.x == rows - 1) {
+            derive_surface(s_surf[rows - 1], CUDART_INF, 0.0, rec[5], Rc[3 * rows - 1], 1.0);
+            simple_surface(s_surf[rows - 1], 0.0);
+        } else if (threadIdx.x == CS_THREADS - 1) {
+            if (AIMED) {
+                const int st = (int)rec[6];
+                const bool good = rec[11] == 0.0 && st >= 1 && st <= rows - 1;     // NaN record / failed prelude -> NaN result
+                s_stop = good ? st : 0;
+                s_par[0] = rec[0]; s_par[1] = rec[1]; s_par[2] = SD(SS(rec[1], rec[0]), (double)(A.ny - 1));
+                s_par[3] = rec[2]; s_par[4] = SD(rec[2], (double)(A.nx - 1));
+                s_par[5] = rec[7]; s_par[6] = rec[7] * rec[7]; s_par[7] = rec[3]; s_par[8] = rec[4];
+                // common shift of the moments: the two rim rays straddle the spot
+                const bool have = rec[14] == 1.0 && rec[16] == 1.0 && rec[20] == 1.0;
+                s_par[9] = have ? 0.5 * (rec[18] + rec[22]) : 0.0;
+            } else {
+                s_stop = A.stop;
+                s_par[5] = A.a_stop; s_par[6] = A.a_stop2; s_par[7] = A.u; s_par[8] = A.h_prime; s_par[9] = 0.0;
+            }
+        }
+        __syncthreads();
+        const volatile double* par = s_par;
+        const int stop = s_stop;
+        const bool ok = stop > 0;
+        const double n0 = Rc[2 * rows];
+        const double cy = par[9];
+        double K0[3];
+        {
+            const double fu = par[7];
+            const double inv = n0 * fast_rsqrt(fma(A.v, A.v, fma(fu, fu, 1.0)));
+            K0[0] = A.v * inv; K0[1] = fu * inv; K0[2] = inv;
+        }
+        int n = 0;
+        double s1x = 0.0, s2x = 0.0, s1y = 0.0, s2y = 0.0, rmax = -CUDART_INF;
+        const unsigned edge_b = (unsigned)(A.ny - 1) * nxu;
+        if (AIMED && ok && threadIdx.x < 2) {           // the two rim rays (first / last row at x = 0), see k_candidates
+            double ex, ey, rr; bool keep;
+            if (rec[14] == 1.0) { const double* e = rec + 16 + 4 * threadIdx.x; keep = e[0] == 1.0; ex = e[1]; ey = e[2]; rr = e[3]; }
+            else {
+                const Hit he = trace_strict_cold<false>(s_surf, nsurf, stop, threadIdx.x ? par[1] : par[0], 0.0, par[7], A.v);
+                const double ri = jl_hypot(he.xs, he.ys);
+                keep = !(ri > par[5] || is_nan_bits(he.xf) || is_nan_bits(he.yf)); ex = he.xf; ey = he.yf - par[8]; rr = ri * ri;
+            }
+            if (keep) { const double dy = ey - cy; s1x += ex; s2x = fma(ex, ex, s2x); s1y += dy; s2y = fma(dy, dy, s2y); rmax = fmax(rmax, rr); n++; }
+        }
+        unsigned iyj[CS_RPT], ixj[CS_RPT];
+#pragma unroll
+        for (int j = 0; j < CS_RPT; j++) { const unsigned i = threadIdx.x + j * CS_THREADS; iyj[j] = i / nxu; ixj[j] = i - iyj[j] * nxu; }
+        for (unsigned i0 = threadIdx.x; ok && i0 < NN; i0 += step) {
+            double y0[CS_RPT], x0[CS_RPT], uu[CS_RPT], vv[CS_RPT];
+            bool valid[CS_RPT];
+#pragma unroll
+            for (int j = 0; j < CS_RPT; j++) {
+                const unsigned i = i0 + j * CS_THREADS;
+                valid[j] = i < NN && !(AIMED && (i == 0 || i == edge_b));
+                const unsigned iy = i < NN ? iyj[j] : (unsigned)A.ny - 1, ix = i < NN ? ixj[j] : nxu - 1;
+                if (AIMED) {        // range(a, b, n)[i] = a + i * step, last point exactly b
+                    y0[j] = (iy == (unsigned)A.ny - 1) ? par[1] : SA(par[0], SM((double)iy, par[2]));
+                    x0[j] = (ix == nxu - 1) ? par[3] : SM((double)ix, par[4]);
+                } else { y0[j] = __ldg(A.ys + iy); x0[j] = __ldg(A.xs + ix); }
+                uu[j] = 0.0; vv[j] = A.v;                           // the fast path takes the direction from K0
+                ixj[j] += dr; iyj[j] += dq;
+                if (ixj[j] >= nxu) { ixj[j] -= nxu; iyj[j]++; }
+            }
+            Hit h[CS_RPT]; int amb[CS_RPT];
+            trace_fast<CS_RPT, false, SurfK*, false, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+#pragma unroll
+            for (int j = 0; j < CS_RPT; j++) {
+                const double a_stop2 = par[6];
+                double r2 = fma(h[j].xs, h[j].xs, h[j].ys * h[j].ys);
+                amb[j] |= tiny_vs_bit(r2 - a_stop2, a_stop2);
+                bool drop = r2 > a_stop2;
+                if (amb[j] < 0 && valid[j]) {                       // guard band / miss / TIR: the reference arithmetic decides
+                    h[j] = trace_strict_cold<false>(s_surf, nsurf, stop, y0[j], x0[j], par[7], A.v);
+                    const double ri = jl_hypot(h[j].xs, h[j].ys);
+                    drop = ri > par[5] || is_nan_bits(h[j].xf) || is_nan_bits(h[j].yf);
+                    r2 = ri * ri;
+                }
+                if (valid[j] && !drop) {
+                    const double ex = h[j].xf, dy = (h[j].yf - par[8]) - cy;
+                    s1x += ex; s2x = fma(ex, ex, s2x); s1y += dy; s2y = fma(dy, dy, s2y);
+                    if (r2 > rmax) rmax = r2;
+                    n++;
+                }
+            }
+        }
+        // deterministic CTA reduction: shuffle tree, then thread 0 folds the warp leaders in warp order
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            n += __shfl_down_sync(0xffffffffu, n, d);
+            s1x += __shfl_down_sync(0xffffffffu, s1x, d); s2x += __shfl_down_sync(0xffffffffu, s2x, d);
+            s1y += __shfl_down_sync(0xffffffffu, s1y, d); s2y += __shfl_down_sync(0xffffffffu, s2y, d);
+            rmax = fmax(rmax, __shfl_down_sync(0xffffffffu, rmax, d));
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { s_redn[warp] = n; s_red[warp][0] = s1x; s_red[warp][1] = s2x; s_red[warp][2] = s1y; s_red[warp][3] = s2y; s_red[warp][4] = rmax; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < CS_THREADS / 32; w++) {
+                n += s_redn[w]; s1x += s_red[w][0]; s2x += s_red[w][1]; s1y += s_red[w][2]; s2y += s_red[w][3];
+            }
+            double* o = A.out + 4 * c;
+            o[0] = ok ? (double)n : CUDART_NAN;
+            if (ok && n > 0) {
+                const double dn = (double)n;
+                const double m2 = fmax(s2x - s1x * s1x / dn, 0.0) + fmax(s2y - s1y * s1y / dn, 0.0);
+                o[1] = s1x / dn; o[2] = cy + s1y / dn; o[3] = sqrt(m2 / dn);
+            } else { o[1] = o[2] = o[3] = CUDART_NAN; }
+        }
     }
 }
 
@@ -790,7 +955,11 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool stats_only = !ext && !others && !A.ex && !A.ey && !A.mask;
         const int variant = grid_variant(P, arith, ext);
         const bool simple = variant == 2;
-        if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        // the output set of an OPD sweep (ex, ey, opd, mask + statistics) has its own lean epilogue
+        const bool lean_opd = (A.ext & ORT_EXT_OPD) && A.ex && A.ey && A.mask && A.opd && !(A.r || A.theta || A.wx || A.wy || A.flags);
+        if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE) && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 3 && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (variant == 3) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
@@ -845,15 +1014,44 @@ cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st)
+int candidates_blocks_per_sm(int simple)
+{
+    int nb = 0;
+    cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_candidates_simple<true>, CS_THREADS, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_candidates<ORT_ARITH_FAST, true>, ORT_TILE, 0);
+    if (e != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+// FAST: classify, then the SIMPLE candidates through k_candidates_simple and the rest through k_candidates, both
+// grid-strided over their list (an empty list costs one wave of CTAs that exit at once).  STRICT: one CTA per candidate.
+cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st, int sm_count)
 {
     if (A.C == 0) return cudaSuccess;
+    if (arith != ORT_ARITH_FAST || !A.lists) {
+        CandArgs B = A; B.lists = nullptr;
+        const unsigned nb = (unsigned)A.C;
+        if (A.aim) {
+            if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, true><<<nb, ORT_TILE, 0, st>>>(B);
+            else k_candidates<ORT_ARITH_STRICT, true><<<nb, ORT_TILE, 0, st>>>(B);
+        } else {
+            if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, false><<<nb, ORT_TILE, 0, st>>>(B);
+            else k_candidates<ORT_ARITH_STRICT, false><<<nb, ORT_TILE, 0, st>>>(B);
+        }
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(A.lists, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_cand_classify<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A.rows, A.C, A.RtnK, A.aim != nullptr, A.lists);
+    static const int bps_s = candidates_blocks_per_sm(1), bps_g = candidates_blocks_per_sm(0);
+    const long long gs = (long long)sm_count * bps_s * 8, gg = (long long)sm_count * bps_g;
+    const unsigned nbs = (unsigned)(A.C < gs ? A.C : gs), nbg = (unsigned)(A.C < gg ? A.C : gg);
     if (A.aim) {
-        if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, true><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
-        else k_candidates<ORT_ARITH_STRICT, true><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+        k_candidates_simple<true><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates<ORT_ARITH_FAST, true><<<nbg, ORT_TILE, 0, st>>>(A);
     } else {
-        if (arith == ORT_ARITH_FAST) k_candidates<ORT_ARITH_FAST, false><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
-        else k_candidates<ORT_ARITH_STRICT, false><<<(unsigned)A.C, ORT_TILE, 0, st>>>(A);
+        k_candidates_simple<false><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates<ORT_ARITH_FAST, false><<<nbg, ORT_TILE, 0, st>>>(A);
     }
     return cudaGetLastError();
 }

@@ -629,13 +629,50 @@ int ort_aim2d(ort_ctx* ctx, int64_t N, const double* x_start, const double* othe
     return ORT_OK;
 }
 
+// Per-row constants of the clip classifier of k_paraxial (kern_first_order.cu): with T = the high word of a read as a
+// float, S = 1 / ulp(T) (a power of two) and M = T S (an integer below 2^24, exact), z = fma(|hf|, S, -M) counts high-word
+// units between |y| and a.  +Inf / NaN apertures never clip (z = -4 for every ray); apertures too small for the
+// 2^-21 a > 1e-13 argument, or whose constants leave the float range, send every ray to the exact test (z = 0).
+static void paraxial_clip_constants(double a, float* cs, float* ncm)
+{
+    *cs = 0.0f; *ncm = 0.0f;
+    if (isnan(a) || a == INFINITY) { *ncm = -4.0f; return; }
+    if (!(a > 2.2e-7) || !isfinite(a)) return;
+    int64_t bits; memcpy(&bits, &a, 8);
+    const int32_t hi = (int32_t)(bits >> 32);
+    float T; memcpy(&T, &hi, 4);
+    const int ef = (hi >> 23) & 0xFF;
+    if (ef < 1 || ef > 253) return;                          // T (and T + 2 units) must be a normal float
+    const float ulp = nextafterf(T, INFINITY) - T;
+    const float S = 1.0f / ulp, M = T * S;
+    if (!isfinite(S) || !isfinite(M)) return;
+    *cs = S; *ncm = -M;
+}
+
 static int lens_fill(ort_ctx* ctx, LensK& L, int k, const double* tau, const double* phi, const double* a, int clip)
 {
     if (k < 0 || k > ORT_MAX_LENS) return fail(ctx, ORT_EINVAL, "paraxial_batch: k = %d not in [0, %d]", k, ORT_MAX_LENS);
     if (k > 0 && (!tau || !phi)) return fail(ctx, ORT_EINVAL, "paraxial_batch: NULL tau/phi");
     memset(&L, 0, sizeof L);
     L.k = k; L.clip = (clip && a) ? 1 : 0;
-    for (int i = 0; i < k; i++) { L.tau[i] = tau[i]; L.phi[i] = phi[i]; L.a[i] = a ? a[i] : INFINITY; }
+    L.tau_finite = 1; L.clip_nice = 1;
+    float umax = 0.0f;
+    for (int i = 0; i < k; i++) {
+        L.tau[i] = tau[i]; L.phi[i] = phi[i]; L.a[i] = a ? a[i] : INFINITY;
+        paraxial_clip_constants(L.a[i], &L.csm[i].x, &L.csm[i].y);
+        if (!isfinite(tau[i])) L.tau_finite = 0;
+        // the streaming kernel's classifier: T = high word of a as a float; rows that never clip get +Inf
+        L.ctf[i] = INFINITY;
+        if (isnan(L.a[i]) || L.a[i] == INFINITY) continue;
+        if (L.csm[i].x == 0.0f) { L.clip_nice = 0; continue; }      // needs the exact test on every ray: general kernel
+        int64_t bits; memcpy(&bits, &L.a[i], 8);
+        const int32_t hi = (int32_t)(bits >> 32);
+        float T; memcpy(&T, &hi, 4);
+        L.ctf[i] = T;
+        const float ulp = nextafterf(T, INFINITY) - T;
+        if (ulp > umax) umax = ulp;
+    }
+    L.amb_thr = 1.5f * umax;
     return ORT_OK;
 }
 
@@ -765,11 +802,13 @@ int ort_trace3d_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* 
     A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.ys = d_ys; A.xs = d_xs; A.ny = ny; A.nx = nx;
     A.stop = stop; A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
     A.u = field->u; A.v = field->v; A.h_prime = field->h_prime; A.out = d_out;
+    ScratchScope scratch(ctx, (cudaStream_t)stream);
+    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (2 + 2 * (size_t)C), A.lists);
     {
         ProfScope prof(ctx, (cudaStream_t)stream);
-        CK(launch_candidates(A, arith, (cudaStream_t)stream));
+        CK(launch_candidates(A, arith, (cudaStream_t)stream, ctx->sm_count));
     }
-    if (C > 0) ctx->launches++;
+    if (C > 0) ctx->launches += A.lists ? 3 : 1;
     return ORT_OK;
 }
 
@@ -920,11 +959,13 @@ int ort_trace3d_candidates_aimed_dev(ort_ctx* ctx, int rows, int64_t C, const do
     A.rows = rows; A.C = C; A.RtnK = d_RtnK; A.aim = d_aim; A.ny = ny; A.nx = nx; A.stop = 1;
     A.v = 0.0;                                       // V = 0 (meridional field, src/PupilSampling.jl:98)
     A.out = d_out;
+    ScratchScope scratch(ctx, (cudaStream_t)stream);
+    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (2 + 2 * (size_t)C), A.lists);
     {
         ProfScope prof(ctx, (cudaStream_t)stream);
-        CK(launch_candidates(A, arith, (cudaStream_t)stream));
+        CK(launch_candidates(A, arith, (cudaStream_t)stream, ctx->sm_count));
     }
-    if (C > 0) ctx->launches++;
+    if (C > 0) ctx->launches += A.lists ? 3 : 1;
     return ORT_OK;
 }
 

@@ -728,7 +728,8 @@ def _mirror(r, f, nu, H):
     ex, ey, rr, th = (r[k][f][:n] for k in ("ex", "ey", "r", "theta"))
     x2 = np.concatenate([ex, -ex])
     y2 = np.concatenate([ey, ey])
-    rho = rr / st["r_max"] if n else rr
+    # r_max is the correctly rounded sqrt of the largest r^2 while FAST r values carry ~1 ulp: clamp so max(rho) == 1 (:142)
+    rho = np.minimum(rr / st["r_max"], 1.0) if n else rr
     rho2 = np.concatenate([rho, rho])
     t2 = np.concatenate([th, math.pi - th])
     return RealRayError(x2, y2, nu, rho2, t2, H, rms_from_stats(st), stats=r["stats"][f:f + 1].copy())

@@ -75,6 +75,62 @@ def test_paraxial_batch(ctx, orc, ort):
         assert bits_equal(ya[:, j], rt[:, 0]) and bits_equal(wa[:, j], rt[:, 1])
 
 
+def test_paraxial_clip_classifier_adversarial(ctx, orc, ort):
+    """the FP32 high-word classifier of k_paraxial's clip test (src/RayTracing.jl:135) must agree with the exact FP64 test
+    everywhere: rays that hug an aperture to the last ulp, the 1e-13 threshold itself, apertures of every magnitude
+    (tiny, huge, +Inf, NaN, 0, negative), more than 32 rows (second mask chunk), NaN / Inf rays.  STRICT bit-exact."""
+    rng = np.random.default_rng(11)
+    # (1) a lens that leaves y untouched (tau = 0, phi = 0): y_row == y0, so y0 can be placed at will against a[row]
+    k = 70
+    tau, phi = np.zeros(k), np.zeros(k)
+    a = np.full(k, np.inf)
+    a[41] = 7.25
+    base = 7.25
+    offs = np.concatenate([np.arange(-40, 41) * np.spacing(base), [1e-13, 1e-13 + np.spacing(base), 1e-13 - np.spacing(base),
+                                                                  2e-13, 5e-14, -1e-13, 3e-7, -3e-7, 1e-6, -1e-6]])
+    y0 = np.concatenate([base + offs, -(base + offs), [np.nan, np.inf, -np.inf, 0.0, 1e300, -1e300, 5e-324]])
+    w0 = np.zeros_like(y0)
+    for arith in (ort.STRICT, ort.FAST):
+        yo, wo, co = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=True)
+        y, w, c = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=True, arith=arith)
+        assert np.array_equal(c, co), np.flatnonzero(c != co)
+        assert n_bits_differ(y, yo) == 0 and n_bits_differ(w, wo) == 0
+    assert set(np.unique(co)) == {0, 42}
+    # (2) apertures of every magnitude and kind, rays of every magnitude, real zoom rows
+    S = ort.prescriptions.zoom20()
+    tau, phi, n = orc.lens(S)
+    N = 60_000
+    for trial, amag in enumerate((1e-9, 1e-7, 2.2e-7, 1e-3, 1.0, 25.0, 1e6, 1e30)):
+        a = amag * rng.uniform(0.5, 2.0, len(tau))
+        a[rng.integers(0, len(a), 4)] = [np.inf, np.nan, 0.0, -1.0][trial % 4]
+        y0 = amag * rng.uniform(-3, 3, N)
+        w0 = amag * rng.uniform(-0.05, 0.05, N)
+        yo, wo, co = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=True)
+        y, w, c = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=True, arith=ort.STRICT)
+        assert np.array_equal(c, co), (amag, int((c != co).sum()))
+        assert n_bits_differ(y, yo) == 0 and n_bits_differ(w, wo) == 0
+        cf = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=True, arith=ort.FAST)[2]
+        assert (cf == co).mean() > 0.9995                     # FMA rounding may move a ray across the 1e-13 edge
+    # (3) rays aimed at an aperture edge of a real row: bisect y0 so that |y_row| lands within an ulp of a[row]
+    a = np.full(len(tau), 1e9)
+    row = 17
+    a[row] = 12.5
+    lo, hi = np.full(64, 0.0), np.full(64, 60.0)
+    w0 = rng.uniform(-0.02, 0.02, 64)
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        # height at `row` from the oracle's table
+        hts = np.array([abs(orc.paraxial_trace(tau, phi, m, ww)[0][row + 1, 0]) for m, ww in zip(mid, w0)])
+        big = hts - a[row] > 1e-13                      # the reference's own test (:135)
+        hi = np.where(big, mid, hi); lo = np.where(big, lo, mid)
+    y0 = np.concatenate([lo, hi, np.nextafter(lo, -1), np.nextafter(hi, 100)])
+    w0 = np.tile(w0, 4)
+    yo, wo, co = orc.paraxial_batch(tau, phi, y0, w0, a=a, clip=True)
+    y, w, c = ctx.paraxial_batch(tau, phi, y0, w0, a=a, clip=True, arith=ort.STRICT)
+    assert np.array_equal(c, co) and n_bits_differ(y, yo) == 0
+    assert 0 < (co == row + 1).sum() < len(co)
+
+
 def test_paraxial_clip_threshold(ctx, orc, pre, ort):
     """test/runtests.jl:252-257: the half-vignetted chief ray passes; lowered by 1e-12 it is clipped."""
     P = ort.prescriptions.COOKE
