@@ -523,6 +523,9 @@ def _main(real_stdout):
     #      (ex, ey compacted to the kept rays in push! order + mask), which moves ~21 % fewer bytes
     #      over PCIe.  The headline e2e is the compacted form (what full_trace returns). ----
     e2e_steps = max(2, min(args.steps, 5))
+    # at N > 1 every rank places its pinned buffers (and itself) on the NUMA node of its GPU: eight concurrent 1.1 GB
+    # device-to-host streams otherwise meet on one socket (tools/pcie_d2h_concurrent.py measures both placements)
+    placement = {"numa_node": ctx.device_numa()[0], "bound": ctx.bind_host_thread() if n > 1 else 0}
     h_ex, h_ey = ort.PinnedArray((nf, NN)), ort.PinnedArray((nf, NN))
     h_mask = ort.PinnedArray((nf, NN), dtype=np.uint8)
     out = dict(ex=h_ex.array, ey=h_ey.array, mask=h_mask.array)
@@ -633,7 +636,7 @@ def _main(real_stdout):
             "strong": strong, "secondary": sec,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": e2e_ms,
+                "steps": e2e_steps, "ms_per_step": e2e_ms, "host_placement": placement,
                 "api": "ort_trace3d_grid (host pointers, pinned host buffers), outputs ex, ey compacted to the kept rays "
                        "in the reference's push! order + mask + stats; per-field launches overlapped with D2H",
                 "full_grid_form": {"value": e2e["full_grid"]["value"], "ms_per_step": e2e["full_grid"]["ms_per_step"],

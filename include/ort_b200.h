@@ -145,6 +145,15 @@ const char *ort_last_error(ort_ctx *ctx);                  /* ctx may be NULL (e
 int         ort_sync(ort_ctx *ctx);
 int         ort_device_info(ort_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                             char *name, int name_len);
+/* Host placement for the PCIe copies of the host-pointer entry points (Linux).  ort_device_numa reports the NUMA node the
+ * context's GPU hangs off (-1 = unknown) and that node's CPU list ("0-31,64-95").  ort_bind_host_thread pins the CALLING
+ * thread to those CPUs and makes that node the preferred one for its future allocations, so pinned buffers allocated
+ * afterwards (ort_host_alloc, cudaHostAlloc) land next to the GPU; with one process per GPU on a two-socket host this is
+ * what keeps eight concurrent device-to-host streams off the socket interconnect.  Returns ORT_OK, or ORT_EUNSUPPORTED when
+ * the node is unknown or the process may not use those CPUs (cpuset); *bound (optional) = 1 affinity set, 2 memory policy
+ * set, 3 both. */
+int         ort_device_numa(ort_ctx *ctx, int *node, char *cpulist, int cpulist_len);
+int         ort_bind_host_thread(ort_ctx *ctx, int *bound);
 void       *ort_host_alloc(size_t bytes);                  /* pinned host memory for fast D2H/H2D */
 void        ort_host_free(void *p);
 int64_t     ort_launch_count(ort_ctx *ctx);                /* kernels launched by this context so far */

@@ -23,7 +23,7 @@ VIG_TAIL = 12
 # every symbol include/ort_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "ort_version", "ort_init", "ort_free", "ort_last_error", "ort_sync", "ort_device_info",
-    "ort_host_alloc", "ort_host_free", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
+    "ort_host_alloc", "ort_host_free", "ort_device_numa", "ort_bind_host_thread", "ort_launch_count", "ort_profile_enable", "ort_profile_read",
     "ort_set_layout", "ort_set_apertures", "ort_set_polynomials",
     "ort_trace3d_grid", "ort_trace3d_grid_dev", "ort_trace3d_rays", "ort_trace3d_rays_opl", "ort_trace3d_rays_dev", "ort_trace2d_batch", "ort_aim2d",
     "ort_paraxial_batch", "ort_paraxial_batch_dev", "ort_transfer_batch", "ort_transfer_batch_dev",
@@ -102,6 +102,8 @@ def load():
     L.ort_sync.argtypes = [C.c_void_p]
     L.ort_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.ort_device_numa.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.ort_bind_host_thread.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.ort_host_alloc.argtypes = [C.c_size_t]
     L.ort_host_alloc.restype = C.c_void_p
     L.ort_host_free.argtypes = [C.c_void_p]
@@ -337,6 +339,19 @@ class Context:
 
     def sync(self):
         self._ck(self.L.ort_sync(self.h))
+
+    def device_numa(self):
+        """(NUMA node of this context's GPU or -1, that node's CPU list)"""
+        node, buf = C.c_int(-1), C.create_string_buffer(1024)
+        self._ck(self.L.ort_device_numa(self.h, C.byref(node), buf, 1024))
+        return node.value, buf.value.decode()
+
+    def bind_host_thread(self):
+        """pin the calling thread (and its future allocations) next to this context's GPU; -> 0 if not possible, else
+        bit 0 = CPU affinity set, bit 1 = memory policy set"""
+        got = C.c_int(0)
+        rc = self.L.ort_bind_host_thread(self.h, C.byref(got))
+        return got.value if rc == ORT_OK else 0
 
     def launch_count(self):
         return int(self.L.ort_launch_count(self.h))

@@ -737,10 +737,17 @@ __global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, co
 // K5 for SIMPLE candidates: the three-body surface loop (fast_step<.., SIMPLE>), CS_RPT rays per thread, its own launch
 // bounds (no spills), plain shifted sums instead of per-thread Chan records.  One candidate per CTA pass, grid-strided
 // over the list of k_cand_classify.  4096 rays = 10.67 passes of 128 x 3 rays (3 % padding; 256 x 3 would pad 11 %).
+#ifndef CS_THREADS
 #define CS_THREADS 128
+#endif
+#ifndef CS_RPT
 #define CS_RPT 3
+#endif
+#ifndef CS_MINB
+#define CS_MINB 4
+#endif
 template <bool AIMED>
-__global__ void __launch_bounds__(CS_THREADS, 4)
+__global__ void __launch_bounds__(CS_THREADS, CS_MINB)
 k_candidates_simple(CandArgs A)
 {
     __shared__ SurfK s_surf[ORT_MAX_ROWS];

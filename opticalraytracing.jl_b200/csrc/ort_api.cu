@@ -8,7 +8,13 @@
 
 #include <new>
 
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
 #include <stdlib.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include "ort_ctx.cuh"
 
 thread_local char g_init_err[512] = "";
@@ -135,6 +141,64 @@ int ort_device_info(ort_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, c
     if (cc_major) *cc_major = ctx->cc_major;
     if (cc_minor) *cc_minor = ctx->cc_minor;
     if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", ctx->name);
+    return ORT_OK;
+}
+
+// NUMA node of the context's GPU from sysfs (cudaDeviceGetPCIBusId -> /sys/bus/pci/devices/<id>/numa_node)
+static int device_numa_node(ort_ctx* ctx, char* cpulist, int len)
+{
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) return -1;
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (cpulist && len > 0) {
+        cpulist[0] = 0;
+        if (node >= 0) {
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+            f = fopen(path, "r");
+            if (f) { if (!fgets(cpulist, len, f)) cpulist[0] = 0; fclose(f); }
+            for (char* p = cpulist; *p; p++) if (*p == '\n') *p = 0;
+        }
+    }
+    return node;
+}
+
+int ort_device_numa(ort_ctx* ctx, int* node, char* cpulist, int cpulist_len)
+{
+    if (!ctx) return ORT_EINVAL;
+    const int n = device_numa_node(ctx, cpulist, cpulist_len);
+    if (node) *node = n;
+    return ORT_OK;
+}
+
+int ort_bind_host_thread(ort_ctx* ctx, int* bound)
+{
+    if (!ctx) return ORT_EINVAL;
+    if (bound) *bound = 0;
+    char list[1024];
+    const int node = device_numa_node(ctx, list, sizeof list);
+    if (node < 0 || !list[0]) return fail(ctx, ORT_EUNSUPPORTED, "ort_bind_host_thread: NUMA node of device %d unknown", ctx->device);
+    int got = 0;
+    cpu_set_t set; CPU_ZERO(&set);
+    for (const char* p = list; *p;) {                     // "0-31,64-95"
+        char* e; long a = strtol(p, &e, 10), b = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, &set);
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',' ) break;
+    }
+    if (sched_setaffinity(0, sizeof set, &set) == 0) got |= 1;
+    if (node < 64) {                                      // MPOL_PREFERRED = 1: allocate on this node when possible
+        unsigned long mask = 1UL << node;
+        if (syscall(SYS_set_mempolicy, 1, &mask, (unsigned long)(8 * sizeof mask)) == 0) got |= 2;
+    }
+    if (bound) *bound = got;
+    if (!got) return fail(ctx, ORT_EUNSUPPORTED, "ort_bind_host_thread: node %d (cpus %s) is outside this process's cpuset", node, list);
     return ORT_OK;
 }
 
