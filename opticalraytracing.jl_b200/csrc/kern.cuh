@@ -144,8 +144,8 @@ struct TransferArgs {
 #define ORT_SE_RPT 2                        // rays per thread of the SIMPLE x EXT instantiations (OPD sweeps over simple prescriptions)
 #endif
 #ifndef ORT_BPSE
-#define ORT_BPSE 2                          // ... and their resident CTAs/SM
-#endif
+#define ORT_BPSE 3                          // ... and their resident CTAs/SM (80 registers, ~190 B of spills: 0.530 ms per 16.8 M-ray OPD field
+#endif                                      //     against 0.541 at 2 x 127 registers and 0.595 at 3 rays per thread)
 #ifndef ORT_GRID_WAVES_DEFAULT
 #define ORT_GRID_WAVES_DEFAULT 8            // CTA waves per grid sweep (grid_dims in ort_api.cu)
 #endif

@@ -736,15 +736,17 @@ __global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, co
 
 // K5 for SIMPLE candidates: the three-body surface loop (fast_step<.., SIMPLE>), CS_RPT rays per thread, its own launch
 // bounds (no spills), plain shifted sums instead of per-thread Chan records.  One candidate per CTA pass, grid-strided
-// over the list of k_cand_classify.  4096 rays = 10.67 passes of 128 x 3 rays (3 % padding; 256 x 3 would pad 11 %).
+// over the list of k_cand_classify.  Measured on 65 536 triplets x 4096 rays (tools/bench_cand.py): 64 threads x 2 rays x
+// 12 CTAs/SM 5.38 ms, 128 x 2 x 6 5.42, 128 x 2 x 5 (no spills) 5.53, 64 x 3 x 8 5.54, 128 x 3 x 4 5.60 (4096 rays are
+// 10.67 passes of 384: 3 % padding), 256 x 2 x 3 5.57, 128 x 4 x 3 5.66; the mixed kernel of round 1: 5.95.
 #ifndef CS_THREADS
-#define CS_THREADS 128
+#define CS_THREADS 64
 #endif
 #ifndef CS_RPT
-#define CS_RPT 3
+#define CS_RPT 2
 #endif
 #ifndef CS_MINB
-#define CS_MINB 4
+#define CS_MINB 12
 #endif
 template <bool AIMED>
 __global__ void __launch_bounds__(CS_THREADS, CS_MINB)
