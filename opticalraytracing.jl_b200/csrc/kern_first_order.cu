@@ -734,20 +734,31 @@ __device__ __noinline__ double cand_height(const CandView& V, int upto, int asph
     return y;
 }
 
-__global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ AimCandArgs A)
+// The prelude of one candidate is a chain of serial root finds, so the kernel is latency-bound (0.21 ms for 8192 candidates,
+// 0.30 ms for 65 536): the two independent links of the chain run side by side in the two warps of a CTA -- warp 0 aims the
+// chief ray (secant + the final reversed trace), warp 1 the marginal ray; after one exchange through shared memory warp 0
+// polishes the upper edge ray, warp 1 the lower one.  Lane i of both warps works on candidate 32 blockIdx.x + i; every
+// quantity is computed by exactly one thread with the operations it always had, so the records are bit-identical to
+// the one-thread-per-candidate form.
+#define AIM_CPB 32                                       // candidates per CTA
+__global__ void __launch_bounds__(2 * AIM_CPB) k_aim_candidates(const __grid_constant__ AimCandArgs A)
 {
-    const long long c = (long long)blockIdx.x * 64 + threadIdx.x;
-    if (c >= A.C) return;
+    __shared__ double s_x[3][AIM_CPB];                   // Ubar, EP_t (warp 0) | y_m (warp 1)
+    __shared__ double s_e2[AIM_CPB];
+    __shared__ int s_st[2][AIM_CPB];
+    const int lane = threadIdx.x & (AIM_CPB - 1), role = threadIdx.x / AIM_CPB;
+    const long long craw = (long long)blockIdx.x * AIM_CPB + lane;
+    const bool live = craw < A.C;
+    const long long c = live ? craw : A.C - 1;           // idle lanes shadow the last candidate (no stores)
     const int rows = A.rows, k = rows - 1;
     CandView V;
     V.R = A.RtnK + (A.n_fields > 0 ? 0 : (size_t)c * 4 * rows);       // fields of one system share its prescription
     V.t = V.R + rows; V.n = V.t + rows; V.K = V.n + rows; V.rows = rows; V.bfd = 0.0;
     const double Hrel = A.n_fields > 0 ? A.Hs[c] : A.H;
     double* out = A.out + (size_t)c * ORT_AIM_NOUT;
-    for (int j = 0; j < ORT_AIM_NOUT; j++) out[j] = CUDART_NAN;
     const double tl = V.t[rows - 1];
-    if (!(tl == 0.0 || !isfinite(tl))) { out[11] = 8.0; return; }     // Lens() would keep the last row
-    // ---- first-order solve: both fundamental rays (:209, :252), stop = argmin a ./ y (:215-216)
+    const bool lastrow_ok = (tl == 0.0 || !isfinite(tl));             // else Lens() would keep the last row
+    // ---- first-order solve: both fundamental rays (:209, :252), stop = argmin a ./ y (:215-216)  [both warps]
     const FirstOrder fo = first_order(V.R, V.t, V.n, k, A.a);
     const double y1 = fo.y1, w1 = fo.w1, w2 = fo.w2, s = fo.s, ys1 = fo.ys1, ys2 = fo.ys2, yfirst = fo.yfirst, zsum = fo.zsum;
     const int stop = fo.stop;
@@ -758,18 +769,18 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
     const double nub = SD(SM(-numk, A.h_prime), SM(yfirst, s));       // :256
     const double nuck = SM(nub, SS(w2, SD(SM(numk, ys2), SM(ys1, s))));   // chief nu after the last surface :258
     V.bfd = bfd;
-    const double a_stop_signed = A.a[stop - 1];
+    const int stop_c = stop < 1 ? 1 : (stop > k ? k : stop);          // a degenerate solve must not index outside the prescription
+    const double a_stop_signed = A.a[stop_c - 1];
     const double a_stop = fabs(a_stop_signed);
     const double tol = 1.4901161193847656e-08;
     int status = 0;
-    // ---- real chief ray, backwards (:265-296)
-    const double ybp = A.h_prime;
-    double ubp = -SD(nuck, nlast);
-    const int rstop = rows - stop;
     bool fin = true;
-    if (secant_reference([&](double uu) { return cand_height<true>(V, rstop, 1, ybp, uu); }, ubp, 0.0, tol, &fin) < 0 || !fin) status |= 1;
-    double EP_t, Ubar;
-    {
+    if (role == 0) {
+        // ---- real chief ray, backwards (:265-296)
+        const double ybp = A.h_prime;
+        double ubp = -SD(nuck, nlast);
+        const int rstop = rows - stop_c;
+        if (secant_reference([&](double uu) { return cand_height<true>(V, rstop, 1, ybp, uu); }, ubp, 0.0, tol, &fin) < 0 || !fin) status |= 1;
         double y = ybp, U = ubp, sprev = 0.0, csum = 0.0; unsigned fl = 0;
         for (int j = 0; j < k; j++) {
             const Surf2 S = cand_surf<true>(V, j);
@@ -778,23 +789,36 @@ __global__ void __launch_bounds__(64) k_aim_candidates(const __grid_constant__ A
         }
         const double ts_last = SS(V.t[0], sprev);
         const double z1 = SS(SA(csum, ts_last), csum);                 // z[2] = ray.z[end] - ray.z[end-1]  :292
-        Ubar = -U;                                                     // u_bar[1] = -ray.u[end]  :289
-        EP_t = SA(SD(-y, tan(Ubar)), z1);                              // :293
+        const double Ubar = -U;                                        // u_bar[1] = -ray.u[end]  :289
+        s_x[0][lane] = Ubar;
+        s_x[1][lane] = SA(SD(-y, tan(Ubar)), z1);                      // EP_t  :293
+    } else {
+        // ---- real marginal ray (:223-240)
+        double ym = SM(1.0, s);
+        if (secant_reference([&](double yy) { return cand_height<false>(V, stop_c, A.aspheric, yy, 0.0); }, ym, a_stop_signed, tol, &fin) < 0 || !fin) status |= 2;
+        s_x[2][lane] = ym;
     }
-    // ---- real marginal ray (:223-240)
-    double ym = SM(1.0, s);
-    if (secant_reference([&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, 0.0); }, ym, a_stop_signed, tol, &fin) < 0 || !fin) status |= 2;
+    s_st[role][lane] = status;
+    __syncthreads();
+    const double Ubar = s_x[0][lane], EP_t = s_x[1][lane], ym = s_x[2][lane];
     const double y_EP = fabs(ym);
-    // ---- field point and edge rays (src/PupilSampling.jl:92-100)
+    // ---- field point and edge rays (src/PupilSampling.jl:92-100): warp 0 the upper one, warp 1 the lower one
     const double U = SM(fabs(Hrel), Ubar);
     const double u = tan(U);
-    double e1 = SS(y_EP, SM(u, EP_t)), e2 = SS(-y_EP, SM(u, EP_t));
-    auto edge = [&](double yy) { return cand_height<false>(V, stop, A.aspheric, yy, U); };
-    if (secant_polish(edge, e1, a_stop, a_stop) < 0) status |= 4;
-    if (secant_polish(edge, e2, -a_stop, a_stop) < 0) status |= 4;
-    out[0] = e1; out[1] = e2; out[2] = y_EP; out[3] = u; out[4] = SM(u, f); out[5] = bfd;
-    out[6] = (double)stop; out[7] = a_stop; out[8] = EP_t; out[9] = Ubar; out[10] = f; out[11] = (double)status;
-    out[12] = numk; out[13] = U; out[14] = 0.0; out[15] = 0.0;     // 14..23: k_aim_edges
+    double e = role == 0 ? SS(y_EP, SM(u, EP_t)) : SS(-y_EP, SM(u, EP_t));
+    auto edge = [&](double yy) { return cand_height<false>(V, stop_c, A.aspheric, yy, U); };
+    int st2 = 0;
+    if (secant_polish(edge, e, role == 0 ? a_stop : -a_stop, a_stop) < 0) st2 = 4;
+    if (role == 1) { s_e2[lane] = e; s_st[1][lane] |= st2; }
+    __syncthreads();
+    if (role == 0 && live) {
+        status = s_st[0][lane] | s_st[1][lane] | st2;
+        for (int j = 0; j < ORT_AIM_NOUT; j++) out[j] = CUDART_NAN;
+        if (!lastrow_ok) { out[11] = 8.0; return; }
+        out[0] = e; out[1] = s_e2[lane]; out[2] = y_EP; out[3] = u; out[4] = SM(u, f); out[5] = bfd;
+        out[6] = (double)stop; out[7] = a_stop; out[8] = EP_t; out[9] = Ubar; out[10] = f; out[11] = (double)status;
+        out[12] = numk; out[13] = U; out[14] = 0.0; out[15] = 0.0;     // 14..23: k_aim_edges
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -893,7 +917,7 @@ cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st)
 cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st)
 {
     if (A.C == 0) return cudaSuccess;
-    k_aim_candidates<<<(unsigned)((A.C + 63) / 64), 64, 0, st>>>(A);
+    k_aim_candidates<<<(unsigned)((A.C + AIM_CPB - 1) / AIM_CPB), 2 * AIM_CPB, 0, st>>>(A);
     return cudaGetLastError();
 }
 
