@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libort_oracle.so")
+_SO = os.environ.get("ORT_ORACLE_LIB", os.path.join(_HERE, "libort_oracle.so"))      # the sanitizer build sets it
 
 F_MISS, F_TIR, F_DOMAIN, F_CLIP, F_VIGN = 1, 2, 4, 8, 16
 
