@@ -217,13 +217,13 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         clip = r2 > A.a_stop2;
     }
     const bool sv = (ARITH == ORT_ARITH_STRICT) || amb < 0;
-    if (sv) {                                       // rare in FAST mode: recompute the ray's inputs here
-        const unsigned iy = idx / (unsigned)A.nx, ix = idx - iy * (unsigned)A.nx;
-        const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
-        double u, v; field_slopes(fld, y0, x0, u, v);
-        h = (ARITH == ORT_ARITH_STRICT)
-                ? trace_strict<EXT, decltype(P.s), EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette, P.poly, P.npoly)
-                : trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
+    if (sv) {
+        if (ARITH != ORT_ARITH_STRICT) {            // rare in FAST mode: recompute the ray's inputs here and re-trace it
+            const unsigned iy = idx / (unsigned)A.nx, ix = idx - iy * (unsigned)A.nx;
+            const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
+            double u, v; field_slopes(fld, y0, x0, u, v);
+            h = trace_strict_cold<EXT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette);
+        }                                           // STRICT: h is the reference-arithmetic trace already (k_grid)
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
         r2 = ri * ri;
@@ -364,6 +364,28 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         if (ARITH == ORT_ARITH_FAST)
             trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
                                                         collimated ? K0 : nullptr);
+        else {      // STRICT: the thread's RPT rays advance surface by surface together (independent chains of the slow ops: / and sqrt)
+            RayS r[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                strict_init(r[j], y0[j], x0[j], u[j], v[j]);
+                if (EXT) r[j].opl = strict_opl_start(r[j], fld.mode, P.n0, y0[j], x0[j], fld.z0);
+                h[j].xs = h[j].ys = CUDART_NAN; h[j].opl = 0.0;
+            }
+            const int nsurf = P.nsurf, stop = A.stop;
+            for (int i = 0; i < nsurf; i++) {
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    strict_step<EXT, EXT>(P.s[i], r[j], vignette, (EXT && P.poly) ? P.poly + (size_t)i * P.npoly : nullptr, P.npoly);
+                    if (i == stop - 1) { h[j].xs = r[j].x; h[j].ys = r[j].y; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                h[j].xf = r[j].x; h[j].yf = r[j].y; h[j].flags = r[j].flags;
+                if (EXT) h[j].opl = strict_opl_close(r[j], fld, P.nlast);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
@@ -934,7 +956,7 @@ int grid_variant(const Presc& P, int arith, int ext)
 
 int grid_rays_per_thread(int arith, int variant)
 {
-    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : (variant == 3 ? ORT_SE_RPT : ORT_FAST_RPT)) : 1;
+    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : (variant == 3 ? ORT_SE_RPT : ORT_FAST_RPT)) : ORT_STRICT_RPT;
 }
 
 int grid_blocks_per_sm(int arith, int variant)
@@ -949,8 +971,8 @@ int grid_blocks_per_sm(int arith, int variant)
         e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1>, ORT_TILE, 0)
                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0>, ORT_TILE, 0);
     else
-        e = (variant & 1) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, 1>, ORT_TILE, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, 1, 0>, ORT_TILE, 0);
+        e = (variant & 1) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 1>, ORT_TILE, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 0>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
@@ -982,8 +1004,8 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
         else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
     } else {
-        if (ext) k_grid<ORT_ARITH_STRICT, 1, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else k_grid<ORT_ARITH_STRICT, 1, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
+        if (ext) k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
     }
     return cudaGetLastError();
 }
