@@ -140,6 +140,12 @@ struct TransferArgs {
 #ifndef ORT_BPSP
 #define ORT_BPSP 2                          // ... and its resident CTAs/SM (128 registers, no spills)
 #endif
+#ifndef ORT_SC_RPT
+#define ORT_SC_RPT 2                        // rays per thread of the SIMPLE-conic instantiations (Presc::simple == 2)
+#endif
+#ifndef ORT_BPSC
+#define ORT_BPSC 3                          // ... and their resident CTAs/SM
+#endif
 #ifndef ORT_STRICT_RPT
 #define ORT_STRICT_RPT 1                    // rays per thread of k_grid<STRICT>: 13.4 ms per bench step at 1 x 3 CTAs/SM (80 registers);
 #endif                                      // 2 x 3 (spills) 13.5, 2 x 2 (108 registers) 15.3, 3 x 2 15.5 -- the IEEE / and sqrt sequences keep

@@ -85,7 +85,7 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
 // (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
 // (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
-template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, bool SIMPLE = false>
+template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, int SIMPLE = 0>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
@@ -285,8 +285,8 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
 // thread through the three-body fast_step<.., SIMPLE>, ORT_BPSP resident CTAs/SM.
 // EXTK: 0 = the reference's outputs only; 1 = extensions (OPD and / or per-surface apertures, chosen at run time; polynomial
 // terms in STRICT); 2 = OPD only (no aperture test compiled in: the instantiation of OPD sweeps over SIMPLE prescriptions).
-template <int ARITH, int RPT, int EXTK, int LEAN = 0, bool MIRROR = true, bool SIMPLE = false>
-__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (SIMPLE ? (EXTK ? ORT_BPSE : ORT_BPSP) : (RPT == 1 ? ORT_BPS1 : (EXTK ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
+template <int ARITH, int RPT, int EXTK, int LEAN = 0, bool MIRROR = true, int SIMPLE = 0>
+__global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? (SIMPLE == 2 ? ORT_BPSC : SIMPLE ? (EXTK ? ORT_BPSE : ORT_BPSP) : (RPT == 1 ? ORT_BPS1 : (EXTK ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
 k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
 {
     constexpr bool EXT = EXTK != 0;
@@ -311,7 +311,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         double u, v; field_slopes(fld, y0, x0, u, v);
         Hit h; int amb = 0;
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<1, EXT, decltype(P.s), !SIMPLE, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
+            trace_fast<1, EXT, decltype(P.s), SIMPLE == 0, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette);
         if (ARITH == ORT_ARITH_STRICT || amb < 0)
             h = trace_strict_cold<EXT, decltype(P.s), EXT && ARITH == ORT_ARITH_STRICT>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0,
                                                                                        P.nlast, vignette, P.poly, P.npoly);
@@ -945,18 +945,19 @@ cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* 
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from ort_api.cu)
 // ------------------------------------------------------------------------------------------
-// kernel variant of a FAST sweep: 0 general, 1 EXT (OPD / apertures / polynomial terms), 2 SIMPLE, 3 SIMPLE x EXT;
-// STRICT has 0 and 1
+// kernel variant of a FAST sweep: 0 general, 1 EXT (OPD / apertures / polynomial terms), 2 SIMPLE, 3 SIMPLE x EXT,
+// 4 SIMPLE-conic (Presc::simple == 2); STRICT has 0 and 1
 int grid_variant(const Presc& P, int arith, int ext)
 {
-    const bool simple = arith == ORT_ARITH_FAST && P.simple && !P.has_mirror;
+    const bool simple = arith == ORT_ARITH_FAST && P.simple == 1 && !P.has_mirror;
     if (ext || P.poly) return (simple && !P.poly) ? 3 : 1;
+    if (arith == ORT_ARITH_FAST && P.simple == 2 && !P.has_mirror) return 4;
     return simple ? 2 : 0;
 }
 
 int grid_rays_per_thread(int arith, int variant)
 {
-    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : (variant == 3 ? ORT_SE_RPT : ORT_FAST_RPT)) : ORT_STRICT_RPT;
+    return arith == ORT_ARITH_FAST ? (variant == 2 ? ORT_SIMPLE_RPT : (variant == 3 ? ORT_SE_RPT : (variant == 4 ? ORT_SC_RPT : ORT_FAST_RPT))) : ORT_STRICT_RPT;
 }
 
 int grid_blocks_per_sm(int arith, int variant)
@@ -967,6 +968,8 @@ int grid_blocks_per_sm(int arith, int variant)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true>, ORT_TILE, 0);
     else if (arith == ORT_ARITH_FAST && variant == 3)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true>, ORT_TILE, 0);
+    else if (arith == ORT_ARITH_FAST && variant == 4)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 1, false, 2>, ORT_TILE, 0);
     else if (arith == ORT_ARITH_FAST)
         e = variant ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1>, ORT_TILE, 0)
                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0>, ORT_TILE, 0);
@@ -992,6 +995,9 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         else if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (variant == 3 && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (variant == 3) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 4 && lean) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 1, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 4 && stats_only) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 2, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (variant == 4) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 0, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
         else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);

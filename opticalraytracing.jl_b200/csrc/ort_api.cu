@@ -96,7 +96,7 @@ int ort_init(ort_ctx** out, int device)
     for (int i = 0; i < ORT_MAX_FIELDS; i++) CKI(cudaEventCreateWithFlags(&ctx->ev_field[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) { CKI(cudaEventCreate(&ctx->prof_ev[i][0])); CKI(cudaEventCreate(&ctx->prof_ev[i][1])); }
 #undef CKI
-    for (int v = 0; v < 4; v++) {
+    for (int v = 0; v < 5; v++) {
         ctx->bps[ORT_ARITH_STRICT][v] = grid_blocks_per_sm(ORT_ARITH_STRICT, v);
         ctx->bps[ORT_ARITH_FAST][v] = grid_blocks_per_sm(ORT_ARITH_FAST, v);
     }
@@ -257,10 +257,18 @@ int ort_set_layout(ort_ctx* ctx, int rows, const double* R, const double* t, con
             P.fast_ok = 0;
         if (!(n[i] > 0.0) || !(n[i + 1] > 0.0)) P.has_mirror = 1;      // reflection (n2 = -n1) or anything unusual
     }
+    // class of the prescription (ort_internal.cuh): 1 = refracting spheres (|R| <= 64 L) and planes; 2 = refracting conics /
+    // spheres and planes with at least one conic; 0 = anything else (mirrors, dummy curved surfaces, weak spheres without conics)
     const double L = gap_scale(t, rows);
     P.simple = P.fast_ok && !P.has_mirror;
-    for (int i = 0; i + 1 < rows; i++)
+    bool conic_class = P.simple, any_conic = false;
+    for (int i = 0; i + 1 < rows; i++) {
+        const bool plane = (P.s[i].kcode & SURF_KIND_MASK) == SURF_PLANE;
+        if (!plane && !(P.s[i].kcode & SURF_REFR)) conic_class = false;               // dummy curved surface
+        if ((P.s[i].kcode & SURF_KIND_MASK) == SURF_CONIC) any_conic = true;
         if (!simple_surface(P.s[i], L)) P.simple = 0;
+    }
+    if (!P.simple && conic_class && any_conic) P.simple = 2;
     ctx->rows = rows;
     ctx->have_layout = true;
     ctx->fast_ok_layout = P.fast_ok;

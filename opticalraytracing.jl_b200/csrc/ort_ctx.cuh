@@ -28,7 +28,7 @@ struct ort_ctx {
     int rows;
     bool have_layout;
     int fast_ok_layout;         // fast_ok as derived from R, t, n, K alone (polynomial terms force it to 0 while set)
-    int bps[2][4];              // resident CTAs/SM of k_grid<STRICT|FAST, variant general|EXT|SIMPLE|SIMPLE x EXT> (grid_variant)
+    int bps[2][5];              // resident CTAs/SM of k_grid<STRICT|FAST, variant general|EXT|SIMPLE|SIMPLE x EXT|SIMPLE-conic> (grid_variant)
     void* slot[SL_COUNT];
     size_t slot_bytes[SL_COUNT];
     // The scratch slots are shared by every entry point of the context.  Work that uses them is ordered across streams

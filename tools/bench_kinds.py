@@ -23,8 +23,8 @@ P = ort.prescriptions.DOUBLE_GAUSS
 s = ort.solve(P["surfaces"], P["a"], P["h"])
 p = ort.host._full_trace_setup(s.layout, s, (0.7,), 64, None, ctx)
 dev = torch.device("cuda", 0)
-xs = torch.from_numpy(np.linspace(0.0, p["y_EP"], NX)).to(dev)
-ys = torch.from_numpy(np.linspace(p["y1"][0], p["y2"][0], NY)).to(dev)
+xs = torch.from_numpy(ort.host.jl_range(0.0, p["y_EP"], NX)).to(dev)
+ys = torch.from_numpy(ort.host.jl_range(p["y1"][0], p["y2"][0], NY)).to(dev)
 b = {k: torch.empty(NY * NX, dtype=torch.float64, device=dev) for k in ("ex", "ey")}
 b["mask"] = torch.empty(NY * NX, dtype=torch.uint8, device=dev)
 st = torch.zeros(ort.STATS_BYTES, dtype=torch.uint8, device=dev)
