@@ -1,6 +1,6 @@
 """Turn the raw captures a gpurun call left in gpurun_out/ into the tracked summaries under profiles/.
-usage: python tools/refresh_profiles.py <tag>      (reads gpurun_out/prof_grid_<tag>.ncu-rep, launches_<tag>.csv,
-bench_<tag>.json, extra_<tag>.json; writes profiles/r01_*)"""
+usage: python tools/refresh_profiles.py <tag> [round = r02]      (reads gpurun_out/prof_grid_<tag>.ncu-rep, launches_<tag>.csv,
+bench_<tag>.json, bench_ref_<tag>.json; writes profiles/<round>_*)"""
 import collections
 import csv
 import json
@@ -32,6 +32,7 @@ def num(x):
 
 def main():
     tag = sys.argv[1]
+    rnd = sys.argv[2] if len(sys.argv) > 2 else "r02"
     go, pr = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
     rep = os.path.join(go, f"prof_grid_{tag}.ncu-rep")
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -59,17 +60,17 @@ def main():
     tot = sum(mix.values())
     fp64 = sum(mix[k] for k in ("DFMA", "DMUL", "DADD", "DSETP"))
     per = RAYS / 32
-    summ["_how"] = ("ncu --set full --clock-control none --import-source on -k regex:^k_grid$ -s 3 -c 1 python bench.py "
-                    "--steps 3 --warmup 3 --no-cpu-baseline (after the same command exited 0 without ncu)")
+    summ["_how"] = ("ncu --set full --clock-control none --import-source on -k regex:k_grid -s 3 -c 1 python bench.py "
+                    "--steps 3 --warmup 3 --no-cpu-baseline --no-extras (after the same command exited 0 without ncu)")
     summ["_derived"] = {"rays_per_launch": RAYS, "warp_instructions_per_32_rays": tot / per,
                         "fp64_pipe_instructions_per_ray": fp64 / per, "other_instructions_per_ray": (tot - fp64) / per,
                         "issue_slot_model_cycles_per_32_rays": (2 * fp64 + (tot - fp64)) / per / 0.9,
                         "measured_cycles_per_32_rays": num(d['sm__cycles_elapsed.avg']) / (per / (148 * 4)),
                         "algorithmic_bytes_per_launch": RAYS * 17, "dram_bytes_per_launch": dram,
                         "instruction_mix_per_ray": {k: round(v / per, 2) for k, v in mix.most_common(16)}}
-    json.dump(summ, open(os.path.join(pr, f"r01_k_grid_fast_{tag}_ncu_summary.json"), "w"), indent=1)
+    json.dump(summ, open(os.path.join(pr, f"{rnd}_k_grid_fast_{tag}_ncu_summary.json"), "w"), indent=1)
     json.dump({"kernel": d['Kernel Name'], "dram_bytes_per_launch": dram,
-               "source": f"profiles/r01_k_grid_fast_{tag}_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, "
+               "source": f"profiles/{rnd}_k_grid_fast_{tag}_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, "
                          "one ncu --set full capture)"}, open(os.path.join(pr, "k_grid_traffic.json"), "w"), indent=1)
     # launch list
     lrows = [r for r in csv.reader(open(os.path.join(go, f"launches_{tag}.csv"))) if len(r) > 10]
@@ -79,28 +80,27 @@ def main():
     for r in lrows[1:]:
         agg.setdefault(r[ki], []).append(num(r[vi]))
     total = sum(sum(v) for v in agg.values())
-    with open(os.path.join(pr, f"r01_launches_{tag}_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 120 python bench.py --steps 3 --warmup 3 "
-                "--no-cpu-baseline\n# (cold-cache, serialised: compare shares).  Prelude (k_paraxial, k_aim2d, k_trace2d), "
+    with open(os.path.join(pr, f"{rnd}_launches_{tag}_summary.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 160 python bench.py --steps 3 --warmup 3 "
+                "--no-cpu-baseline --no-extras\n# (cold-cache, serialised: compare shares).  Prelude (k_paraxial, k_aim2d, k_trace2d), "
                 "device steps (one 5-field k_grid launch + k_grid_finalize each),\n# e2e steps (per-field k_grid + finalize "
                 "[+ k_tile_scan + k_chunk_scan + k_compact]).  Inside a timed step the launches are\n# k_grid + "
                 "k_grid_finalize: k_grid's share of the step = 99.8 %.\n")
         for k, v in agg.items():
             f.write(f"{k[:70]:72s} n={len(v):3d} total={sum(v) / 1e6:9.3f} ms share={100 * sum(v) / total:6.2f}% "
                     f"mean={sum(v) / len(v) / 1e3:9.1f} us\n")
-    shutil.copy(os.path.join(go, f"launches_{tag}.csv"), os.path.join(pr, f"r01_launches_{tag}.csv"))
-    for src_name, dst in ((f"bench_{tag}.json", "r01_bench_1gpu.json"), (f"extra_{tag}.json", "r01_secondary_kernels_bench.json"),
-                          (f"bench_ref_{tag}.json", "r01_bench_reference_arm.json")):
+    shutil.copy(os.path.join(go, f"launches_{tag}.csv"), os.path.join(pr, f"{rnd}_launches_{tag}.csv"))
+    for src_name, dst in ((f"bench_{tag}.json", f"{rnd}_bench_1gpu.json"), (f"bench_ref_{tag}.json", f"{rnd}_bench_reference_arm.json")):
         if os.path.exists(os.path.join(go, src_name)):
             shutil.copy(os.path.join(go, src_name), os.path.join(pr, dst))
     # SASS of the dominant kernel (proof of what runs: DFMA / MUFU.RCP64H / MUFU.RSQ64H, LDCU uniform operands):
     # k_grid<FAST, 3 rays/thread, spot + mask, no-mirror, SIMPLE>
     lib = os.path.join(ROOT, "opticalraytracing.jl_b200", "lib", "libort_b200.so")
-    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_Z6k_gridILi1ELi3ELb0ELi1ELb0ELb1EEv5Presc8GridArgs', lib],
+    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_Z6k_gridILi1ELi3ELi0ELi1ELb0ELi1EEv5Presc8GridArgs', lib],
                           capture_output=True, text=True).stdout
     keep = [ln.split('/*', 2)[0].rstrip() + '  ' + ln.split('*/', 1)[1].rsplit('/*', 1)[0].rstrip() if '*/' in ln and ln.strip().startswith('/*') else ln
             for ln in sass.splitlines() if not ln.strip().startswith('/* 0x')]
-    open(os.path.join(pr, "r01_k_grid_fast_simple_rpt3.sass"), "w").write("\n".join(keep) + "\n")
+    open(os.path.join(pr, f"{rnd}_k_grid_fast_simple_rpt3.sass"), "w").write("\n".join(keep) + "\n")
     print(json.dumps(summ["_derived"], indent=1))
 
 
