@@ -82,10 +82,10 @@ def main():
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(pr, f"{rnd}_launches_{tag}_summary.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 160 python bench.py --steps 3 --warmup 3 "
-                "--no-cpu-baseline --no-extras\n# (cold-cache, serialised: compare shares).  Prelude (k_paraxial, k_aim2d, k_trace2d), "
+                "--no-cpu-baseline --no-extras\n# (cold-cache, serialised: compare shares).  Prelude (k_paraxial, k_aim_candidates, k_aim_edges), "
                 "device steps (one 5-field k_grid launch + k_grid_finalize each),\n# e2e steps (per-field k_grid + finalize "
-                "[+ k_tile_scan + k_chunk_scan + k_compact]).  Inside a timed step the launches are\n# k_grid + "
-                "k_grid_finalize: k_grid's share of the step = 99.8 %.\n")
+                "[+ k_tile_scan + k_chunk_scan + k_compact]), k_fp64_peak = the roofline denominator.  Inside a timed step the\n"
+                "# launches are k_grid + k_grid_finalize: k_grid's share of the step = 99.8 %.\n")
         for k, v in agg.items():
             f.write(f"{k[:70]:72s} n={len(v):3d} total={sum(v) / 1e6:9.3f} ms share={100 * sum(v) / total:6.2f}% "
                     f"mean={sum(v) / len(v) / 1e3:9.1f} us\n")
