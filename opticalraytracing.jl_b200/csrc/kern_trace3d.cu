@@ -201,10 +201,14 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
 // LEAN = 1: the caller wants exactly the spot diagram and the mask (ex, ey, mask -- BASELINE config 2's 17 B per
 // ray): no per-pointer null tests, 32-bit indexing off per-field base pointers.  LEAN = 2: statistics only (config 3's
 // 0 B per ray): no stores at all.  LEAN = 0: any combination of outputs.
+// LEAN == 1 stores go through lp (this ray's slots in ex, ey, mask[, opd]): the kernel derives the three pointers once per
+// tile and the rays of a thread sit at compile-time offsets from them, instead of 64-bit address arithmetic per ray and array.
+struct LeanPtrs { double *ex, *ey, *opd; uint8_t* mask; };
 template <int ARITH, int EXTK, int LEAN>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
-                                             bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc)
+                                             bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc,
+                                             const LeanPtrs& lp)
 {
     constexpr bool EXT = EXTK != 0;
     const size_t o = fbase + idx;
@@ -227,6 +231,11 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
         r2 = ri * ri;
+        if (valid) {        // miss / TIR / domain flags can only come out of a strict trace: counted here, off the fast path
+            acc.nstrict++;
+            acc.nflag_lo += (h.flags & ORT_FLAG_MISS ? 1 : 0) + (h.flags & ORT_FLAG_TIR ? 0x10000 : 0);
+            acc.nflag_hi += (h.flags & ORT_FLAG_DOMAIN ? 1 : 0);
+        }
     } else if (!LEAN && A.r) {
         ri = (r2 > 0.0) ? fast_sqrt(r2) : r2;
     }
@@ -237,19 +246,14 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     const unsigned flags = h.flags | (clip ? ORT_FLAG_CLIP : 0u);
     const int kept = valid && !drop;
     const double ex = h.xf;                                             // :135
-    const double ey = sv ? SS(h.yf, fld.h_prime) : h.yf - fld.h_prime;  // :134
+    const double ey = SS(h.yf, fld.h_prime);                            // :134  (one subtraction: nothing to contract)
     double opd = 0.0;
-    if (EXT && (A.ext & ORT_EXT_OPD)) opd = sv ? SM(SS(h.opl, fld.opl_ref), A.opd_scale) : (h.opl - fld.opl_ref) * A.opd_scale;
+    if (EXT && (A.ext & ORT_EXT_OPD)) opd = SM(SS(h.opl, fld.opl_ref), A.opd_scale);
     if (LEAN) {
         if (valid) {
-            if (LEAN == 1) { (A.ex + fbase)[idx] = ex; (A.ey + fbase)[idx] = ey; (A.mask + fbase)[idx] = (uint8_t)kept; }
-            if (LEAN == 1 && EXT) (A.opd + fbase)[idx] = opd;       // the OPD sweep's output set: ex, ey, opd, mask
+            if (LEAN == 1) { *lp.ex = ex; *lp.ey = ey; *lp.mask = (uint8_t)kept; }
+            if (LEAN == 1 && EXT) *lp.opd = opd;                    // the OPD sweep's output set: ex, ey, opd, mask
             if (EXTK == 1) acc.nvig += vig ? 1 : 0;
-            if (sv) {
-                acc.nstrict++;
-                acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
-                acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0);
-            }
             acc.nflag_hi += clip ? 0x10000 : 0;
         }
     } else if (valid) {
@@ -262,11 +266,6 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
         if (EXT && A.opd) A.opd[o] = opd;
         if (A.mask) A.mask[o] = (uint8_t)kept;
         if (A.flags) A.flags[o] = (uint8_t)flags;
-        if (sv) {           // miss / TIR / domain flags can only come out of a strict trace
-            acc.nstrict++;
-            acc.nflag_lo += (flags & ORT_FLAG_MISS ? 1 : 0) + (flags & ORT_FLAG_TIR ? 0x10000 : 0);
-            acc.nflag_hi += (flags & ORT_FLAG_DOMAIN ? 1 : 0);
-        }
         acc.nflag_hi += clip ? 0x10000 : 0;
         if (EXT) acc.nvig += vig ? 1 : 0;
     }
@@ -386,13 +385,24 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
                 if (EXT) h[j].opl = strict_opl_close(r[j], fld, P.nlast);
             }
         }
+        int keptj[RPT];
+        LeanPtrs lp0 = {nullptr, nullptr, nullptr, nullptr};
+        if (LEAN == 1) {                        // valid rays of this thread: element e0 + j * ORT_TILE of the field's arrays
+            const size_t e0 = fbase + (size_t)tile * (RPT * ORT_TILE) + threadIdx.x;
+            lp0.ex = A.ex + e0; lp0.ey = A.ey + e0; lp0.mask = A.mask + e0;
+            if (EXT) lp0.opd = A.opd + e0;
+        }
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
-            const int kept = grid_epilogue<ARITH, EXTK, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
-                                                             fbase, cx, cy, co, acc);
-            if (A.tile_counts) {
-                const int c = __syncthreads_count(kept);
+            const LeanPtrs lp = {lp0.ex + j * ORT_TILE, lp0.ey + j * ORT_TILE, EXT ? lp0.opd + j * ORT_TILE : nullptr, lp0.mask + j * ORT_TILE};
+            keptj[j] = grid_epilogue<ARITH, EXTK, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
+                                                        fbase, cx, cy, co, acc, lp);
+        }
+        if (LEAN != 2 && A.tile_counts) {       // ordered compaction requested: kept rays per 256-ray sub-tile (one uniform test per tile)
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const int c = __syncthreads_count(keptj[j]);
                 const unsigned sub = tile * RPT + j;
                 if (threadIdx.x == 0 && sub < nsub) A.tile_counts[(size_t)f * nsub + sub] = c;
             }
