@@ -85,12 +85,15 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // RPT rays through the whole prescription in FAST arithmetic.  Two loops split at the stop surface
 // (no per-step select for the stop capture).  amb[j] < 0 on return: ray j needs the strict re-trace
 // (guard band hit, or a miss / TIR / non-finite value turned its position into NaN).
-template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, int SIMPLE = 0>
+// R2ONLY: the caller only needs r^2 of the stop position (lean output sets): h.xs carries it, h.ys is unused -- three
+// doubles instead of six live across the second surface loop.  KZCHECK = false: the prescription ends with a plain plane, so
+// a non-finite Kz has already reached x, y (s = (t - z) / Kz) and needs no test of its own.
+template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, int SIMPLE = 0, bool R2ONLY = false>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
                                            const ort_field* fld = nullptr, double nlast = 1.0, bool vignette = false,
-                                           const double* K0 = nullptr)
+                                           const double* K0 = nullptr, bool kzcheck = true)
 {
     RaysF<RPT> r;
 #pragma unroll
@@ -107,13 +110,17 @@ __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int st
     int i = 0;
     for (; i < stop; i++) fast_step<RPT, EXT, MIRROR, SIMPLE>(S[i], r, vignette);
 #pragma unroll
-    for (int j = 0; j < RPT; j++) { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
+    for (int j = 0; j < RPT; j++) {
+        if (R2ONLY) { h[j].xs = fma(r.x[j], r.x[j], r.y[j] * r.y[j]); h[j].ys = 0.0; }
+        else { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
+    }
     for (; i < nsurf; i++) fast_step<RPT, EXT, MIRROR, SIMPLE>(S[i], r, vignette);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         h[j].xf = r.x[j]; h[j].yf = r.y[j];
         h[j].flags = (EXT && r.vig[j]) ? ORT_FLAG_VIGN : 0u;
-        amb[j] = r.amb[j] | nonfinite_bit(r.x[j]) | nonfinite_bit(r.y[j]) | nonfinite_bit(r.Kz[j]);
+        amb[j] = r.amb[j] | nonfinite_bit(r.x[j]) | nonfinite_bit(r.y[j]);
+        if (kzcheck) amb[j] |= nonfinite_bit(r.Kz[j]);
         h[j].opl = 0.0;
         if (EXT) {          // reference sphere in optical cosines: n tau = -q.K - sgn(rr) sgn(n) sqrt((q.K)^2 - n^2 (|q|^2 - rr^2))
             double opl = r.opl[j];
@@ -204,7 +211,7 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
 // LEAN == 1 stores go through lp (this ray's slots in ex, ey, mask[, opd]): the kernel derives the three pointers once per
 // tile and the rays of a thread sit at compile-time offsets from them, instead of 64-bit address arithmetic per ray and array.
 struct LeanPtrs { double *ex, *ey, *opd; uint8_t* mask; };
-template <int ARITH, int EXTK, int LEAN>
+template <int ARITH, int EXTK, int LEAN, bool R2ONLY = false>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
                                              bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc,
@@ -216,7 +223,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
     double ri = 0.0, r2 = 0.0;
     bool clip = false;
     if (ARITH == ORT_ARITH_FAST) {
-        r2 = fma(h.xs, h.xs, h.ys * h.ys);
+        r2 = R2ONLY ? h.xs : fma(h.xs, h.xs, h.ys * h.ys);
         amb |= tiny_vs_bit(r2 - A.a_stop2, A.a_stop2);                  // within 2^-30 of the stop edge
         clip = r2 > A.a_stop2;
     }
@@ -254,7 +261,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
             if (LEAN == 1) { *lp.ex = ex; *lp.ey = ey; *lp.mask = (uint8_t)kept; }
             if (LEAN == 1 && EXT) *lp.opd = opd;                    // the OPD sweep's output set: ex, ey, opd, mask
             if (EXTK == 1) acc.nvig += vig ? 1 : 0;
-            acc.nflag_hi += clip ? 0x10000 : 0;
+            if (clip) acc.nflag_hi += 0x10000;
         }
     } else if (valid) {
         if (A.ex) A.ex[o] = ex;
@@ -323,6 +330,10 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
     }
     __syncthreads();
     const double cx = s_shift[0], cy = s_shift[1], co = s_shift[2];
+    // the lean output sets need only r^2 of the stop position; a prescription that ends with a plain plane (full_trace's image
+    // plane) needs no finiteness test on Kz
+    constexpr bool R2ONLY = ARITH == ORT_ARITH_FAST && LEAN != 0;
+    const bool kzcheck = P.s[P.nsurf - 1].kcode != SURF_PLANE;
 
     // collimated field (mode 0): K = n0 normalize([v, u, 1]) once per thread, not once per ray
     const bool collimated = (fld.mode == 0);
@@ -350,8 +361,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         for (int j = 0; j < RPT; j++) {
             const unsigned i0 = (tile * RPT + j) * ORT_TILE + threadIdx.x;
             valid[j] = i0 < NN;
-            idx[j] = valid[j] ? i0 : NN - 1;     // padded lanes re-trace the last ray: the warp stays convergent
-            const unsigned iy = valid[j] ? iyj[j] : (unsigned)A.ny - 1, ix = valid[j] ? ixj[j] : nxu - 1;   // y outer, x inner (:123)
+            idx[j] = min(i0, NN - 1);            // padded lanes trace a ray of the last row: the warp stays convergent
+            const unsigned iy = min(iyj[j], (unsigned)A.ny - 1), ix = ixj[j];       // y outer, x inner (:123); ix < nx always
             y0[j] = __ldg(A.ys + (ysoff + iy)); x0[j] = __ldg(A.xs + ix);      // 32-bit offsets: one IMAD.WIDE each
             if (collimated) { u[j] = fld.u; v[j] = fld.v; }
             else field_slopes(fld, y0[j], x0[j], u[j], v[j]);
@@ -361,8 +372,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         Hit h[RPT];
         int amb[RPT];
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
-                                                        collimated ? K0 : nullptr);
+            trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE, R2ONLY>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
+                                                                collimated ? K0 : nullptr, kzcheck);
         else {      // STRICT: the thread's RPT rays advance surface by surface together (independent chains of the slow ops: / and sqrt)
             RayS r[RPT];
 #pragma unroll
@@ -396,8 +407,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         for (int j = 0; j < RPT; j++) {
             if (ARITH != ORT_ARITH_FAST) amb[j] = 0;
             const LeanPtrs lp = {lp0.ex + j * ORT_TILE, lp0.ey + j * ORT_TILE, EXT ? lp0.opd + j * ORT_TILE : nullptr, lp0.mask + j * ORT_TILE};
-            keptj[j] = grid_epilogue<ARITH, EXTK, LEAN>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
-                                                        fbase, cx, cy, co, acc, lp);
+            keptj[j] = grid_epilogue<ARITH, EXTK, LEAN, R2ONLY>(P, A, fld, ysf, h[j], amb[j], idx[j], valid[j],
+                                                                fbase, cx, cy, co, acc, lp);
         }
         if (LEAN != 2 && A.tile_counts) {       // ordered compaction requested: kept rays per 256-ray sub-tile (one uniform test per tile)
 #pragma unroll
