@@ -364,10 +364,13 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
             idx[j] = min(i0, NN - 1);            // padded lanes trace a ray of the last row: the warp stays convergent
             const unsigned iy = min(iyj[j], (unsigned)A.ny - 1), ix = ixj[j];       // y outer, x inner (:123); ix < nx always
             y0[j] = __ldg(A.ys + (ysoff + iy)); x0[j] = __ldg(A.xs + ix);      // 32-bit offsets: one IMAD.WIDE each
-            if (collimated) { u[j] = fld.u; v[j] = fld.v; }
-            else field_slopes(fld, y0[j], x0[j], u[j], v[j]);
+            u[j] = 0.0; v[j] = 0.0;              // collimated FAST sweeps take the direction from K0 (the strict re-trace derives its own)
             ixj[j] += dr; iyj[j] += dq;
             if (ixj[j] >= nxu) { ixj[j] -= nxu; iyj[j]++; }
+        }
+        if (!collimated || ARITH != ORT_ARITH_FAST) {        // one uniform test per tile
+#pragma unroll
+            for (int j = 0; j < RPT; j++) field_slopes(fld, y0[j], x0[j], u[j], v[j]);
         }
         Hit h[RPT];
         int amb[RPT];
