@@ -863,6 +863,8 @@ k_candidates_simple(CandArgs A)
         unsigned iyj[CS_RPT], ixj[CS_RPT];
 #pragma unroll
         for (int j = 0; j < CS_RPT; j++) { const unsigned i = threadIdx.x + j * CS_THREADS; iyj[j] = i / nxu; ixj[j] = i - iyj[j] * nxu; }
+        // the candidate's grid parameters in registers for the whole sweep (an LDS in front of every trace otherwise)
+        const double g_y1 = par[0], g_y2 = par[1], g_dy = par[2], g_xe = par[3], g_dx = par[4], a_stop2 = par[6], hpc = par[8] + cy;
         for (unsigned i0 = threadIdx.x; ok && i0 < NN; i0 += step) {
             double y0[CS_RPT], x0[CS_RPT], uu[CS_RPT], vv[CS_RPT];
             bool valid[CS_RPT];
@@ -870,10 +872,10 @@ k_candidates_simple(CandArgs A)
             for (int j = 0; j < CS_RPT; j++) {
                 const unsigned i = i0 + j * CS_THREADS;
                 valid[j] = i < NN && !(AIMED && (i == 0 || i == edge_b));
-                const unsigned iy = i < NN ? iyj[j] : (unsigned)A.ny - 1, ix = i < NN ? ixj[j] : nxu - 1;
+                const unsigned iy = min(iyj[j], (unsigned)A.ny - 1), ix = ixj[j];       // idle lanes shadow a ray of the last row
                 if (AIMED) {        // range(a, b, n)[i] = a + i * step, last point exactly b
-                    y0[j] = (iy == (unsigned)A.ny - 1) ? par[1] : SA(par[0], SM((double)iy, par[2]));
-                    x0[j] = (ix == nxu - 1) ? par[3] : SM((double)ix, par[4]);
+                    y0[j] = (iy == (unsigned)A.ny - 1) ? g_y2 : SA(g_y1, SM((double)iy, g_dy));
+                    x0[j] = (ix == nxu - 1) ? g_xe : SM((double)ix, g_dx);
                 } else { y0[j] = __ldg(A.ys + iy); x0[j] = __ldg(A.xs + ix); }
                 uu[j] = 0.0; vv[j] = A.v;                           // the fast path takes the direction from K0
                 ixj[j] += dr; iyj[j] += dq;
@@ -883,7 +885,6 @@ k_candidates_simple(CandArgs A)
             trace_fast<CS_RPT, false, SurfK*, false, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
 #pragma unroll
             for (int j = 0; j < CS_RPT; j++) {
-                const double a_stop2 = par[6];
                 double r2 = fma(h[j].xs, h[j].xs, h[j].ys * h[j].ys);
                 amb[j] |= tiny_vs_bit(r2 - a_stop2, a_stop2);
                 bool drop = r2 > a_stop2;
@@ -894,7 +895,7 @@ k_candidates_simple(CandArgs A)
                     r2 = ri * ri;
                 }
                 if (valid[j] && !drop) {
-                    const double ex = h[j].xf, dy = (h[j].yf - par[8]) - cy;
+                    const double ex = h[j].xf, dy = h[j].yf - hpc;      // (yf - h') - cy up to one rounding of the shift
                     s1x += ex; s2x = fma(ex, ex, s2x); s1y += dy; s2y = fma(dy, dy, s2y);
                     if (r2 > rmax) rmax = r2;
                     n++;
