@@ -177,7 +177,9 @@ int ort_set_layout(ort_ctx *ctx, int rows, const double *R, const double *t, con
  *      (src/PupilSampling.jl:7, src/RayTracing.jl:82 -- of the vertex-plane y only, and ignored on a plane) and tilt +
  *      dp_dy(p, .) with the reference's complex-step derivative (src/RayTracing.jl:103), in the 3-D tracers and -- with
  *      aspheric = 1 -- the 2-D tracer / ray aiming.  Call after ort_set_layout (which clears them); coef = NULL clears.
- *      Prescriptions with polynomial terms run in reference arithmetic (ORT_ARITH_FAST requests resolve to STRICT).
+ *      ORT_ARITH_FAST: the 3-D tracers run a K-form body for surfaces with terms (analytic dp/dy; within 1e-12 of the
+ *      reference arithmetic, guard-band rays re-traced strictly, clip mask and flags bit-exact); prescriptions that also
+ *      hold a mirror, or terms on a PLANE (whose sag ignores p while its tilt keeps dp_dy), resolve to STRICT.
  *      Parity unpinned: the evaluation order of a user's closure is unknowable (Horner here), and the reference has no
  *      test with p != zero. */
 #define ORT_MAX_POLY 18

@@ -131,6 +131,9 @@ struct TransferArgs {
 #ifndef ORT_BPSS
 #define ORT_BPSS 3                          // ... for k_grid<STRICT,1> (80 registers, no spills: 15.3 vs 16.5 ms at 2; 4 is slower)
 #endif
+#ifndef ORT_BPS_POLY
+#define ORT_BPS_POLY 3                      // ... for the k_grid<FAST,2> instantiations with the polynomial body (2 CTAs x 128 registers: the same time)
+#endif
 #ifndef ORT_BPS2E
 #define ORT_BPS2E 3                         // ... for k_grid<FAST,2,EXT> (80 registers, ~190 B of spills: 5-7 % faster than 2 CTAs x 126 registers)
 #endif

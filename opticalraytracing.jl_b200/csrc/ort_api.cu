@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -280,7 +281,11 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
     if (!ctx) return ORT_EINVAL;
     if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: call ort_set_layout first");
     Presc& P = ctx->presc;
-    if (!coef || ncoef <= 0) { P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; return ORT_OK; }     // cleared
+    auto clear = [&]() {                             // no terms: every surface dispatches on its own kind again
+        P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout;
+        for (int i = 0; i < P.nsurf; i++) P.s[i].kcode = P.s[i].kind & 7;
+    };
+    if (!coef || ncoef <= 0) { clear(); return ORT_OK; }
     if (rows != ctx->rows) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: rows = %d, layout has %d", rows, ctx->rows);
     if (ncoef > ORT_MAX_POLY) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: ncoef = %d > %d", ncoef, ORT_MAX_POLY);
     bool any = false;
@@ -288,15 +293,28 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
         if (isnan(coef[i])) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: NaN coefficient");
         any = any || coef[i] != 0.0;
     }
-    if (!any) { P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; return ORT_OK; }     // all zero == Polynomial(zero)
+    if (!any) { clear(); return ORT_OK; }            // all zero == Polynomial(zero)
     CK(cudaSetDevice(ctx->device));
     ScratchScope scratch(ctx, ctx->stream);
-    double* d_c; ENSURE(SL_POLY, (size_t)(rows - 1) * ncoef * 8, d_c);
-    // surface step i uses Layout row i + 1 (row 0 is object space)
-    CK(cudaMemcpyAsync(d_c, coef + ncoef, (size_t)(rows - 1) * ncoef * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t ntab = (size_t)(rows - 1) * ncoef;
+    double* d_c; ENSURE(SL_POLY, 2 * ntab * 8, d_c);
+    // surface step i uses Layout row i + 1 (row 0 is object space); behind the coefficients, k c_k for the FAST body's dp/dy
+    std::vector<double> tab(2 * ntab);
+    for (size_t i = 0; i < ntab; i++) { tab[i] = coef[ncoef + i]; tab[ntab + i] = (double)(i % ncoef) * coef[ncoef + i]; }
+    CK(cudaMemcpyAsync(d_c, tab.data(), 2 * ntab * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     P.poly = d_c; P.npoly = ncoef;
-    P.fast_ok = 0;                                   // the K-form has no polynomial terms: reference arithmetic only
+    // FAST: curved surfaces with terms take fast_step's polynomial body (kcode 7).  It has no mirror form, so prescriptions
+    // with mirrors (and the degenerate ones) stay in the reference arithmetic.
+    // A plane with terms keeps no sag term but does keep the tilt term (:12, :18) -- an oddity the FAST body does not restate.
+    P.fast_ok = ctx->fast_ok_layout && !P.has_mirror;
+    for (int i = 0; i < P.nsurf; i++) {
+        bool row = false;
+        for (int k = 0; k < ncoef; k++) row = row || coef[(size_t)(i + 1) * ncoef + k] != 0.0;
+        const bool curved = (P.s[i].kind & SURF_KIND_MASK) != SURF_PLANE;
+        if (row && !curved) P.fast_ok = 0;
+        P.s[i].kcode = (row && curved) ? SURF_KCODE_POLY : (P.s[i].kind & 7);
+    }
     return ORT_OK;
 }
 

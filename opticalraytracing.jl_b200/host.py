@@ -159,7 +159,7 @@ class Layout:
     """Layout{Spherical|Aspheric} (src/Types.jl:82-112): columns R, t, n, K.  Polynomial terms `p` are arbitrary Julia
     closures in the reference and cannot cross the C ABI; here they are accepted in COEFFICIENT form (an extension):
     p[i] = (c0, c1, c2, ...) means p_i(y) = c0 + c1 y + c2 y^2 + ... for row i (None or empty = zero); callables are
-    rejected.  Layouts with polynomial terms are traced in the reference arithmetic (STRICT)."""
+    rejected.  FAST traces them with fast_step's polynomial body (STRICT when the layout also holds a mirror)."""
 
     def __init__(self, M, K=None, aspheric=None, p=None):
         P = None

@@ -525,7 +525,7 @@ def _poly_layout(ort, name, rng):
 @pytest.mark.parametrize("name", ["COOKE", "DOUBLE_GAUSS", "SINGLET"])
 def test_polynomial_terms_rays(ctx, orc, ort, name):
     """3-D and 2-D tracers with polynomial terms == the CPU restatement, bit for bit (same Horner / complex-step order);
-    a FAST request runs the reference arithmetic; zero coefficients == no polynomial; clearing works."""
+    FAST within 1e-12 of it with the oracle's flags; zero coefficients == no polynomial; clearing works."""
     rng = np.random.default_rng(21)
     S, K, P = _poly_layout(ort, name, rng)
     N = 3000
@@ -541,10 +541,22 @@ def test_polynomial_terms_rays(ctx, orc, ort, name):
     assert np.nanmax(np.abs(yo - yn)) > 1e-6                      # the terms do something
     ctx.set_layout(S, K)
     ctx.set_polynomials(P)
-    for arith in (ort.STRICT, ort.FAST):
-        xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=arith)
-        assert np.array_equal(fs, fo)
-        assert n_bits_differ(xs, xo) == 0 and n_bits_differ(ys, yo) == 0 and n_bits_differ(ks, ko) == 0
+    xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
+    assert np.array_equal(fs, fo)
+    assert n_bits_differ(xs, xo) == 0 and n_bits_differ(ys, yo) == 0 and n_bits_differ(ks, ko) == 0
+    # FAST: the K-form body for surfaces with terms (fast_step, kcode 7); rays it cannot vouch for are re-traced in the
+    # reference arithmetic, so the flags and the NaN pattern are the oracle's
+    xf, yf, kf, ff = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
+    assert np.array_equal(ff, fo)
+    assert np.array_equal(np.isnan(yf), np.isnan(yo)) and np.array_equal(np.isnan(kf), np.isnan(ko))
+    assert n_bits_differ(yf, yo) > 0                              # it is not the reference arithmetic
+    tame = (np.hypot(y0, x0) < 6.0) & (np.hypot(u0, v0) < 0.06) & (fo == 0)
+    assert tame.sum() > 300
+    with np.errstate(all="ignore"):
+        e_pos = np.nan_to_num(np.maximum(np.nanmax(np.abs(xf - xo), axis=0), np.nanmax(np.abs(yf - yo), axis=0)) / 10.0, nan=0.0)
+        e_dir = np.nan_to_num(np.nanmax(np.abs(kf - ko), axis=0), nan=0.0)
+    assert e_pos[tame].max() < TOL and e_dir[tame].max() < TOL    # north_star tolerance on well-conditioned rays
+    assert e_pos.max() < 1e-9 and e_dir.max() < 1e-9              # the wild ones (1.3 x aperture, grazing) stay close too
     y2, U2, ts, f2 = ctx.trace2d_batch(y0, np.arctan(u0), aspheric=True)
     assert np.array_equal(f2, f2o)
     # libm (tan, atan, asin) differs in the last ulp: error relative to the position / angle scale
@@ -566,7 +578,7 @@ def test_polynomial_terms_rays(ctx, orc, ort, name):
 
 
 def test_polynomial_terms_grid_and_full_trace(ctx, orc, pre, ort):
-    """grid sweep with polynomial terms (EXT instantiation, reference arithmetic): spot, mask, flags and counts == oracle;
+    """grid sweep with polynomial terms (EXT instantiation): STRICT == oracle bit for bit, FAST within 1e-12 with the same mask;
     full_trace through the host API (prelude with the 2-D polynomial tracer, reversed chief-ray layout with reverse(p))"""
     rng = np.random.default_rng(22)
     S, K, P = _poly_layout(ort, "COOKE", rng)
@@ -582,11 +594,17 @@ def test_polynomial_terms_grid_and_full_trace(ctx, orc, pre, ort):
         orc.set_poly(None)
     ctx.set_layout(p.ext, p.K)
     ctx.set_polynomials(Pext)
+    scale = max(abs(p.h_prime), 1.0)
     for arith in (ort.STRICT, ort.FAST):
         for want in (("ex", "ey", "r", "theta", "mask", "flags", "stats"), ("ex", "ey", "mask", "stats")):
             r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop, arith=arith, want=want)
             assert np.array_equal(r["mask"][0], g["mask"]) and int(r["stats"]["n_kept"][0]) == g["n_kept"]
-            assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
+            if arith == ort.STRICT:
+                assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
+            else:                                   # the K-form polynomial body; a handful of rays re-traced strictly
+                assert abs_rel_err(r["ex"][0], g["ex"], scale) < TOL and abs_rel_err(r["ey"][0], g["ey"], scale) < TOL
+                assert not bits_equal(r["ex"][0], g["ex"]) and int(r["stats"]["n_strict"][0]) < 48 * 24 // 20
+                if "flags" in want: assert np.array_equal(r["flags"][0], g["flags"])
     ctx.set_polynomials(None)
     # host API: a Layout with coefficient polynomials, against the oracle prelude + grid on the same layout
     L = ort.Layout(S, p=list(P))

@@ -3,7 +3,10 @@ cemented groups; tests/test_gpu_random_systems.random_system) and deliberately h
 misses and near-equator hits, steep slopes -> TIR and grazing incidence).  STRICT is bit-identical to the CPU restatement
 of the reference (tests), so agreement here is agreement with the reference: flags and NaN patterns must be IDENTICAL,
 positions within 1e-12 of the position scale on well-conditioned rays (outliers are re-examined against the 80-bit oracle).
-usage: python tools/fuzz_fast_vs_strict.py [n_systems] [rays_per_system]  -> JSON summary on stdout"""
+usage: python tools/fuzz_fast_vs_strict.py [n_systems] [rays_per_system] [poly]  -> JSON summary on stdout
+       python tools/fuzz_fast_vs_strict.py grid [n_systems] [poly]
+`poly`: refracting systems only, with random y^3 .. y^8 terms on most curved surfaces (EXTENSION, fast_step's polynomial body);
+the 80-bit oracle has no polynomial terms, so outliers are counted but not re-examined."""
 import json
 import os
 import sys
@@ -16,15 +19,26 @@ import ort_b200 as ort
 from test_gpu_random_systems import random_system
 
 
-def grid_mode(nsys):
+def random_terms(rng, S):
+    """coefficient rows for random_system's S: y^4, y^6, y^8 (and sometimes y^3) terms on ~70 % of the curved surfaces"""
+    rows = S.shape[0]
+    P = np.zeros((rows, 9))
+    for i in range(1, rows):
+        if np.isfinite(S[i, 0]) and rng.uniform() < 0.7:
+            P[i, 4], P[i, 6], P[i, 8] = rng.uniform(-3e-7, 3e-7), rng.uniform(-3e-10, 3e-10), rng.uniform(-1e-13, 1e-13)
+            if rng.uniform() < 0.3: P[i, 3] = rng.uniform(-1e-6, 1e-6)
+    return P
+
+
+def grid_mode(nsys, poly=False):
     """FAST vs STRICT through the grid kernel: random systems, random stop surface and radius, collimated and finite-object
     fields, every output-set instantiation (generic / spot + mask / statistics only): masks, flags and counts identical."""
     ctx = ort.Context(0)
-    tot = dict(mode="grid", systems=nsys, rays=0, mask_mismatch=0, flag_mismatch=0, count_mismatch=0, lean_mismatch=0,
+    tot = dict(mode="grid" + ("+poly" if poly else ""), systems=nsys, rays=0, mask_mismatch=0, flag_mismatch=0, count_mismatch=0, lean_mismatch=0,
                stats_only_mismatch=0, max_err=0.0, kept=0, strict_retraced=0)
     for seed in range(nsys):
         rng = np.random.default_rng(70000 + seed)
-        S = random_system(rng, mirrors=seed % 3 == 1, conics=seed % 2 == 1)
+        S = random_system(rng, mirrors=seed % 3 == 1 and not poly, conics=seed % 2 == 1)
         K = np.append(S[:, 3], 0.0)
         ext = np.vstack([S[:, :3], [np.inf, 0.0, S[-1, 2]]])
         ext[-2, 1] = rng.uniform(20.0, 80.0) * np.sign(S[-1, 2])
@@ -37,6 +51,7 @@ def grid_mode(nsys):
         else:
             fld = dict(u=float(rng.uniform(-0.2, 0.2)), v=float(rng.uniform(-0.05, 0.05)), h_prime=0.3)
         ctx.set_layout(ext, K)
+        if poly: ctx.set_polynomials(np.vstack([random_terms(rng, S), np.zeros((1, 9))]))
         want = ("ex", "ey", "r", "theta", "mask", "flags", "stats")
         rs = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.STRICT, want=want)
         rf = ctx.trace3d_grid([fld], ys, xs, stop, a_stop, arith=ort.FAST, want=want)
@@ -47,6 +62,11 @@ def grid_mode(nsys):
         tot["flag_mismatch"] += int(np.count_nonzero(rs["flags"] != rf["flags"]))
         tot["count_mismatch"] += int(rs["stats"]["n_kept"][0] != rf["stats"]["n_kept"][0])
         tot["lean_mismatch"] += int(np.count_nonzero(rl["mask"] != rf["mask"])) + int(rl["stats"].tobytes() != rf["stats"].tobytes())
+        for k in rl["stats"].dtype.names:           # which statistics differ between the output-set instantiations, if any
+            if rl["stats"][k].tobytes() != rf["stats"][k].tobytes():
+                tot.setdefault("lean_stat_fields", {}).setdefault(k, 0)
+                tot["lean_stat_fields"][k] += 1
+        tot["lean_ex_bits"] = tot.get("lean_ex_bits", 0) + int(np.count_nonzero(rl["ex"][0].view(np.int64) != rf["ex"][0].view(np.int64)))
         tot["stats_only_mismatch"] += int(ro["stats"].tobytes() != rf["stats"].tobytes())
         tot["kept"] += int(rs["stats"]["n_kept"][0]); tot["strict_retraced"] += int(rf["stats"]["n_strict"][0])
         m = rs["mask"][0].astype(bool)
@@ -59,7 +79,8 @@ def grid_mode(nsys):
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grid":
-        return grid_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 300)
+        return grid_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 300, poly="poly" in sys.argv[3:])
+    poly = "poly" in sys.argv[3:]
     nsys = int(sys.argv[1]) if len(sys.argv) > 1 else 400
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     ctx = ort.Context(0)
@@ -67,12 +88,13 @@ def main():
         from oracle import oracle as orc
     except Exception:
         orc = None
-    tot = dict(systems=nsys, rays=0, flag_mismatch=0, nan_mismatch=0, miss=0, tir=0, domain=0, finite=0, over_1e12=0,
+    if poly: orc = None
+    tot = dict(mode="rays" + ("+poly" if poly else ""), systems=nsys, rays=0, flag_mismatch=0, nan_mismatch=0, miss=0, tir=0, domain=0, finite=0, over_1e12=0,
                over_1e12_well_conditioned=0, max_err=0.0, max_err_well_conditioned=0.0)
     worst = []
     for seed in range(nsys):
         rng = np.random.default_rng(50000 + seed)
-        S = random_system(rng, mirrors=seed % 3 == 1, conics=seed % 2 == 1)
+        S = random_system(rng, mirrors=seed % 3 == 1 and not poly, conics=seed % 2 == 1)
         K = S[:, 3].copy()
         hostile = seed % 4
         h = (9.0, 25.0, 40.0, 15.0)[hostile]
@@ -80,6 +102,7 @@ def main():
         y0, x0 = rng.uniform(-h, h, N), rng.uniform(-h, h, N)
         u0, v0 = rng.uniform(-sl, sl, N), rng.uniform(-sl, sl, N)
         ctx.set_layout(S[:, :3], K)
+        if poly: ctx.set_polynomials(random_terms(rng, S))
         xs, ys, ks, fs = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.STRICT)
         xf, yf, kf, ff = ctx.trace3d_rays(y0, x0, u0, v0, arith=ort.FAST)
         tot["rays"] += N
