@@ -447,7 +447,7 @@ k_paraxial_final(const __grid_constant__ LensK L, ParaxArgs A)
             if (i >= N) continue;
             if (A.y) __stcs(A.y + i, (CLIP && ci[j]) ? CUDART_NAN : y[j]);
             if (A.w) __stcs(A.w + i, (CLIP && ci[j]) ? CUDART_NAN : w[j]);
-            if (CLIP && A.clip_idx) __stcs(A.clip_idx + i, ci[j]);
+            if (A.clip_idx) __stcs(A.clip_idx + i, CLIP ? ci[j] : 0);      // 0 = not clipped (also without the clip test)
         }
     }
 }
