@@ -43,6 +43,15 @@ int ort_ensure(ort_ctx* ctx, int id, size_t bytes, void** out)
         ctx->slot_bytes[id] = bytes;
     }
     *out = ctx->slot[id];
+    // ORT_POISON_SCRATCH=1 (tests): every slot is filled with 0xFF bytes -- NaNs, -1 counts -- each time an entry point
+    // asks for it, on the stream the entry point works on, so that a kernel that reads scratch it did not write (or an
+    // output the library forgot to write) shows up as a wrong result instead of depending on what the block held before.
+    // SL_POLY is the one slot whose content outlives the call that fills it.
+    static const bool poison = [] { const char* e = getenv("ORT_POISON_SCRATCH"); return e && atoi(e) != 0; }();
+    if (poison && id != SL_POLY) {
+        cudaError_t e = cudaMemsetAsync(ctx->slot[id], 0xFF, bytes, ctx->scratch_now ? ctx->scratch_now : ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ORT_ECUDA, "poison memset -> %s", cudaGetErrorString(e));
+    }
     return ORT_OK;
 }
 

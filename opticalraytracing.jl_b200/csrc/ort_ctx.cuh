@@ -36,6 +36,7 @@ struct ort_ctx {
     cudaEvent_t ev_scratch;
     cudaStream_t scratch_stream;
     bool scratch_busy;
+    cudaStream_t scratch_now;   // stream of the entry point that is running (ScratchScope), for ORT_POISON_SCRATCH
     long long launches;
     int prof_on;
     long long prof_n;               // event pairs recorded since the last read
@@ -70,6 +71,7 @@ struct ScratchScope {
     ScratchScope(ort_ctx* c_, cudaStream_t st_) : c(c_), st(st_)
     {
         if (c->scratch_busy && c->scratch_stream != st) cudaStreamWaitEvent(st, c->ev_scratch, 0);
+        c->scratch_now = st;
     }
     ~ScratchScope()
     {
