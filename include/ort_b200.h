@@ -119,7 +119,7 @@ typedef struct ort_stats {
     double  r_max;            /* maximum(r) (:142) */
     int64_t n_miss, n_tir, n_domain, n_clip;   /* rays carrying each flag */
     int64_t n_vig;            /* EXTENSION: rays clipped by a surface aperture */
-    double  mean_opd, m2_opd; /* EXTENSION: mean and sum of squared deviations of out->opd over kept rays */
+    double  mean_opd, m2_opd; /* EXTENSION: mean and sum of squared deviations of out->opd over kept rays (0 without ORT_EXT_OPD) */
     int64_t n_strict;         /* rays whose outputs come from the strict re-trace (all of them in ORT_ARITH_STRICT; in
                                  ORT_ARITH_FAST the guard-band / miss / TIR rays) */
 } ort_stats;
