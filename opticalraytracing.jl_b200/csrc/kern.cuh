@@ -165,7 +165,7 @@ struct TransferArgs {
 int grid_variant(const Presc& P, int arith, int ext);
 int grid_rays_per_thread(int arith, int variant);
 int grid_blocks_per_sm(int arith, int variant);
-cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st);
+cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st, const PolyK* Q = nullptr);
 cudaError_t launch_grid_finalize(const RawPart* partials, int nparts, int n_fields, ort_stats* stats,
                                  cudaStream_t st);
 cudaError_t launch_compact(int* tile_counts, const CompactArgs& C, int n_fields, cudaStream_t st);

@@ -88,13 +88,13 @@ __device__ __forceinline__ bool is_nan_bits(double a)
 // R2ONLY: the caller only needs r^2 of the stop position (lean output sets): h.xs carries it, h.ys is unused -- three
 // doubles instead of six live across the second surface loop.  KZCHECK = false: the prescription ends with a plain plane, so
 // a non-finite Kz has already reached x, y (s = (t - z) / Kz) and needs no test of its own.
-template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, int SIMPLE = 0, bool R2ONLY = false, bool POLY = false>
+template <int RPT, bool EXT, class SurfArray, bool MIRROR = true, int SIMPLE = 0, bool R2ONLY = false, int POLY = 0, class QT = NoPolyK>
 __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int stop, double n0,
                                            const double* y, const double* x, const double* u,
                                            const double* v, Hit* h, int* amb,
                                            const ort_field* fld = nullptr, double nlast = 1.0, bool vignette = false,
                                            const double* K0 = nullptr, bool kzcheck = true, const double* poly = nullptr,
-                                           int npoly = 0)
+                                           int npoly = 0, const QT* Q = nullptr)
 {
     RaysF<RPT> r;
 #pragma unroll
@@ -110,14 +110,16 @@ __device__ __forceinline__ void trace_fast(const SurfArray& S, int nsurf, int st
     }
     int i = 0;
     for (; i < stop; i++)
-        fast_step<RPT, EXT, MIRROR, SIMPLE, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly, nsurf * npoly);
+        if constexpr (POLY == 2) fast_step<RPT, EXT, MIRROR, SIMPLE, 2>(S[i], r, vignette, nullptr, 0, 0, &Q->r[i]);
+        else fast_step<RPT, EXT, MIRROR, SIMPLE, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly, nsurf * npoly);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         if (R2ONLY) { h[j].xs = fma(r.x[j], r.x[j], r.y[j] * r.y[j]); h[j].ys = 0.0; }
         else { h[j].xs = r.x[j]; h[j].ys = r.y[j]; }
     }
     for (; i < nsurf; i++)
-        fast_step<RPT, EXT, MIRROR, SIMPLE, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly, nsurf * npoly);
+        if constexpr (POLY == 2) fast_step<RPT, EXT, MIRROR, SIMPLE, 2>(S[i], r, vignette, nullptr, 0, 0, &Q->r[i]);
+        else fast_step<RPT, EXT, MIRROR, SIMPLE, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly, nsurf * npoly);
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         h[j].xf = r.x[j]; h[j].yf = r.y[j];
@@ -214,7 +216,7 @@ __device__ __forceinline__ void field_slopes(const ort_field& fld, double y0, do
 // LEAN == 1 stores go through lp (this ray's slots in ex, ey, mask[, opd]): the kernel derives the three pointers once per
 // tile and the rays of a thread sit at compile-time offsets from them, instead of 64-bit address arithmetic per ray and array.
 struct LeanPtrs { double *ex, *ey, *opd; uint8_t* mask; };
-template <int ARITH, int EXTK, int LEAN, bool R2ONLY = false, bool POLYK = false>
+template <int ARITH, int EXTK, int LEAN, bool R2ONLY = false, int POLYK = 0>
 __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, const ort_field& fld,
                                              const double* ysf, Hit h, int amb, unsigned idx,
                                              bool valid, size_t fbase, double cx, double cy, double co, RawAcc& acc,
@@ -236,7 +238,7 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
             const unsigned iy = idx / (unsigned)A.nx, ix = idx - iy * (unsigned)A.nx;
             const double y0 = __ldg(ysf + iy), x0 = __ldg(A.xs + ix);
             double u, v; field_slopes(fld, y0, x0, u, v);
-            h = trace_strict_cold<EXT, decltype(P.s), POLYK>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette, P.poly, P.npoly);
+            h = trace_strict_cold<EXT, decltype(P.s), POLYK != 0>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0, P.nlast, vignette, P.poly, P.npoly);
         }                                           // STRICT: h is the reference-arithmetic trace already (k_grid)
         ri = jl_hypot(h.xs, h.ys);                                      // :131
         clip = ri > A.a_stop;
@@ -294,9 +296,9 @@ __device__ __forceinline__ int grid_epilogue(const Presc& P, const GridArgs& A, 
 // thread through the three-body fast_step<.., SIMPLE>, ORT_BPSP resident CTAs/SM.
 // EXTK: 0 = the reference's outputs only; 1 = extensions (OPD and / or per-surface apertures, chosen at run time; polynomial
 // terms in STRICT); 2 = OPD only (no aperture test compiled in: the instantiation of OPD sweeps over SIMPLE prescriptions).
-template <int ARITH, int RPT, int EXTK, int LEAN = 0, bool MIRROR = true, int SIMPLE = 0, bool POLYK = false>
+template <int ARITH, int RPT, int EXTK, int LEAN = 0, bool MIRROR = true, int SIMPLE = 0, int POLYK = 0>
 __global__ void __launch_bounds__(ORT_TILE, (ARITH == ORT_ARITH_FAST) ? POLYK ? ORT_BPS_POLY : (SIMPLE == 2 ? ORT_BPSC : SIMPLE ? (EXTK ? ORT_BPSE : ORT_BPSP) : (RPT == 1 ? ORT_BPS1 : (EXTK ? ORT_BPS2E : ORT_BPS2))) : ORT_BPSS)
-k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
+k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A, const __grid_constant__ typename PolyArg<POLYK>::type Q)
 {
     constexpr bool EXT = EXTK != 0;
     __shared__ RawPart s_part[ORT_TILE / 32];
@@ -320,10 +322,10 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         double u, v; field_slopes(fld, y0, x0, u, v);
         Hit h; int amb = 0;
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<1, EXT, decltype(P.s), SIMPLE == 0, SIMPLE, false, POLYK>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette,
-                                                                   nullptr, true, P.poly, P.npoly);
+            trace_fast<1, EXT, decltype(P.s), SIMPLE == 0, SIMPLE, false, POLYK, typename PolyArg<POLYK>::type>(P.s, P.nsurf, A.stop, P.n0, &y0, &x0, &u, &v, &h, &amb, &fld, P.nlast, vignette,
+                                                                   nullptr, true, P.poly, P.npoly, &Q);
         if (ARITH == ORT_ARITH_STRICT || amb < 0)
-            h = trace_strict_cold<EXT, decltype(P.s), (EXT && ARITH == ORT_ARITH_STRICT) || POLYK>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0,
+            h = trace_strict_cold<EXT, decltype(P.s), (EXT && ARITH == ORT_ARITH_STRICT) || POLYK != 0>(P.s, P.nsurf, A.stop, y0, x0, u, v, &fld, P.n0,
                                                                                                   P.nlast, vignette, P.poly, P.npoly);
         const double ey = h.yf - fld.h_prime;
         const bool bad = nonfinite_bit(h.xf) < 0 || nonfinite_bit(ey) < 0;
@@ -379,8 +381,8 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A)
         Hit h[RPT];
         int amb[RPT];
         if (ARITH == ORT_ARITH_FAST)
-            trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE, R2ONLY, POLYK>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
-                                                                collimated ? K0 : nullptr, kzcheck, P.poly, P.npoly);
+            trace_fast<RPT, EXT, decltype(P.s), MIRROR, SIMPLE, R2ONLY, POLYK, typename PolyArg<POLYK>::type>(P.s, P.nsurf, A.stop, P.n0, y0, x0, u, v, h, amb, &fld, P.nlast, vignette,
+                                                                collimated ? K0 : nullptr, kzcheck, P.poly, P.npoly, &Q);
         else {      // STRICT: the thread's RPT rays advance surface by surface together (independent chains of the slow ops: / and sqrt)
             RayS r[RPT];
 #pragma unroll
@@ -562,7 +564,7 @@ k_rays(const __grid_constant__ Presc P, RaysArgs A)
         RaysF<1> r;
         fast_init(r, 0, P.n0, y0, x0, u0, v0);
         for (int s = 0; s < nsurf; s++) {
-            fast_step<1, EXT, true, 0, EXT>(P.s[s], r, vignette, (EXT && P.poly) ? P.poly + (size_t)s * P.npoly : nullptr, P.npoly, nsurf * P.npoly);
+            fast_step<1, EXT, true, 0, EXT ? 1 : 0>(P.s[s], r, vignette, (EXT && P.poly) ? P.poly + (size_t)s * P.npoly : nullptr, P.npoly, nsurf * P.npoly);
             if (A.xv) A.xv[(size_t)s * A.N + i] = r.x[0];
             if (A.yv) A.yv[(size_t)s * A.N + i] = r.y[0];
         }
@@ -1009,7 +1011,7 @@ int grid_blocks_per_sm(int arith, int variant)
     return nb;
 }
 
-cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st)
+cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid, cudaStream_t st, const PolyK* Q)
 {
     const bool ext = A.ext != 0 || P.poly != nullptr;          // polynomial terms live in the EXT instantiations
     if (arith == ORT_ARITH_FAST) {
@@ -1020,30 +1022,32 @@ cudaError_t launch_grid(const Presc& P, const GridArgs& A, int arith, dim3 grid,
         const bool simple = variant == 2;
         // the output set of an OPD sweep (ex, ey, opd, mask + statistics) has its own lean epilogue
         const bool lean_opd = (A.ext & ORT_EXT_OPD) && A.ex && A.ey && A.mask && A.opd && !(A.r || A.theta || A.wx || A.wy || A.flags);
-        if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE) && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 3 && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 3) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 4 && lean) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 1, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 4 && stats_only) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 2, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (variant == 4) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 0, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A);
+        if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE) && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 3 && !(A.ext & ORT_EXT_VIGNETTE)) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 2, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 3 && lean_opd) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 3) k_grid<ORT_ARITH_FAST, ORT_SE_RPT, 1, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 4 && lean) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 1, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 4 && stats_only) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 2, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (variant == 4) k_grid<ORT_ARITH_FAST, ORT_SC_RPT, 0, 0, false, 2><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (simple && lean) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 1, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (simple && stats_only) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 2, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (simple) k_grid<ORT_ARITH_FAST, ORT_SIMPLE_RPT, 0, 0, false, true><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
         // polynomial terms (no mirrors: ort_set_polynomials): spot + mask sweeps without the extension outputs have their own instantiation
-        else if (P.poly && !A.ext && !others && A.ex && A.ey && A.mask) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false, 0, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (P.poly) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false, 0, true><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
+        else if (P.poly && Q && !A.ext && !others && A.ex && A.ey && A.mask) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A, *Q);
+        else if (P.poly && Q) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A, *Q);
+        else if (P.poly && !A.ext && !others && A.ex && A.ey && A.mask) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false, 0, 1><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (P.poly) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false, 0, 1><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (ext && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (ext) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (lean && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1, false><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (stats_only && !P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2, false><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (!P.has_mirror) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 0, false><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (lean) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 1><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else if (stats_only) k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0, 2><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else k_grid<ORT_ARITH_FAST, ORT_FAST_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
     } else {
-        if (ext) k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A);
-        else k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A);
+        if (ext) k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 1><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
+        else k_grid<ORT_ARITH_STRICT, ORT_STRICT_RPT, 0><<<grid, ORT_TILE, 0, st>>>(P, A, NoPolyK());
     }
     return cudaGetLastError();
 }

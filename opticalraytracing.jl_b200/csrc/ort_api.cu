@@ -291,7 +291,7 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
     if (!ctx->have_layout) return fail(ctx, ORT_EINVAL, "ort_set_polynomials: call ort_set_layout first");
     Presc& P = ctx->presc;
     auto clear = [&]() {                             // no terms: every surface dispatches on its own kind again
-        P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout;
+        P.poly = nullptr; P.npoly = 0; P.fast_ok = ctx->fast_ok_layout; ctx->have_polyk = false;
         for (int i = 0; i < P.nsurf; i++) P.s[i].kcode = P.s[i].kind & 7;
     };
     if (!coef || ncoef <= 0) { clear(); return ORT_OK; }
@@ -313,6 +313,15 @@ int ort_set_polynomials(ort_ctx* ctx, int rows, int ncoef, const double* coef)
     CK(cudaMemcpyAsync(d_c, tab.data(), 2 * ntab * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     P.poly = d_c; P.npoly = ncoef;
+    ctx->have_polyk = ncoef <= ORT_POLYK_N;
+    if (ctx->have_polyk) {
+        memset(&ctx->polyk, 0, sizeof ctx->polyk);
+        for (int i = 0; i + 1 < rows; i++)
+            for (int k = 0; k < ncoef; k++) {
+                ctx->polyk.r[i].c[k] = tab[(size_t)i * ncoef + k];
+                ctx->polyk.r[i].d[k] = tab[ntab + (size_t)i * ncoef + k];
+            }
+    }
     // FAST: curved surfaces with terms take fast_step's polynomial body (kcode 7).  It has no mirror form, so prescriptions
     // with mirrors (and the degenerate ones) stay in the reference arithmetic.
     // A plane with terms keeps no sag term but does keep the tilt term (:12, :18) -- an oddity the FAST body does not restate.
@@ -390,7 +399,7 @@ int ort_grid_enqueue(ort_ctx* ctx, const ort_field* fields, int n_fields, const 
     const int arith = resolve_arith(ctx, opts->arith);
     if (NN > 0) {
         ProfScope prof(ctx, st);
-        CK(launch_grid(ctx->presc, A, arith, dim3((unsigned)gx, (unsigned)n_fields), st));
+        CK(launch_grid(ctx->presc, A, arith, dim3((unsigned)gx, (unsigned)n_fields), st, ctx->have_polyk ? &ctx->polyk : nullptr));
         ctx->launches++;
     } else {
         CK(cudaMemsetAsync(d_partials, 0, sizeof(RawPart) * (size_t)gx * n_fields, st));

@@ -275,8 +275,9 @@ static int grid_multi_impl(ort_ctx** ctxs, int n, const ort_field* fields, int n
         if (d > 0) {                                        // the layout of ctxs[0] on every context
             const double* poly0 = ctxs[0]->presc.poly;
             c->presc = ctxs[0]->presc; c->rows = ctxs[0]->rows; c->have_layout = true; c->fast_ok_layout = ctxs[0]->fast_ok_layout;
+            c->have_polyk = ctxs[0]->have_polyk; if (c->have_polyk) c->polyk = ctxs[0]->polyk;
             if (poly0) {
-                const size_t nb = (size_t)(c->rows - 1) * c->presc.npoly * 8;
+                const size_t nb = 2 * (size_t)(c->rows - 1) * c->presc.npoly * 8;      // coefficients and k c_k
                 double* dp; ENSURE(SL_POLY, nb, dp);
                 CK(cudaMemcpyPeerAsync(dp, c->device, poly0, ctxs[0]->device, nb, c->stream));
                 c->presc.poly = dp;

@@ -25,6 +25,8 @@ struct ort_ctx {
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_field[ORT_MAX_FIELDS];
     Presc presc;
+    PolyK polyk;                // polynomial terms of <= ORT_POLYK_N coefficients, as k_grid's third parameter
+    bool have_polyk;
     int rows;
     bool have_layout;
     int fast_ok_layout;         // fast_ok as derived from R, t, n, K alone (polynomial terms force it to 0 while set)

@@ -169,6 +169,19 @@ def test_grid_multi_two_gpus_equals_one(ort):
                     n = int(one["stats"][f]["n_kept"]) if compact else ys.shape[1] * len(xs)
                     for k in ("ex", "ey", "r", "theta"):
                         assert np.array_equal(one[k][f][:n], two[k][f][:n], equal_nan=True), (arith, compact, f, k)
+        # polynomial terms travel with the layout of ctxs[0]: the device table (coefficients and k c_k) is copied to the
+        # other device, short rows go as a kernel parameter; 9 and 13 coefficient columns
+        rows = p["ext"].shape[0]
+        for ncol in (9, 13):
+            P = np.zeros((rows, ncol)); P[1, 4] = 2e-7; P[3, 6] = -1e-10; P[2, ncol - 1] = 1e-13 if ncol == 9 else 3e-19
+            cs[0].set_layout(p["ext"], p["K"]); cs[0].set_polynomials(P)
+            for arith in (ort.FAST, ort.STRICT):
+                one = cs[0].trace3d_grid(flds, ys, xs, p["stop"], p["a_stop"], want=want, arith=arith)
+                two = ort._lib.trace3d_grid_multi(cs, flds, ys, xs, p["stop"], p["a_stop"], want=want, arith=arith)
+                assert np.array_equal(one["mask"], two["mask"]) and np.array_equal(one["flags"], two["flags"])
+                for k in ("ex", "ey", "r", "theta"):
+                    assert np.array_equal(one[k], two[k], equal_nan=True), (ncol, arith, k)
+        cs[0].set_polynomials(None)
     finally:
         for c in cs:
             c.close()

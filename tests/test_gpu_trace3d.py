@@ -586,26 +586,30 @@ def test_polynomial_terms_grid_and_full_trace(ctx, orc, pre, ort):
     Pc = ort.prescriptions.COOKE
     sysm = pre.solve(S, Pc["a"], Pc["h"])
     p = pre.full_trace_inputs(sysm, 0.7, 48)
-    Pext = np.vstack([P, np.zeros((1, P.shape[1]))])
-    try:
-        orc.set_poly(Pext)
-        g = orc.grid_trace(p.ext, p.ys, p.xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
-    finally:
-        orc.set_poly(None)
-    ctx.set_layout(p.ext, p.K)
-    ctx.set_polynomials(Pext)
+    # <= 10 coefficients travel as a kernel parameter (unrolled Horner, fast_step<POLY = 2>), longer rows are read from
+    # global memory in a run-time loop (POLY = 1): 9 columns, then 13 with a y^12 term
+    P13 = np.hstack([P, np.zeros((P.shape[0], 4))]); P13[2, 12] = 3e-19
     scale = max(abs(p.h_prime), 1.0)
-    for arith in (ort.STRICT, ort.FAST):
-        for want in (("ex", "ey", "r", "theta", "mask", "flags", "stats"), ("ex", "ey", "mask", "stats")):
-            r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop, arith=arith, want=want)
-            assert np.array_equal(r["mask"][0], g["mask"]) and int(r["stats"]["n_kept"][0]) == g["n_kept"]
-            if arith == ort.STRICT:
-                assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
-            else:                                   # the K-form polynomial body; a handful of rays re-traced strictly
-                assert abs_rel_err(r["ex"][0], g["ex"], scale) < TOL and abs_rel_err(r["ey"][0], g["ey"], scale) < TOL
-                assert not bits_equal(r["ex"][0], g["ex"]) and int(r["stats"]["n_strict"][0]) < 48 * 24 // 20
-                if "flags" in want: assert np.array_equal(r["flags"][0], g["flags"])
-    ctx.set_polynomials(None)
+    for Pq in (P, P13):
+        Pext = np.vstack([Pq, np.zeros((1, Pq.shape[1]))])
+        try:
+            orc.set_poly(Pext)
+            g = orc.grid_trace(p.ext, p.ys, p.xs, p.stop, p.a_stop, p.h_prime, u=p.u, v=p.v, K=p.K)
+        finally:
+            orc.set_poly(None)
+        ctx.set_layout(p.ext, p.K)
+        ctx.set_polynomials(Pext)
+        for arith in (ort.STRICT, ort.FAST):
+            for want in (("ex", "ey", "r", "theta", "mask", "flags", "stats"), ("ex", "ey", "mask", "stats")):
+                r = ctx.trace3d_grid([dict(u=p.u, v=p.v, h_prime=p.h_prime)], p.ys, p.xs, p.stop, p.a_stop, arith=arith, want=want)
+                assert np.array_equal(r["mask"][0], g["mask"]) and int(r["stats"]["n_kept"][0]) == g["n_kept"]
+                if arith == ort.STRICT:
+                    assert bits_equal(r["ex"][0], g["ex"]) and bits_equal(r["ey"][0], g["ey"])
+                else:                                   # the K-form polynomial body; a handful of rays re-traced strictly
+                    assert abs_rel_err(r["ex"][0], g["ex"], scale) < TOL and abs_rel_err(r["ey"][0], g["ey"], scale) < TOL
+                    assert not bits_equal(r["ex"][0], g["ex"]) and int(r["stats"]["n_strict"][0]) < 48 * 24 // 20
+                    if "flags" in want: assert np.array_equal(r["flags"][0], g["flags"])
+        ctx.set_polynomials(None)
     # host API: a Layout with coefficient polynomials, against the oracle prelude + grid on the same layout
     L = ort.Layout(S, p=list(P))
     system = ort.solve(L, Pc["a"], Pc["h"], backend=ctx)
