@@ -377,6 +377,13 @@ double ort_rms_from_stats(const ort_stats *s);
  *      denominator (MEASURED_PEAKS.json holds no FP64 figure).  Returns TFLOP/s (2 flop per DFMA). */
 int ort_fp64_peak(ort_ctx *ctx, double *tflops, double *ms);
 
+/* Self-test of the STRICT kernels' division and square root (correctly rounded fast paths with the slow path deferred to a
+ * per-ray re-trace, csrc/ort_internal.cuh xdiv / xsqrt) against the CUDA library's __ddiv_rn / __dsqrt_rn on >= n operand
+ * pairs: random bit patterns, moderate magnitudes, every exponent, special values.  out8: [0] divisions tested, [1] flagged
+ * for the slow path, [2] kept and different from the intrinsic (must be 0); [3..5] the same for square roots; [6], [7] flags
+ * raised among operands of moderate magnitude (division: only zero numerators; square root: 0).  No reference counterpart. */
+int ort_selftest_exact_ops(ort_ctx *ctx, long long n, unsigned long long seed, long long *out8);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

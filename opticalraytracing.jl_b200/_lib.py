@@ -30,7 +30,7 @@ SYMBOLS = [
     "ort_trace3d_candidates", "ort_trace3d_candidates_dev", "ort_aim_candidates", "ort_aim_candidates_dev", "ort_aim_fields",
     "ort_trace3d_candidates_aimed", "ort_trace3d_candidates_aimed_dev", "ort_vignetting_candidates",
     "ort_vignetting_candidates_dev", "ort_seidel_candidates",
-    "ort_seidel_candidates_dev", "ort_merge_stats", "ort_merge_stats_dev", "ort_rms_from_stats", "ort_fp64_peak",
+    "ort_seidel_candidates_dev", "ort_merge_stats", "ort_merge_stats_dev", "ort_rms_from_stats", "ort_fp64_peak", "ort_selftest_exact_ops",
     "ort_comm_unique_id", "ort_comm_init_rank", "ort_comm_init_all", "ort_comm_info", "ort_comm_free", "ort_comm_range",
     "ort_trace3d_grid_multi", "ort_candidates_sharded", "ort_candidates_sharded_dev",
 ]
@@ -155,6 +155,7 @@ def load():
     L.ort_rms_from_stats.argtypes = [C.c_void_p]
     L.ort_rms_from_stats.restype = C.c_double
     L.ort_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+    L.ort_selftest_exact_ops.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     L.ort_comm_unique_id.argtypes = [C.c_void_p]
     L.ort_comm_init_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.ort_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -371,6 +372,16 @@ class Context:
         t, ms = C.c_double(), C.c_double()
         self._ck(self.L.ort_fp64_peak(self.h, C.byref(t), C.byref(ms)))
         return t.value, ms.value
+
+    def selftest_exact_ops(self, n=1 << 26, seed=1):
+        """xdiv / xsqrt of the STRICT kernels against __ddiv_rn / __dsqrt_rn on >= n operand pairs (ort_selftest_exact_ops)
+        -> dict(div_tested, div_flagged, div_mismatch, sqrt_tested, sqrt_flagged, sqrt_mismatch, div_flagged_moderate,
+        sqrt_flagged_moderate)"""
+        out = (C.c_longlong * 8)()
+        self._ck(self.L.ort_selftest_exact_ops(self.h, int(n), int(seed), out))
+        keys = ("div_tested", "div_flagged", "div_mismatch", "sqrt_tested", "sqrt_flagged", "sqrt_mismatch",
+                "div_flagged_moderate", "sqrt_flagged_moderate")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def set_layout(self, surfaces, K=None):
         """surfaces: rows x 3 [R t n] (or rows x 4 with K); row 1 = object space."""

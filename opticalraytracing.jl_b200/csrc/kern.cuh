@@ -129,7 +129,11 @@ struct TransferArgs {
 #define ORT_BPS2 3                          // ... for k_grid<FAST,2>
 #endif
 #ifndef ORT_BPSS
-#define ORT_BPSS 3                          // ... for k_grid<STRICT,1> (80 registers, no spills: 15.3 vs 16.5 ms at 2; 4 is slower)
+#define ORT_BPSS 4                          // ... for k_grid<STRICT,1>: 64 registers, 132 B of spills.  With xdiv / xsqrt 12.44 ms per bench step
+                                            // against 12.83 at 3 (78 registers, no spills); before them 3 was the optimum (13.4)
+#endif
+#ifndef ORT_STRICT_XF
+#define ORT_STRICT_XF true                 // k_grid<STRICT>: IEEE / and sqrt with the slow path deferred (xdiv, xsqrt)
 #endif
 #ifndef ORT_BPS_POLY
 #define ORT_BPS_POLY 3                      // ... for the k_grid<FAST,2> instantiations with the polynomial body (2 CTAs x 128 registers: the same time)
@@ -150,9 +154,10 @@ struct TransferArgs {
 #define ORT_BPSC 3                          // ... and their resident CTAs/SM
 #endif
 #ifndef ORT_STRICT_RPT
-#define ORT_STRICT_RPT 1                    // rays per thread of k_grid<STRICT>: 13.4 ms per bench step at 1 x 3 CTAs/SM (80 registers);
-#endif                                      // 2 x 3 (spills) 13.5, 2 x 2 (108 registers) 15.3, 3 x 2 15.5 -- the IEEE / and sqrt sequences keep
-                                            // the FP64 pipe ~90 % busy whatever the interleaving
+#define ORT_STRICT_RPT 1                    // rays per thread of k_grid<STRICT>.  With the library intrinsics: 13.4 ms per bench step at
+#endif                                      // 1 x 3 CTAs/SM, 2 x 3 (spills) 13.5, 2 x 2 15.3, 3 x 2 15.5; with xdiv / xsqrt: 1 x 4 12.44, 1 x 3 12.83,
+                                            // 2 x 3 13.3, 2 x 2 14.5 (ncu: FP64 pipe 62 % busy, stall reason `wait` 3.4 per issue -- the
+                                            // serial chain of correctly rounded / and sqrt, which more rays per thread do not shorten)
 #ifndef ORT_SE_RPT
 #define ORT_SE_RPT 2                        // rays per thread of the SIMPLE x EXT instantiations (OPD sweeps over simple prescriptions)
 #endif
@@ -179,5 +184,6 @@ cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st);
 cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st);
 cudaError_t launch_aim_edges(int rows, long long C, const double* RtnK, double* aim, int shared_prescription, cudaStream_t st);
 cudaError_t launch_aim2d(const Presc& P, const AimArgs& A, cudaStream_t st);
+cudaError_t launch_selftest_exact(long long n, unsigned long long seed, unsigned long long* d_out, int sm_count, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* d_sink, int sm_count, long long iters, cudaStream_t st,
                              long long* dfma_per_launch);

@@ -845,6 +845,68 @@ __global__ void __launch_bounds__(512) k_fp64_peak(double* sink, long long iters
 }
 
 // ------------------------------------------------------------------------------------------
+// Self-test of xdiv / xsqrt (ort_internal.cuh) against the library's __ddiv_rn / __dsqrt_rn: wherever the deferred-slow-path
+// forms do NOT raise their flag, the result must be the intrinsic's bit for bit.  Four operand classes per thread and
+// iteration: raw 64-bit patterns; moderate magnitudes (2^-80 .. 2^80: no flag expected unless the numerator is zero);
+// every exponent with random mantissas; special values (zeros, denormals, the ends of the range, Inf, NaN) against the rest.
+// out: [0] divisions tested, [1] flagged, [2] kept-and-different; [3..5] the same for square roots; [6], [7] flags raised
+// in the moderate class (division, square root).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& x)
+{
+    unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double selftest_operand(int cls, unsigned long long& st)
+{
+    const unsigned long long z = splitmix64(st);
+    const unsigned long long mant = z & 0x000FFFFFFFFFFFFFull, sign = z & 0x8000000000000000ull;
+    if (cls == 0) return __longlong_as_double((long long)z);
+    if (cls == 1) return __longlong_as_double((long long)(sign | ((1023ull - 80ull + (z >> 52) % 161ull) << 52) | mant));
+    if (cls == 2) return __longlong_as_double((long long)(sign | (((z >> 52) % 2047ull) << 52) | mant));
+    const unsigned long long special[16] = {0x0ull, 0x8000000000000000ull, 0x7FF0000000000000ull, 0xFFF0000000000000ull,
+                                            0x7FF8000000000000ull, 0x1ull, 0x000FFFFFFFFFFFFFull, 0x0010000000000000ull,
+                                            0x7FEFFFFFFFFFFFFFull, 0x3FF0000000000000ull, 0xBFF0000000000000ull,
+                                            0x0360000000000000ull, 0x035FFFFFFFFFFFFFull, 0x0350000000000000ull,
+                                            0x7FD0000000000000ull, 0x7F90000000000000ull};
+    return __longlong_as_double((long long)special[(z >> 56) & 15]);
+}
+__global__ void __launch_bounds__(256) k_selftest_exact(long long iters, unsigned long long seed, unsigned long long* out)
+{
+    unsigned long long st = seed + 0x632BE59BD9B4E019ull * ((unsigned long long)blockIdx.x * 256 + threadIdx.x + 1);
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long it = 0; it < iters; it++) {
+        const int cls = (int)(it & 3);
+        const double a = selftest_operand(cls, st);
+        const double b = selftest_operand(cls == 3 ? (int)(splitmix64(st) & 3) : cls, st);
+        int bad = 0;
+        const double q = xdiv(a, b, bad), q0 = __ddiv_rn(a, b);
+        c[0]++; c[1] += bad; c[2] += (!bad && __double_as_longlong(q) != __double_as_longlong(q0)) ? 1 : 0;
+        if (cls == 1) c[6] += bad;
+        const double aa = (cls == 1) ? fabs(a) : a;
+        int bad2 = 0;
+        const double g = xsqrt(aa, bad2), g0 = __dsqrt_rn(aa);
+        c[3]++; c[4] += bad2; c[5] += (!bad2 && __double_as_longlong(g) != __double_as_longlong(g0)) ? 1 : 0;
+        if (cls == 1) c[7] += bad2;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned long long v = c[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
+    }
+}
+cudaError_t launch_selftest_exact(long long n, unsigned long long seed, unsigned long long* d_out, int sm_count, cudaStream_t st)
+{
+    const int blocks = sm_count * 4;
+    long long iters = (n + (long long)blocks * 256 - 1) / ((long long)blocks * 256);
+    if (iters < 4) iters = 4;
+    k_selftest_exact<<<blocks, 256, 0, st>>>(iters, seed, d_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 cudaError_t launch_trace2d(const Presc& P, const Trace2dArgs& A, cudaStream_t st)
 {
     const unsigned nb = (unsigned)((A.N + 255) / 256);

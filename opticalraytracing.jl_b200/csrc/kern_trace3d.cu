@@ -387,7 +387,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A, cons
             RayS r[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
-                strict_init(r[j], y0[j], x0[j], u[j], v[j]);
+                strict_init<ORT_STRICT_XF>(r[j], y0[j], x0[j], u[j], v[j]);
                 if (EXT) r[j].opl = strict_opl_start(r[j], fld.mode, P.n0, y0[j], x0[j], fld.z0);
                 h[j].xs = h[j].ys = CUDART_NAN; h[j].opl = 0.0;
             }
@@ -395,7 +395,7 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A, cons
             for (int i = 0; i < nsurf; i++) {
 #pragma unroll
                 for (int j = 0; j < RPT; j++) {
-                    strict_step<EXT, EXT>(P.s[i], r[j], vignette, (EXT && P.poly) ? P.poly + (size_t)i * P.npoly : nullptr, P.npoly);
+                    strict_step<EXT, EXT, ORT_STRICT_XF>(P.s[i], r[j], vignette, (EXT && P.poly) ? P.poly + (size_t)i * P.npoly : nullptr, P.npoly);
                     if (i == stop - 1) { h[j].xs = r[j].x; h[j].ys = r[j].y; }
                 }
             }
@@ -403,6 +403,10 @@ k_grid(const __grid_constant__ Presc P, const __grid_constant__ GridArgs A, cons
             for (int j = 0; j < RPT; j++) {
                 h[j].xf = r[j].x; h[j].yf = r[j].y; h[j].flags = r[j].flags;
                 if (EXT) h[j].opl = strict_opl_close(r[j], fld, P.nlast);
+                // an operand left the range of xdiv / xsqrt's fast path (ort_internal.cuh): this ray once more with the
+                // library's division and square root
+                if (ORT_STRICT_XF && r[j].bad)
+                    h[j] = trace_strict_cold<EXT, decltype(P.s), EXT>(P.s, P.nsurf, A.stop, y0[j], x0[j], u[j], v[j], &fld, P.n0, P.nlast, vignette, P.poly, P.npoly);
             }
         }
         int keptj[RPT];

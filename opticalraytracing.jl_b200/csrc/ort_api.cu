@@ -1181,6 +1181,21 @@ double ort_rms_from_stats(const ort_stats* s)
     return sqrt((2.0 * sxx + 2.0 * s->m2_y) / (2.0 * n));
 }
 
+int ort_selftest_exact_ops(ort_ctx* ctx, long long n, unsigned long long seed, long long* out8)
+{
+    if (!ctx || !out8 || n < 0) return ORT_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ScratchScope scratch(ctx, st);
+    unsigned long long* d; ENSURE(SL_OUT0, 8 * sizeof(unsigned long long), d);
+    CK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), st));
+    CK(launch_selftest_exact(n, seed, d, ctx->sm_count, st));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORT_OK;
+}
+
 int ort_fp64_peak(ort_ctx* ctx, double* tflops, double* ms)
 {
     if (!ctx || !tflops) return ORT_EINVAL;

@@ -177,6 +177,20 @@ def test_error_paths(ctx, ort):
         ctx.trace3d_grid([dict(u=0.0)] * 40, np.zeros(4), np.zeros(4), 5, 1.0)   # too many fields
 
 
+def test_exact_division_and_sqrt_with_deferred_slow_path(ctx):
+    """k_grid<STRICT> takes its divisions and square roots from xdiv / xsqrt: the CUDA library's own fast paths with the
+    range test folded into a per-ray flag (flagged rays are traced again with the intrinsics).  Every result that is kept
+    must be the intrinsic's, bit for bit: 2^28 operand pairs of four classes (raw bit patterns, moderate magnitudes,
+    every exponent, special values).  Moderate operands never raise the flag."""
+    r = ctx.selftest_exact_ops(1 << 28, seed=12345)
+    assert r["div_tested"] >= 1 << 28 and r["sqrt_tested"] >= 1 << 28
+    assert r["div_mismatch"] == 0 and r["sqrt_mismatch"] == 0, r
+    assert 0 < r["div_flagged"] < r["div_tested"] and 0 < r["sqrt_flagged"] < r["sqrt_tested"]     # both paths exercised
+    assert r["div_flagged_moderate"] == 0 and r["sqrt_flagged_moderate"] == 0, r
+    r2 = ctx.selftest_exact_ops(1 << 24, seed=999)
+    assert r2["div_mismatch"] == 0 and r2["sqrt_mismatch"] == 0
+
+
 def test_fp64_peak(ctx):
     tf, ms = ctx.fp64_peak()
     assert 10.0 < tf < 60.0, tf
