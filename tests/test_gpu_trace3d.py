@@ -138,6 +138,61 @@ def test_grid_edge_cases(ctx, orc, pre, ort):
         assert np.array_equal(np.isnan(r["ex"][0]), np.isnan(g["ex"]))
 
 
+def test_strict_exact_paths_adversarial(ctx, orc, ort):
+    """k_grid<STRICT> takes divisions and square roots from xdiv / xsqrt (flag + per-ray re-trace with the intrinsics) and
+    planes from an exact shortcut.  Operands chosen to sit on every seam: the x = 0 column and y = 0 row (zero numerators),
+    -0.0, denormal / tiny / huge coordinates (|x| >= 1e150 leaves the plane shortcut; 1e200 overflows r^2), NaN and Inf
+    coordinates, rays that miss a surface and then meet the planes, planes at both ends and in the middle, a plane with
+    K != 0, a plane with polynomial terms (its tilt keeps dp_dy), R = -Inf.  Everything bit-identical to the CPU oracle."""
+    inf = np.inf
+    S = np.array([[inf, 0.0, 1.0], [inf, 3.0, 1.5], [40.0, 2.0, 1.0], [-inf, 4.0, 1.6], [-35.0, 3.0, 1.0],
+                  [inf, 5.0, 1.0], [60.0, 2.0, 1.7], [inf, 30.0, 1.0], [inf, 0.0, 1.0]])
+    K = np.array([0.0, 0.3, -0.5, -1.7, 0.2, 0.0, 0.0, 2.0, 0.0])
+    xs = np.array([0.0, -0.0, 5e-324, 1e-310, 1e-200, 1e-30, 0.3, 2.0, 7.5, 11.0, 38.0, 41.0, 1e3, 1e149, 1e150, 1e160, 1e200,
+                   inf, np.nan])
+    ys = np.concatenate([-xs[::-1], xs])
+    stop = 5
+    for u, v in ((0.0, 0.0), (0.05, 0.0), (-0.03, 0.02)):
+        fld = [dict(u=u, v=v, h_prime=0.25)]
+        for poly in (None, "plane+curved"):
+            P = None
+            if poly:
+                P = np.zeros((S.shape[0], 7)); P[3, 4] = 2e-6; P[3, 3] = -1e-5; P[2, 6] = 1e-9; P[7, 2] = 1e-4
+            try:
+                orc.set_poly(P)
+                g = orc.grid_trace(S, ys, xs, stop, 9.0, 0.25, u=u, v=v, K=K)
+            finally:
+                orc.set_poly(None)
+            ctx.set_layout(S, K); ctx.set_polynomials(P)
+            with np.errstate(all="ignore"):
+                r = ctx.trace3d_grid(fld, ys, xs, stop, 9.0, arith=ort.STRICT, want=("ex", "ey", "r", "theta", "mask", "flags", "stats"))
+            assert np.array_equal(r["mask"][0], g["mask"]) and np.array_equal(r["flags"][0], g["flags"]), (u, v, poly)
+            for k in ("ex", "ey", "r"):
+                assert bits_equal(r[k][0], g[k]), (u, v, poly, k)
+            assert np.array_equal(np.isnan(r["theta"][0]), np.isnan(g["theta"]))      # atan2: CUDA vs glibc, last ulp
+            m = g["mask"].astype(bool)
+            assert abs_rel_err(r["theta"][0][m], g["theta"][m], math.pi) < 1e-11
+            assert int(r["stats"]["n_kept"][0]) == g["n_kept"] and g["n_kept"] > 20
+            # the single-ray kernel (library intrinsics + the same plane shortcut) on the same rays
+            yy, xx = np.meshgrid(ys, xs, indexing="ij")
+            N = yy.size
+            xo, yo, ko, fo = orc_rays(orc, S, yy.ravel(), xx.ravel(), u, v, K, P)
+            with np.errstate(all="ignore"):
+                xr, yr, kr, fr = ctx.trace3d_rays(yy.ravel(), xx.ravel(), np.full(N, u), np.full(N, v), arith=ort.STRICT)
+            assert np.array_equal(fr, fo)
+            assert n_bits_differ(xr, xo) == 0 and n_bits_differ(yr, yo) == 0 and n_bits_differ(kr, ko) == 0
+    ctx.set_polynomials(None)
+
+
+def orc_rays(orc, S, y0, x0, u, v, K, P):
+    try:
+        orc.set_poly(P)
+        with np.errstate(all="ignore"):
+            return orc.trace3d_batch(S, y0, x0, np.full(y0.size, u), np.full(y0.size, v), K=K)
+    finally:
+        orc.set_poly(None)
+
+
 def test_grid_point_mode_raybasis(ctx, orc, pre, ort):
     """RayBasis mode (src/PupilSampling.jl:124-127): per-ray slopes through tan()."""
     P = ort.prescriptions.COOKE
