@@ -330,6 +330,15 @@ def secondary(R, hbm_peak, fp64_peak):
     out["opd_sweep_16Mi_rays"] = {"ms": ms, "rays_per_s": NY * NX / ms * 1e3, "fp64_frac_of_723": NY * NX * FLOPS_PER_RAY / ms / 1e9 / fp64_peak,
                                   "kept": int(rec["n_kept"]), "rms_opd_waves": float(np.sqrt(rec["m2_opd"] / max(int(rec["n_kept"]), 1))),
                                   "bytes_per_ray": 25, "bound": "fp64"}
+    # ---- the bit-identical arithmetic (STRICT) on the same field: spot + mask, no extension
+    pt2 = {k: pt[k] for k in ("ex", "ey", "mask", "stats")}
+    fld2 = dict(u=float(pe["u"][0]), h_prime=float(pe["h_prime"][0]))
+    ms = kern_ms(lambda: ctx.trace3d_grid_dev([fld2], ysb.data_ptr(), NY, xsb.data_ptr(), NX, pe["stop"], pe["a_stop"], pt2, stream=st,
+                                              arith=ort.STRICT), reps=3, warm=1)
+    rec = R.stats_of(stb, (1,))[0]
+    out["strict_sweep_16Mi_rays"] = {"ms": ms, "rays_per_s": NY * NX / ms * 1e3, "fp64_frac_of_723": NY * NX * FLOPS_PER_RAY / ms / 1e9 / fp64_peak,
+                                     "kept": int(rec["n_kept"]), "bound": "issue slots (IEEE / and sqrt sequences)",
+                                     "note": "bit-identical to the CPU oracle (parity.gpu_vs_cpu_oracle.strict_values_with_different_bits)"}
     return out
 
 
