@@ -117,6 +117,65 @@ __device__ __forceinline__ int secant_polish(F f, double& x, double tgt, double 
     return it;
 }
 
+// The same two iterations with the two function evaluations of a step -- f(x) and f(x + eps) -- taken SIDE BY SIDE by the two
+// lanes of a pair (even lane: x, odd lane: x + eps; one shuffle each way).  Same operations on the same operands, so the
+// same bits and the same iteration counts as the one-thread forms; the chain of serial 2-D traces is half as long (the
+// f(x + eps) of the last step is wasted).  The loop is warp-uniform: pairs that have converged idle until the last one has.
+// Every lane of the warp must call these together.
+template <class F>
+__device__ __forceinline__ int secant_reference_pair(F f, double& x, double tgt, double tol, bool* finite, int odd)
+{
+    const double eps = 1.4901161193847656e-08;                 // sqrt(eps())  src/RayTracing.jl:1
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int it = 0, ret = 0;
+    bool active = true;
+    double val = SS(f(odd ? SA(x, eps) : x), tgt);
+    double v = __shfl_sync(full, val, lane & ~1), ve = __shfl_sync(full, val, lane | 1);
+    for (;;) {
+        bool go = active && fabs(v) > tol;                      // :229, :282
+        if (go && (++it > 100 || !isfinite(v))) { ret = -(it + 1); active = false; go = false; }
+        if (active && !go) { active = false; ret = it; if (finite) *finite = isfinite(v); }
+        if (!__any_sync(full, go)) break;
+        if (go) {
+            x = SS(x, SD(SM(v, eps), SS(ve, v)));               // :231, :284
+            val = SS(f(odd ? SA(x, eps) : x), tgt);
+            active = true;
+        }
+        v = __shfl_sync(full, val, lane & ~1); ve = __shfl_sync(full, val, lane | 1);
+    }
+    return ret;
+}
+
+template <class F>
+__device__ __forceinline__ int secant_polish_pair(F f, double& x, double tgt, double scale, int odd)
+{
+    const double eps = 1.4901161193847656e-08;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double v_prev = 0.0;
+    int it = 0, ret = 0;
+    bool active = true;
+    for (;;) {
+        if (active && it >= 60) { active = false; ret = it; }
+        if (!__any_sync(full, active)) break;
+        const double h = SM(eps, fmax(1.0, fabs(x)));
+        double val = 0.0;
+        if (active) val = SS(f(odd ? SA(x, h) : x), tgt);
+        const double v = __shfl_sync(full, val, lane & ~1), vh = __shfl_sync(full, val, lane | 1);
+        if (active) {
+            if (!isfinite(v)) { active = false; ret = -(it + 1); }
+            else {
+                bool done = fabs(v) <= SM(4e-16, scale);
+                if (it > 0) done = done || (fabs(v) >= fabs(v_prev) && fabs(v_prev) <= SM(1e-13, scale));
+                if (done) { active = false; ret = it; }
+                else { x = SS(x, SD(SM(v, h), SS(vh, v))); v_prev = v; it++; }
+            }
+        }
+    }
+    return ret;
+}
+
 __device__ __forceinline__ double aim_eval(const Presc& P, const AimArgs& A, double x, double other)
 {
     double y = A.vary_u ? other : x, U = A.vary_u ? x : other, sprev = 0.0;
@@ -735,18 +794,24 @@ __device__ __noinline__ double cand_height(const CandView& V, int upto, int asph
 }
 
 // The prelude of one candidate is a chain of serial root finds, so the kernel is latency-bound (0.21 ms for 8192 candidates,
-// 0.30 ms for 65 536): the two independent links of the chain run side by side in the two warps of a CTA -- warp 0 aims the
-// chief ray (secant + the final reversed trace), warp 1 the marginal ray; after one exchange through shared memory warp 0
-// polishes the upper edge ray, warp 1 the lower one.  Lane i of both warps works on candidate 32 blockIdx.x + i; every
-// quantity is computed by exactly one thread with the operations it always had, so the records are bit-identical to
+// 0.30 ms for 65 536 in the one-thread form).  Two splits shorten the chain.  (1) The two independent links run side by
+// side in the two halves of a CTA: half 0 aims the chief ray (secant + the final reversed trace), half 1 the marginal
+// ray; after one exchange through shared memory half 0 polishes the upper edge ray, half 1 the lower one.  (2) Inside a
+// half, a PAIR of lanes works on one candidate: the two function evaluations of every secant step are taken side by side
+// (secant_*_pair).  Every quantity is computed with the operations it always had, so the records are bit-identical to
 // the one-thread-per-candidate form.
 #define AIM_CPB 32                                       // candidates per CTA
-__global__ void __launch_bounds__(2 * AIM_CPB) k_aim_candidates(const __grid_constant__ AimCandArgs A)
+#define AIM_PAIR_MAX_C 24576                             // populations up to this size take the lane-pair form
+// PAIR = false: one lane per candidate and half (2 warps per CTA) -- half the work, twice the chain: the form for large
+// populations, where the kernel is throughput-bound (65 536 candidates: 0.28 ms against 0.30 ms; 8192: 0.139 against 0.094).
+template <bool PAIR>
+__global__ void __launch_bounds__((PAIR ? 4 : 2) * AIM_CPB) k_aim_candidates(const __grid_constant__ AimCandArgs A)
 {
-    __shared__ double s_x[3][AIM_CPB];                   // Ubar, EP_t (warp 0) | y_m (warp 1)
+    __shared__ double s_x[3][AIM_CPB];                   // Ubar, EP_t (half 0) | y_m (half 1)
     __shared__ double s_e2[AIM_CPB];
     __shared__ int s_st[2][AIM_CPB];
-    const int lane = threadIdx.x & (AIM_CPB - 1), role = threadIdx.x / AIM_CPB;
+    const int role = threadIdx.x / ((PAIR ? 2 : 1) * AIM_CPB), odd = PAIR ? (threadIdx.x & 1) : 0;
+    const int lane = PAIR ? ((threadIdx.x & (2 * AIM_CPB - 1)) >> 1) : (threadIdx.x & (AIM_CPB - 1));   // candidate within the CTA
     const long long craw = (long long)blockIdx.x * AIM_CPB + lane;
     const bool live = craw < A.C;
     const long long c = live ? craw : A.C - 1;           // idle lanes shadow the last candidate (no stores)
@@ -780,7 +845,8 @@ __global__ void __launch_bounds__(2 * AIM_CPB) k_aim_candidates(const __grid_con
         const double ybp = A.h_prime;
         double ubp = -SD(nuck, nlast);
         const int rstop = rows - stop_c;
-        if (secant_reference([&](double uu) { return cand_height<true>(V, rstop, 1, ybp, uu); }, ubp, 0.0, tol, &fin) < 0 || !fin) status |= 1;
+        auto fc = [&](double uu) { return cand_height<true>(V, rstop, 1, ybp, uu); };
+        if ((PAIR ? secant_reference_pair(fc, ubp, 0.0, tol, &fin, odd) : secant_reference(fc, ubp, 0.0, tol, &fin)) < 0 || !fin) status |= 1;
         double y = ybp, U = ubp, sprev = 0.0, csum = 0.0; unsigned fl = 0;
         for (int j = 0; j < k; j++) {
             const Surf2 S = cand_surf<true>(V, j);
@@ -795,7 +861,8 @@ __global__ void __launch_bounds__(2 * AIM_CPB) k_aim_candidates(const __grid_con
     } else {
         // ---- real marginal ray (:223-240)
         double ym = SM(1.0, s);
-        if (secant_reference([&](double yy) { return cand_height<false>(V, stop_c, A.aspheric, yy, 0.0); }, ym, a_stop_signed, tol, &fin) < 0 || !fin) status |= 2;
+        auto fm = [&](double yy) { return cand_height<false>(V, stop_c, A.aspheric, yy, 0.0); };
+        if ((PAIR ? secant_reference_pair(fm, ym, a_stop_signed, tol, &fin, odd) : secant_reference(fm, ym, a_stop_signed, tol, &fin)) < 0 || !fin) status |= 2;
         s_x[2][lane] = ym;
     }
     s_st[role][lane] = status;
@@ -808,10 +875,10 @@ __global__ void __launch_bounds__(2 * AIM_CPB) k_aim_candidates(const __grid_con
     double e = role == 0 ? SS(y_EP, SM(u, EP_t)) : SS(-y_EP, SM(u, EP_t));
     auto edge = [&](double yy) { return cand_height<false>(V, stop_c, A.aspheric, yy, U); };
     int st2 = 0;
-    if (secant_polish(edge, e, role == 0 ? a_stop : -a_stop, a_stop) < 0) st2 = 4;
+    if ((PAIR ? secant_polish_pair(edge, e, role == 0 ? a_stop : -a_stop, a_stop, odd) : secant_polish(edge, e, role == 0 ? a_stop : -a_stop, a_stop)) < 0) st2 = 4;
     if (role == 1) { s_e2[lane] = e; s_st[1][lane] |= st2; }
     __syncthreads();
-    if (role == 0 && live) {
+    if (role == 0 && live && !odd) {
         status = s_st[0][lane] | s_st[1][lane] | st2;
         for (int j = 0; j < ORT_AIM_NOUT; j++) out[j] = CUDART_NAN;
         if (!lastrow_ok) { out[11] = 8.0; return; }
@@ -979,7 +1046,11 @@ cudaError_t launch_vignetting(const VigArgs& A, cudaStream_t st)
 cudaError_t launch_aim_candidates(const AimCandArgs& A, cudaStream_t st)
 {
     if (A.C == 0) return cudaSuccess;
-    k_aim_candidates<<<(unsigned)((A.C + AIM_CPB - 1) / AIM_CPB), 2 * AIM_CPB, 0, st>>>(A);
+    // lane pairs halve the chain of serial traces and double the work: worth it while the kernel is latency-bound
+    static const int pair_env = [] { const char* e = getenv("ORT_AIM_PAIR"); return e ? atoi(e) : -1; }();
+    const bool pair = pair_env >= 0 ? pair_env != 0 : A.C <= AIM_PAIR_MAX_C;
+    if (pair) k_aim_candidates<true><<<(unsigned)((A.C + AIM_CPB - 1) / AIM_CPB), 4 * AIM_CPB, 0, st>>>(A);
+    else k_aim_candidates<false><<<(unsigned)((A.C + AIM_CPB - 1) / AIM_CPB), 2 * AIM_CPB, 0, st>>>(A);
     return cudaGetLastError();
 }
 
