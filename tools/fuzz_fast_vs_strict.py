@@ -72,8 +72,14 @@ def grid_mode(nsys, poly=False):
         m = rs["mask"][0].astype(bool)
         if m.any():
             sc = max(np.abs(rs["ex"][0][m]).max(), np.abs(rs["ey"][0][m]).max(), 10.0)
-            tot["max_err"] = max(tot["max_err"], float(np.abs(rf["ex"][0][m] - rs["ex"][0][m]).max() / sc),
-                                 float(np.abs(rf["ey"][0][m] - rs["ey"][0][m]).max() / sc))
+            e = np.maximum(np.abs(rf["ex"][0] - rs["ex"][0]), np.abs(rf["ey"][0] - rs["ey"][0])) / sc
+            e[~m] = 0.0
+            j = int(np.argmax(e))
+            if float(e[j]) > tot["max_err"]:
+                tot["max_err"] = float(e[j])
+                tot["worst"] = dict(seed=seed, iy=j // nx, ix=j % nx, y0=float(ys[j // nx]), x0=float(xs[j % nx]), err=float(e[j]),
+                                    field=fld, stop=stop, a_stop=float(a_stop), r_over_a=float(rs["r"][0][j] / a_stop))
+            tot["over_1e12"] = tot.get("over_1e12", 0) + int(np.count_nonzero(e > 1e-12))
     print(json.dumps(tot, indent=1))
 
 
