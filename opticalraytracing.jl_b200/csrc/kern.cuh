@@ -51,7 +51,7 @@ struct CandArgs {
     int stop; double a_stop, a_stop2, u, v, h_prime;
     const double* aim;                      // NULL, or [C][ORT_AIM_NOUT]: per-candidate grid, stop, field, focus
     double* out;
-    int* lists;                             // FAST: device scratch of 2 + 2 C ints for k_cand_classify (NULL: one CTA per candidate, general kernel)
+    int* lists;                             // FAST: device scratch of 3 + 3 C ints for k_cand_classify (NULL: one CTA per candidate, general kernel)
 };
 
 struct SeidelArgs {

@@ -646,10 +646,10 @@ k_candidates(CandArgs A)
     __shared__ Part s_part[ORT_TILE / 32];
     // FAST sweeps come with the classified lists of k_cand_classify: this kernel then takes the GENERAL candidates
     // (mirrors, conics, weak or dummy spheres), one per CTA, grid-strided
-    const int nlist = A.lists ? A.lists[1] : 0;
+    const int nlist = A.lists ? A.lists[2] : 0;
     for (long long li = blockIdx.x; li < (A.lists ? (long long)nlist : A.C); li += gridDim.x) {
     if (li != (long long)blockIdx.x) __syncthreads();           // the previous candidate's shared state is still being read
-    const long long c = A.lists ? (long long)A.lists[2 + A.C + li] : li;
+    const long long c = A.lists ? (long long)A.lists[3 + 2 * A.C + li] : li;
     const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
     const double* Rc = A.RtnK + (size_t)c * 4 * rows;
     const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
@@ -769,8 +769,10 @@ k_candidates(CandArgs A)
     }
 }
 
-// FAST sweeps first sort the population (one thread per candidate): lists[0] / lists[1] = number of SIMPLE / GENERAL
-// candidates, lists[2 ..) / lists[2 + C ..) their indices.  SIMPLE = refracting spheres (|R| <= 64 L) and planes only,
+// FAST sweeps first sort the population (one thread per candidate): lists[0] / lists[1] / lists[2] = number of SIMPLE /
+// SIMPLE-CONIC / GENERAL candidates, lists[3 ..) / lists[3 + C ..) / lists[3 + 2 C ..) their indices.  SIMPLE-CONIC =
+// refracting conics / spheres and planes only, every index positive (the class of Presc::simple == 2): the same kernel
+// with the conic body.  SIMPLE = refracting spheres (|R| <= 64 L) and planes only,
 // every index positive (simple_surface): those go to k_candidates_simple.  The order inside a list is whatever the
 // atomics produce; every candidate's result is computed alone and written to its own slot, so results do not depend on it.
 __global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, const double* RtnK, int aimed, int* lists)
@@ -779,15 +781,22 @@ __global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, co
     if (c >= C) return;
     const double* Rc = RtnK + (size_t)c * 4 * rows;
     const double L = gap_scale(Rc + rows, rows);
-    bool simple = true;
+    bool simple = true, conic = true;
     for (int i = 0; i + 1 < rows; i++) {
         SurfK S;
-        derive_surface(S, Rc[i + 1], Rc[3 * rows + i + 1], Rc[rows + i], Rc[2 * rows + i], Rc[2 * rows + i + 1]);
-        if (!(Rc[2 * rows + i] > 0.0) || !(Rc[2 * rows + i + 1] > 0.0) || !simple_surface(S, L)) simple = false;
+        const double Ri = Rc[i + 1], Ki = Rc[3 * rows + i + 1], ti = Rc[rows + i], n1 = Rc[2 * rows + i], n2 = Rc[2 * rows + i + 1];
+        derive_surface(S, Ri, Ki, ti, n1, n2);
+        const bool pos = n1 > 0.0 && n2 > 0.0;
+        if (!pos || !simple_surface(S, L)) simple = false;
+        // the conic body needs finite operands and a refracting surface wherever the surface is curved (ort_set_layout)
+        const bool plane = (S.kcode & SURF_KIND_MASK) == SURF_PLANE;
+        const bool finite_ops = !(Ri == 0.0) && Ri == Ri && isfinite(Ki) && isfinite(ti) && isfinite(n1) && isfinite(n2);
+        if (!pos || !finite_ops || (!plane && !(S.kcode & SURF_REFR))) conic = false;
     }
-    if (aimed && !(Rc[3 * rows - 1] > 0.0)) simple = false;     // the appended image plane refracts into n = 1
-    const int slot = atomicAdd(&lists[simple ? 0 : 1], 1);
-    lists[2 + (simple ? 0 : C) + slot] = (int)c;
+    if (aimed && !(Rc[3 * rows - 1] > 0.0)) simple = conic = false;     // the appended image plane refracts into n = 1
+    const int cls = simple ? 0 : (conic ? 1 : 2);
+    const int slot = atomicAdd(&lists[cls], 1);
+    lists[3 + cls * C + slot] = (int)c;
 }
 
 // K5 for SIMPLE candidates: the three-body surface loop (fast_step<.., SIMPLE>), CS_RPT rays per thread, its own launch
@@ -804,7 +813,7 @@ __global__ void __launch_bounds__(128) k_cand_classify(int rows, long long C, co
 #ifndef CS_MINB
 #define CS_MINB 12
 #endif
-template <bool AIMED>
+template <bool AIMED, int SIMPLE = 1>
 __global__ void __launch_bounds__(CS_THREADS, CS_MINB)
 k_candidates_simple(CandArgs A)
 {
@@ -814,12 +823,12 @@ k_candidates_simple(CandArgs A)
     __shared__ double s_red[CS_THREADS / 32][6];
     __shared__ int s_redn[CS_THREADS / 32];
     const int rows = A.rows, nsurf = AIMED ? rows : rows - 1;
-    const int nlist = A.lists[0];
+    const int nlist = A.lists[SIMPLE - 1];
     const unsigned NN = (unsigned)A.ny * (unsigned)A.nx, nxu = (unsigned)A.nx;
     const unsigned step = CS_THREADS * CS_RPT, dq = step / nxu, dr = step - dq * nxu;
     for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
         if (li != (int)blockIdx.x) __syncthreads();
-        const long long c = A.lists[2 + li];
+        const long long c = A.lists[3 + (SIMPLE - 1) * A.C + li];
         const double* Rc = A.RtnK + (size_t)c * 4 * rows;
         const double* rec = AIMED ? A.aim + (size_t)c * ORT_AIM_NOUT : nullptr;
         if (threadIdx.x < rows - 1) {
@@ -892,7 +901,7 @@ k_candidates_simple(CandArgs A)
                 if (ixj[j] >= nxu) { ixj[j] -= nxu; iyj[j]++; }
             }
             Hit h[CS_RPT]; int amb[CS_RPT];
-            trace_fast<CS_RPT, false, SurfK*, false, true>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
+            trace_fast<CS_RPT, false, SurfK*, false, SIMPLE>(s_surf, nsurf, stop, n0, y0, x0, uu, vv, h, amb, nullptr, 1.0, false, K0);
 #pragma unroll
             for (int j = 0; j < CS_RPT; j++) {
                 double r2 = fma(h[j].xs, h[j].xs, h[j].ys * h[j].ys);
@@ -1094,7 +1103,7 @@ cudaError_t launch_rays(const Presc& P, const RaysArgs& A, int arith, cudaStream
 int candidates_blocks_per_sm(int simple)
 {
     int nb = 0;
-    cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_candidates_simple<true>, CS_THREADS, 0)
+    cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_candidates_simple<true, 1>, CS_THREADS, 0)
                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_candidates<ORT_ARITH_FAST, true>, ORT_TILE, 0);
     if (e != cudaSuccess || nb < 1) nb = 1;
     return nb;
@@ -1117,17 +1126,19 @@ cudaError_t launch_candidates(const CandArgs& A, int arith, cudaStream_t st, int
         }
         return cudaGetLastError();
     }
-    cudaError_t e = cudaMemsetAsync(A.lists, 0, 2 * sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(A.lists, 0, 3 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     k_cand_classify<<<(unsigned)((A.C + 127) / 128), 128, 0, st>>>(A.rows, A.C, A.RtnK, A.aim != nullptr, A.lists);
     static const int bps_s = candidates_blocks_per_sm(1), bps_g = candidates_blocks_per_sm(0);
     const long long gs = (long long)sm_count * bps_s * 8, gg = (long long)sm_count * bps_g;
     const unsigned nbs = (unsigned)(A.C < gs ? A.C : gs), nbg = (unsigned)(A.C < gg ? A.C : gg);
     if (A.aim) {
-        k_candidates_simple<true><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates_simple<true, 1><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates_simple<true, 2><<<nbs, CS_THREADS, 0, st>>>(A);
         k_candidates<ORT_ARITH_FAST, true><<<nbg, ORT_TILE, 0, st>>>(A);
     } else {
-        k_candidates_simple<false><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates_simple<false, 1><<<nbs, CS_THREADS, 0, st>>>(A);
+        k_candidates_simple<false, 2><<<nbs, CS_THREADS, 0, st>>>(A);
         k_candidates<ORT_ARITH_FAST, false><<<nbg, ORT_TILE, 0, st>>>(A);
     }
     return cudaGetLastError();

@@ -911,12 +911,12 @@ int ort_trace3d_candidates_dev(ort_ctx* ctx, int rows, int64_t C, const double* 
     A.stop = stop; A.a_stop = a_stop; A.a_stop2 = a_stop * a_stop;
     A.u = field->u; A.v = field->v; A.h_prime = field->h_prime; A.out = d_out;
     ScratchScope scratch(ctx, (cudaStream_t)stream);
-    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (2 + 2 * (size_t)C), A.lists);
+    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (3 + 3 * (size_t)C), A.lists);
     {
         ProfScope prof(ctx, (cudaStream_t)stream);
         CK(launch_candidates(A, arith, (cudaStream_t)stream, ctx->sm_count));
     }
-    if (C > 0) ctx->launches += A.lists ? 3 : 1;
+    if (C > 0) ctx->launches += A.lists ? 4 : 1;
     return ORT_OK;
 }
 
@@ -1068,12 +1068,12 @@ int ort_trace3d_candidates_aimed_dev(ort_ctx* ctx, int rows, int64_t C, const do
     A.v = 0.0;                                       // V = 0 (meridional field, src/PupilSampling.jl:98)
     A.out = d_out;
     ScratchScope scratch(ctx, (cudaStream_t)stream);
-    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (2 + 2 * (size_t)C), A.lists);
+    if (arith == ORT_ARITH_FAST && C > 0) ENSURE(SL_CLIST, sizeof(int) * (3 + 3 * (size_t)C), A.lists);
     {
         ProfScope prof(ctx, (cudaStream_t)stream);
         CK(launch_candidates(A, arith, (cudaStream_t)stream, ctx->sm_count));
     }
-    if (C > 0) ctx->launches += A.lists ? 3 : 1;
+    if (C > 0) ctx->launches += A.lists ? 4 : 1;
     return ORT_OK;
 }
 
