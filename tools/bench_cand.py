@@ -51,4 +51,9 @@ d_M = torch.from_numpy(mixed).to(dev)
 ctx.aim_candidates_dev(8, C, d_M.data_ptr(), Pq["a"], Pq["h"], 0.7, d_aim.data_ptr(), aspheric=True, stream=st)
 ms = timed(lambda: ctx.trace3d_candidates_aimed_dev(8, C, d_M.data_ptr(), d_aim.data_ptr(), 64, 64, d_out.data_ptr(), arith=ort.FAST, stream=st))
 out["sweep_aimed_quarter_conic"] = {"ms": ms, "fp64_frac": rays * 513 / ms / 1e9 / peak}
+# the bit-identical arithmetic on the first 8192 candidates of the population (one CTA per candidate, STRICT)
+Cs = min(C, 8192)
+ctx.aim_candidates_dev(8, Cs, d_R.data_ptr(), Pq["a"], Pq["h"], 0.7, d_aim.data_ptr(), stream=st)
+ms = timed(lambda: ctx.trace3d_candidates_aimed_dev(8, Cs, d_R.data_ptr(), d_aim.data_ptr(), 64, 64, d_out.data_ptr(), arith=ort.STRICT, stream=st), reps=5, warm=2)
+out["sweep_aimed_strict_8192"] = {"ms": ms, "fp64_frac": Cs * 4096 * 513 / ms / 1e9 / peak}
 print(json.dumps(out))
