@@ -951,6 +951,10 @@ __global__ void __launch_bounds__(256) k_selftest_exact(long long iters, unsigne
         const double q = xdiv(a, b, bad), q0 = __ddiv_rn(a, b);
         c[0]++; c[1] += bad; c[2] += (!bad && __double_as_longlong(q) != __double_as_longlong(q0)) ? 1 : 0;
         if (cls == 1) c[6] += bad;
+        int bad0 = 0;                                            // the zero-numerator form: (+-0) / normal b kept as +-0
+        const double qz = xdiv0(a, b, bad0);
+        c[2] += (!bad0 && __double_as_longlong(qz) != __double_as_longlong(q0)) ? 1 : 0;
+        if (a == 0.0 && !bad0) c[0]++;                           // (counted twice: zero numerators that stay on the fast path)
         const double aa = (cls == 1) ? fabs(a) : a;
         int bad2 = 0;
         const double g = xsqrt(aa, bad2), g0 = __dsqrt_rn(aa);
