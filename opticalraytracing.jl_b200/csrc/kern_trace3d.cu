@@ -44,23 +44,32 @@ __device__ __forceinline__ double strict_opl_close(const RayS& r, const ort_fiel
     return SA(r.opl, SM(nlast, tau));
 }
 
+template <bool EXT, class SurfArray, bool POLY, bool XF>
+__device__ __forceinline__ Hit trace_strict_impl(const SurfArray& S, int nsurf, int stop, double y, double x, double u, double v,
+                                                 const ort_field* fld, double n0, double nlast, bool vignette, const double* poly,
+                                                 int npoly, int* bad)
+{
+    RayS r;
+    strict_init<XF>(r, y, x, u, v);
+    if (EXT) r.opl = strict_opl_start(r, fld->mode, n0, y, x, fld->z0);
+    Hit h; h.xs = h.ys = CUDART_NAN; h.opl = 0.0;
+    for (int i = 0; i < nsurf; i++) {
+        strict_step<EXT, POLY, XF>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly);
+        if (i == stop - 1) { h.xs = r.x; h.ys = r.y; }
+    }
+    h.xf = r.x; h.yf = r.y; h.flags = r.flags;
+    if (EXT) h.opl = strict_opl_close(r, *fld, nlast);
+    if (XF) *bad = r.bad;
+    return h;
+}
+
 template <bool EXT, class SurfArray, bool POLY = false>
 __device__ __forceinline__ Hit trace_strict(const SurfArray& S, int nsurf, int stop,
                                             double y, double x, double u, double v,
                                             const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
                                             bool vignette = false, const double* poly = nullptr, int npoly = 0)
 {
-    RayS r;
-    strict_init(r, y, x, u, v);
-    if (EXT) r.opl = strict_opl_start(r, fld->mode, n0, y, x, fld->z0);
-    Hit h; h.xs = h.ys = CUDART_NAN; h.opl = 0.0;
-    for (int i = 0; i < nsurf; i++) {
-        strict_step<EXT, POLY>(S[i], r, vignette, (POLY && poly) ? poly + (size_t)i * npoly : nullptr, npoly);
-        if (i == stop - 1) { h.xs = r.x; h.ys = r.y; }
-    }
-    h.xf = r.x; h.yf = r.y; h.flags = r.flags;
-    if (EXT) h.opl = strict_opl_close(r, *fld, nlast);
-    return h;
+    return trace_strict_impl<EXT, SurfArray, POLY, false>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette, poly, npoly, nullptr);
 }
 
 // the strict re-trace of guard-band rays lives out of line so it does not bloat the hot loop
@@ -71,6 +80,19 @@ __device__ __noinline__ Hit trace_strict_cold(const SurfArray& S, int nsurf, int
                                               bool vignette = false, const double* poly = nullptr, int npoly = 0)
 {
     return trace_strict<EXT, SurfArray, POLY>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette, poly, npoly);
+}
+
+// STRICT with the deferred slow paths (xdiv / xsqrt, ort_internal.cuh): a flagged ray is traced again with the intrinsics
+template <bool EXT, class SurfArray, bool POLY = false>
+__device__ __forceinline__ Hit trace_strict_xf(const SurfArray& S, int nsurf, int stop,
+                                               double y, double x, double u, double v,
+                                               const ort_field* fld = nullptr, double n0 = 1.0, double nlast = 1.0,
+                                               bool vignette = false, const double* poly = nullptr, int npoly = 0)
+{
+    int bad = 0;
+    const Hit h = trace_strict_impl<EXT, SurfArray, POLY, true>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette, poly, npoly, &bad);
+    if (bad) return trace_strict_cold<EXT, SurfArray, POLY>(S, nsurf, stop, y, x, u, v, fld, n0, nlast, vignette, poly, npoly);
+    return h;
 }
 
 // sign bit set iff a is NaN or +-Inf (exponent field all ones)
@@ -747,7 +769,7 @@ k_candidates(CandArgs A)
             }
             if (ARITH == ORT_ARITH_STRICT || (amb[j] < 0 && valid[j])) {
                 const double fu = CAND_PAR(7, A.u);
-                h[j] = (ARITH == ORT_ARITH_STRICT) ? trace_strict<false>(s_surf, nsurf, stop, y0[j], x0[j], fu, A.v)
+                h[j] = (ARITH == ORT_ARITH_STRICT) ? trace_strict_xf<false>(s_surf, nsurf, stop, y0[j], x0[j], fu, A.v)
                                                    : trace_strict_cold<false>(s_surf, nsurf, stop, y0[j], x0[j], fu, A.v);
                 ri = jl_hypot(h[j].xs, h[j].ys);
                 clip = ri > CAND_PAR(5, A.a_stop);
