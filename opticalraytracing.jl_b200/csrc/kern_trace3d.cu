@@ -994,7 +994,7 @@ __global__ void __launch_bounds__(128) k_aim_edges(int rows, long long C, const 
     double* o = rec + 16 + 4 * e;
     if (!good) { if (e == 0) { rec[14] = 0.0; rec[15] = 0.0; } o[0] = o[1] = o[2] = o[3] = CUDART_NAN; return; }
     CandSurfGen gen; gen.Rc = RtnK + (shared ? 0 : (size_t)c * 4 * rows); gen.rows = rows; gen.focus = rec[5];
-    const Hit h = trace_strict<false>(gen, rows, stop, rec[e], 0.0, rec[3], 0.0);
+    const Hit h = trace_strict_xf<false>(gen, rows, stop, rec[e], 0.0, rec[3], 0.0);
     const double ri = jl_hypot(h.xs, h.ys);
     const bool drop = ri > rec[7] || is_nan_bits(h.xf) || is_nan_bits(h.yf);
     o[0] = drop ? 0.0 : 1.0; o[1] = h.xf; o[2] = h.yf - rec[4]; o[3] = ri * ri;
